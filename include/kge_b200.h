@@ -1,0 +1,186 @@
+/*
+ * kge_b200.h -- C ABI of the B200-native KG-embedding scoring / link-prediction
+ * ranking engine (libkge_b200.so).
+ *
+ * The reference (torchkge @ 3adb934, v0.17.7) has no FFI of its own: its hot path is
+ * Python over ATen.  Every entry point below therefore names the reference Python
+ * symbol (file:line under /root/reference) whose tensor-op body it replaces; the
+ * Python shim in torchkge_b200/ keeps the reference's class/method signatures and
+ * calls these through ctypes (see INTEGRATION.md for the binding).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All `const float*`/`int64_t*`
+ *     pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - the caller owns every buffer (the shim allocates them as torch tensors);
+ *     the library allocates nothing persistent.
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and
+ *     returns without synchronising.
+ *   - return value: 0 = ok, nonzero = error code (KGE_ERR_*); kge_last_error()
+ *     returns a thread-local message.  Nothing throws or aborts.
+ *   - all embeddings are fp32 row-major with leading dimension = dim; all entity /
+ *     relation indices are int64; rank counters are int32 on device and widened to
+ *     int64 by kge_finalize_ranks().
+ *
+ * Arithmetic contract ("ATen order"): for one (query, candidate) pair the score is
+ * evaluated with exactly the fp32 operation sequence torchkge executes on its CPU
+ * path through ATen 2.11 (separately rounded mul/add, 8-lane vector accumulation,
+ * cascade summation, sqrt-then-square for L2) -- see DESIGN.md "Reduction
+ * schedules".  The sequence depends only on (model, side, dim), never on tile /
+ * thread / shard position, so equal inputs give bit-equal scores everywhere and
+ * ranks equal the reference's CPU ranks bit for bit.
+ */
+#ifndef KGE_B200_H
+#define KGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGE_ABI_VERSION 1
+
+/* error codes */
+#define KGE_OK 0
+#define KGE_ERR_ARG 1     /* bad argument (null pointer, unsupported dim, ...) */
+#define KGE_ERR_CUDA 2    /* a CUDA runtime call failed; see kge_last_error() */
+#define KGE_ERR_UNSUPPORTED 3
+
+/* Scoring models on the path. */
+typedef enum {
+  KGE_TRANSE_L1 = 0, /* torchkge/models/translation.py:18  + utils/dissimilarities.py:11 */
+  KGE_TRANSE_L2 = 1, /* torchkge/models/translation.py:18  + utils/dissimilarities.py:19 */
+  KGE_DISTMULT = 2,  /* torchkge/models/bilinear.py:146 */
+  KGE_RESCAL = 3,    /* torchkge/models/bilinear.py:14 */
+  KGE_COMPLEX = 4,   /* torchkge/models/bilinear.py:414 */
+  KGE_ROTATE = 5     /* not in the reference; oracle/rotate restatement (Sun et al. 2019) */
+} kge_model_t;
+
+/* Which element of the triple is being completed. */
+typedef enum {
+  KGE_SIDE_TAIL = 0, /* (h, r, ?)  evaluation.py:292 */
+  KGE_SIDE_HEAD = 1  /* (?, r, t)  evaluation.py:297 */
+} kge_side_t;
+
+/* Geometry of the packed layouts, fixed at build time; exported so that callers can
+ * size buffers.  A "candidate tile" is KGE_TILE_C consecutive entity rows, a "query
+ * tile" is KGE_TILE_Q consecutive queries. */
+#define KGE_TILE_C 128
+#define KGE_TILE_Q 64
+
+int kge_abi_version(void);
+const char* kge_last_error(void);
+
+/* Number of fp32 planes per entity row / per query for a model:
+ * candidates: 1 (TransE, DistMult, RESCAL) or 2 (ComplEx, RotatE: re, im);
+ * queries: 1, or 2 for TransE head side (r and t stay separate, interfaces.py:256-260)
+ * and for ComplEx / RotatE. */
+int kge_cand_planes(int model);
+int kge_query_planes(int model, int side);
+
+/* ---- reduction schedule (host only; no GPU needed) ------------------------------
+ * Fills perm_host[dim] (schedule position -> original embedding index) and
+ * code_host[dim] (combine micro-ops executed after each position) for the reduction
+ * the reference performs for `model`: sequential (L1 norm), 8-lane norm (L2), or
+ * ATen's cascade sum (bilinear models / RotatE).  Exposed for CPU tests, which
+ * replay the schedule in numpy and compare with ATen bit for bit. */
+int kge_build_schedule(int model, int dim, int32_t* perm_host, uint8_t* code_host);
+
+/* ---- table packing ---------------------------------------------------------------
+ * Re-lays an entity table shard (rows [0, n_rows) of ent0 / ent1, each row-major
+ * [n_rows][dim]; ent1 only for 2-plane models) into the scan layout
+ *   packed[ctile][pos][plane][KGE_TILE_C]      (pos = schedule position, 0..dim-1)
+ * so that one pipeline stage of the scan is a single contiguous bulk copy.
+ * Replaces the zero-copy `expand` of ent_emb.weight in inference_prepare_candidates
+ * (translation.py:105-125, bilinear.py:123-143, 247-267, 530-556). */
+size_t kge_packed_table_floats(int model, int64_t n_rows, int dim);
+int kge_pack_table(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
+                   float* packed, void* stream);
+
+/* ---- query rows --------------------------------------------------------------------
+ * out[i][plane][dim] = ent_plane[idx[i] - ent_lo]  if ent_lo <= idx[i] < ent_lo+n_rows
+ *                      else 0                                   (i < n)
+ * (the Embedding lookups of inference_prepare_candidates).  With a range-partitioned
+ * table each rank calls this on its shard and the shim sum-all-reduces `out`. */
+int kge_gather_rows(int model, const float* ent0, const float* ent1, int64_t ent_lo,
+                    int64_t n_rows, int dim, const int64_t* idx, int64_t n, float* out,
+                    void* stream);
+
+/* ---- link-prediction ranking: the hot path ---------------------------------------
+ * One call ranks n test triples on one side against the entity rows
+ * [ent_lo, ent_lo + n_rows) held by this GPU.  It fuses, without ever writing an
+ * (n, n_ent) score matrix:
+ *   inference_scoring_function   (interfaces.py:240-260, bilinear.py:98-121,
+ *                                 224-245, 501-528)
+ *   filter_scores / get_true_targets (utils/modeling.py:53-102)
+ *   get_rank                     (utils/operations.py:37-61)
+ * Results are ADDED into the int32 counters
+ *   raw_count[i]  += #{c in shard : s(i,c) >= s_true(i)}
+ *   filt_sub[i]   += #{c in shard, c in F(i)\{true} : s(i,c) >= s_true(i) and s_true(i) > -inf}
+ * so that rank_raw = sum over shards of raw_count and rank_filt = rank_raw - sum of
+ * filt_sub (one sum-all-reduce when sharded).
+ */
+typedef struct {
+  int32_t model; /* kge_model_t */
+  int32_t side;  /* kge_side_t */
+  int32_t dim;
+  int32_t reserved0;
+  int64_t n;      /* triples in this call */
+  int64_t n_ent;  /* global number of entities */
+  int64_t ent_lo; /* first global entity id held in `packed` / ent0 / ent1 */
+  int64_t n_rows; /* rows held */
+  const float* packed; /* kge_pack_table output for this shard */
+  const float* ent0;   /* row-major shard (used for the sparse filter pass) */
+  const float* ent1;   /* second plane or NULL */
+  const float* rel0;   /* relation table: rel_emb / re_rel_emb / rel_mat / phases */
+  const float* rel1;   /* im_rel_emb or NULL */
+  const float* hrows;  /* [n][cand_planes][dim] rows of the heads (kge_gather_rows) */
+  const float* trows;  /* [n][cand_planes][dim] rows of the tails */
+  const int64_t* r_idx;    /* [n] relation ids */
+  const int64_t* true_idx; /* [n] global id of the true entity on this side */
+  /* CSR of the filter sets, true entity already removed, quirks of
+   * get_true_targets already applied by the shim: */
+  const int64_t* filt_offs; /* [n+1] or NULL (no filtering) */
+  const int64_t* filt_ids;  /* [n_filt] global entity ids */
+  int64_t n_filt;           /* = filt_offs[n], known to the host */
+  int32_t* raw_count;       /* [n] += */
+  int32_t* filt_sub;        /* [n] += */
+  float* true_score;        /* [n] out (optional, may be NULL): s_true */
+  void* workspace;          /* kge_rank_workspace_bytes() bytes, 256-B aligned */
+  size_t workspace_bytes;
+  void* stream;
+} kge_rank_args_t;
+
+size_t kge_rank_workspace_bytes(int model, int side, int dim, int64_t n);
+int kge_rank_side(const kge_rank_args_t* args);
+
+/* ranks[i] = raw_count[i] (int32 -> int64); filt_ranks[i] = raw_count[i] - filt_sub[i]
+ * (evaluation.py:294-300 store int64). */
+int kge_finalize_ranks(const int32_t* raw_count, const int32_t* filt_sub, int64_t n,
+                       int64_t* ranks, int64_t* filt_ranks, void* stream);
+
+/* ---- dense scores (API parity, not the hot path) ----------------------------------
+ * scores[i][c] for all c in the shard, row-major (n, n_rows): what
+ * inference_scoring_function returns.  Same arithmetic as kge_rank_side. */
+typedef struct {
+  int32_t model, side, dim, reserved0;
+  int64_t n;
+  int64_t n_rows;
+  const float* packed;
+  const float* rel0;
+  const float* rel1;
+  const float* hrows;
+  const float* trows;
+  const int64_t* r_idx;
+  float* scores; /* [n][n_rows] */
+  void* workspace;
+  size_t workspace_bytes;
+  void* stream;
+} kge_score_all_args_t;
+int kge_score_all(const kge_score_all_args_t* args);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGE_B200_H */

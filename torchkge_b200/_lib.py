@@ -1,0 +1,119 @@
+"""ctypes binding of libkge_b200.so (C ABI declared in include/kge_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or a call fails,
+``KgeLibraryError`` is raised.  Host-only entry points (schedule construction, size
+queries) work without a GPU and are what the ``-m "not gpu"`` tests exercise.
+"""
+import ctypes
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libkge_b200.so")
+
+# kge_model_t / kge_side_t (include/kge_b200.h)
+TRANSE_L1, TRANSE_L2, DISTMULT, RESCAL, COMPLEX, ROTATE = range(6)
+SIDE_TAIL, SIDE_HEAD = 0, 1
+TILE_C, TILE_Q = 128, 64
+ABI_VERSION = 1
+
+MODEL_NAMES = {TRANSE_L1: "TransE-L1", TRANSE_L2: "TransE-L2", DISTMULT: "DistMult",
+               RESCAL: "RESCAL", COMPLEX: "ComplEx", ROTATE: "RotatE"}
+
+
+class KgeLibraryError(RuntimeError):
+    """libkge_b200.so is missing, stale or returned an error code."""
+
+
+_c = ctypes
+_p = ctypes.c_void_p
+
+
+class RankArgs(ctypes.Structure):
+    """kge_rank_args_t"""
+    _fields_ = [
+        ("model", _c.c_int32), ("side", _c.c_int32), ("dim", _c.c_int32), ("reserved0", _c.c_int32),
+        ("n", _c.c_int64), ("n_ent", _c.c_int64), ("ent_lo", _c.c_int64), ("n_rows", _c.c_int64),
+        ("packed", _p), ("ent0", _p), ("ent1", _p), ("rel0", _p), ("rel1", _p),
+        ("hrows", _p), ("trows", _p), ("r_idx", _p), ("true_idx", _p),
+        ("filt_offs", _p), ("filt_ids", _p), ("n_filt", _c.c_int64),
+        ("raw_count", _p), ("filt_sub", _p), ("true_score", _p),
+        ("workspace", _p), ("workspace_bytes", _c.c_size_t), ("stream", _p),
+    ]
+
+
+class ScoreAllArgs(ctypes.Structure):
+    """kge_score_all_args_t"""
+    _fields_ = [
+        ("model", _c.c_int32), ("side", _c.c_int32), ("dim", _c.c_int32), ("reserved0", _c.c_int32),
+        ("n", _c.c_int64), ("n_rows", _c.c_int64),
+        ("packed", _p), ("rel0", _p), ("rel1", _p), ("hrows", _p), ("trows", _p), ("r_idx", _p),
+        ("scores", _p), ("workspace", _p), ("workspace_bytes", _c.c_size_t), ("stream", _p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/kge_b200.h declares
+SIGNATURES = {
+    "kge_abi_version": (_c.c_int, []),
+    "kge_last_error": (_c.c_char_p, []),
+    "kge_cand_planes": (_c.c_int, [_c.c_int]),
+    "kge_query_planes": (_c.c_int, [_c.c_int, _c.c_int]),
+    "kge_build_schedule": (_c.c_int, [_c.c_int, _c.c_int, _p, _p]),
+    "kge_packed_table_floats": (_c.c_size_t, [_c.c_int, _c.c_int64, _c.c_int]),
+    "kge_pack_table": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _c.c_int, _p, _p]),
+    "kge_gather_rows": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _c.c_int64, _c.c_int, _p,
+                                   _c.c_int64, _p, _p]),
+    "kge_rank_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int64]),
+    "kge_rank_side": (_c.c_int, [_c.POINTER(RankArgs)]),
+    "kge_finalize_ranks": (_c.c_int, [_p, _p, _c.c_int64, _p, _p, _p]),
+    "kge_score_all": (_c.c_int, [_c.POINTER(ScoreAllArgs)]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises KgeLibraryError if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise KgeLibraryError(
+                "%s not found: build it with `python -m torchkge_b200._build` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        try:
+            lib = ctypes.CDLL(LIB_PATH)
+        except OSError as e:  # missing libcudart etc.
+            raise KgeLibraryError("cannot load %s: %s" % (LIB_PATH, e)) from e
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                raise KgeLibraryError("%s does not export %s (stale build?)" % (LIB_PATH, name)) from e
+            fn.restype = res
+            fn.argtypes = args
+        if lib.kge_abi_version() != ABI_VERSION:
+            raise KgeLibraryError("ABI mismatch: library %d, binding %d"
+                                  % (lib.kge_abi_version(), ABI_VERSION))
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().kge_last_error().decode(errors="replace")
+        raise KgeLibraryError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def build_schedule(model, dim):
+    """(perm, code) numpy arrays of the reduction schedule for (model, dim) -- host only."""
+    import numpy as np
+    lib = load()
+    perm = np.zeros(dim, dtype=np.int32)
+    code = np.zeros(dim, dtype=np.uint8)
+    check(lib.kge_build_schedule(model, dim, perm.ctypes.data, code.ctypes.data), "kge_build_schedule")
+    return perm, code

@@ -1,0 +1,298 @@
+// extern "C" entry points of libkge_b200.so (declared in include/kge_b200.h).
+#include <mutex>
+#include <map>
+#include <memory>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/kge_b200.h"
+#include "kernels.h"
+#include "schedule.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+
+int fail_cuda(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return KGE_ERR_CUDA;
+}
+
+#define KGE_CUDA_TRY(expr, where)                      \
+  do {                                                 \
+    cudaError_t _e = (expr);                           \
+    if (_e != cudaSuccess) return fail_cuda(_e, where); \
+  } while (0)
+
+struct HostSchedule {
+  kge::Schedule s;
+  std::vector<int32_t> inv_perm;
+};
+
+// Schedules depend on (reduce kind, dim) only; building one is O(dim).  Cached per process.
+const HostSchedule* get_schedule(int model, int dim) {
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, std::unique_ptr<HostSchedule>> cache;
+  const int kind = kge::reduce_kind_for_model(model);
+  if (kind < 0) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(kind, dim);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second.get();
+  auto hs = std::make_unique<HostSchedule>();
+  if (!kge::build_schedule(kind, dim, &hs->s)) return nullptr;
+  hs->inv_perm.assign(dim, 0);
+  for (int pos = 0; pos < dim; ++pos) hs->inv_perm[hs->s.perm[pos]] = pos;
+  const HostSchedule* out = hs.get();
+  cache[key] = std::move(hs);
+  return out;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Workspace carve-up shared by kge_rank_side and kge_score_all.
+struct Workspace {
+  float* qplain;
+  float* qpacked;
+  float* s_true;
+  int32_t* perm;
+  uint8_t* code;
+  size_t bytes;
+};
+
+Workspace carve(void* base, int qw, int dim, int64_t n) {
+  const int64_t n_qt = (n + kge::TILE_Q - 1) / kge::TILE_Q;
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  w.qplain = static_cast<float*>(take((size_t)n * qw * dim * sizeof(float)));
+  w.qpacked = static_cast<float*>(take((size_t)n_qt * dim * qw * kge::TILE_Q * sizeof(float)));
+  w.s_true = static_cast<float*>(take((size_t)n_qt * kge::TILE_Q * sizeof(float)));
+  w.perm = static_cast<int32_t*>(take((size_t)dim * sizeof(int32_t)));
+  w.code = static_cast<uint8_t*>(take((size_t)dim));
+  w.bytes = off;
+  return w;
+}
+
+// Steps shared by ranking and dense scoring: upload the schedule, build the query vectors.
+int prepare_queries(int model, int side, int dim, int64_t n, const float* hrows,
+                    const float* trows, const float* rel0, const float* rel1,
+                    const int64_t* r_idx, const HostSchedule* hs, const Workspace& w, int el,
+                    cudaStream_t stream) {
+  KGE_CUDA_TRY(cudaMemcpyAsync(w.perm, hs->s.perm.data(), (size_t)dim * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, stream),
+               "upload schedule perm");
+  KGE_CUDA_TRY(cudaMemcpyAsync(w.code, hs->s.code.data(), (size_t)dim, cudaMemcpyHostToDevice,
+                               stream),
+               "upload schedule code");
+  KGE_CUDA_TRY(kge::launch_prep_queries(model, side, dim, n, hrows, trows, rel0, rel1, r_idx,
+                                        w.qplain, stream),
+               "prep_queries");
+  KGE_CUDA_TRY(kge::launch_pack_queries(w.qplain, kge::elem_qw(el), dim, n, w.perm, w.qpacked,
+                                        stream),
+               "pack_queries");
+  return KGE_OK;
+}
+
+bool model_needs_rel1(int model) { return model == KGE_COMPLEX || model == KGE_ROTATE; }
+
+}  // namespace
+
+extern "C" {
+
+int kge_abi_version(void) { return KGE_ABI_VERSION; }
+
+const char* kge_last_error(void) { return g_err; }
+
+int kge_cand_planes(int model) {
+  const int el = kge::elem_kind_for(model, KGE_SIDE_TAIL);
+  return el < 0 ? 0 : kge::elem_cw(el);
+}
+
+int kge_query_planes(int model, int side) {
+  const int el = kge::elem_kind_for(model, side);
+  return el < 0 ? 0 : kge::elem_qw(el);
+}
+
+int kge_build_schedule(int model, int dim, int32_t* perm_host, uint8_t* code_host) {
+  if (!perm_host || !code_host) return fail(KGE_ERR_ARG, "kge_build_schedule: null output");
+  const HostSchedule* hs = get_schedule(model, dim);
+  if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_build_schedule: unsupported model or dim");
+  memcpy(perm_host, hs->s.perm.data(), (size_t)dim * sizeof(int32_t));
+  memcpy(code_host, hs->s.code.data(), (size_t)dim);
+  return KGE_OK;
+}
+
+size_t kge_packed_table_floats(int model, int64_t n_rows, int dim) {
+  const int planes = kge_cand_planes(model);
+  if (planes == 0 || n_rows < 0 || dim < 1) return 0;
+  const int64_t n_ct = (n_rows + kge::TILE_C - 1) / kge::TILE_C;
+  return (size_t)n_ct * dim * planes * kge::TILE_C;
+}
+
+int kge_pack_table(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
+                   float* packed, void* stream) {
+  const int planes = kge_cand_planes(model);
+  if (planes == 0) return fail(KGE_ERR_ARG, "kge_pack_table: unknown model");
+  if (!ent0 || !packed || (planes == 2 && !ent1))
+    return fail(KGE_ERR_ARG, "kge_pack_table: null table pointer");
+  const HostSchedule* hs = get_schedule(model, dim);
+  if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_pack_table: unsupported dim");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // inv_perm is staged in the tail of the packed buffer?  No: it would be overwritten.  Use a
+  // small stream-ordered allocation instead (freed on the same stream).
+  int32_t* d_inv = nullptr;
+  KGE_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_inv), (size_t)dim * sizeof(int32_t), st),
+               "pack_table: cudaMallocAsync");
+  cudaError_t e = cudaMemcpyAsync(d_inv, hs->inv_perm.data(), (size_t)dim * sizeof(int32_t),
+                                  cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    e = kge::launch_pack_table(ent0, ent1, planes, n_rows, dim, d_inv, packed, st);
+  cudaError_t e2 = cudaFreeAsync(d_inv, st);
+  if (e != cudaSuccess) return fail_cuda(e, "pack_table");
+  if (e2 != cudaSuccess) return fail_cuda(e2, "pack_table: cudaFreeAsync");
+  return KGE_OK;
+}
+
+int kge_gather_rows(int model, const float* ent0, const float* ent1, int64_t ent_lo,
+                    int64_t n_rows, int dim, const int64_t* idx, int64_t n, float* out,
+                    void* stream) {
+  const int planes = kge_cand_planes(model);
+  if (planes == 0) return fail(KGE_ERR_ARG, "kge_gather_rows: unknown model");
+  if (n == 0) return KGE_OK;
+  if (!ent0 || !idx || !out || (planes == 2 && !ent1))
+    return fail(KGE_ERR_ARG, "kge_gather_rows: null pointer");
+  KGE_CUDA_TRY(kge::launch_gather_rows(ent0, ent1, planes, ent_lo, n_rows, dim, idx, n, out,
+                                       static_cast<cudaStream_t>(stream)),
+               "gather_rows");
+  return KGE_OK;
+}
+
+size_t kge_rank_workspace_bytes(int model, int side, int dim, int64_t n) {
+  const int el = kge::elem_kind_for(model, side);
+  if (el < 0 || dim < 1 || n < 0) return 0;
+  return carve(nullptr, kge::elem_qw(el), dim, n).bytes;
+}
+
+int kge_rank_side(const kge_rank_args_t* a) {
+  if (!a) return fail(KGE_ERR_ARG, "kge_rank_side: null args");
+  const int el = kge::elem_kind_for(a->model, a->side);
+  if (el < 0) return fail(KGE_ERR_ARG, "kge_rank_side: unknown model/side");
+  if (a->n == 0) return KGE_OK;
+  if (a->n < 0 || a->n_rows < 0 || a->dim < 1) return fail(KGE_ERR_ARG, "kge_rank_side: bad sizes");
+  if (!a->packed || !a->ent0 || !a->rel0 || !a->hrows || !a->trows || !a->r_idx ||
+      !a->raw_count || !a->workspace)
+    return fail(KGE_ERR_ARG, "kge_rank_side: null pointer");
+  if (kge::elem_cw(el) == 2 && !a->ent1) return fail(KGE_ERR_ARG, "kge_rank_side: ent1 required");
+  if (model_needs_rel1(a->model) && !a->rel1)
+    return fail(KGE_ERR_ARG, "kge_rank_side: rel1 required");
+  if (a->filt_offs && (!a->filt_ids || !a->filt_sub) && a->n_filt > 0)
+    return fail(KGE_ERR_ARG, "kge_rank_side: filter arrays incomplete");
+  const HostSchedule* hs = get_schedule(a->model, a->dim);
+  if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_rank_side: unsupported dim");
+  const int qw = kge::elem_qw(el);
+  Workspace w = carve(a->workspace, qw, a->dim, a->n);
+  if (w.bytes > a->workspace_bytes) return fail(KGE_ERR_ARG, "kge_rank_side: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  const bool casc = hs->s.has_cascade;
+
+  int rc = prepare_queries(a->model, a->side, a->dim, a->n, a->hrows, a->trows, a->rel0, a->rel1,
+                           a->r_idx, hs, w, el, st);
+  if (rc != KGE_OK) return rc;
+
+  // true scores: the true entity's row is the gathered tail (tail side) / head (head side) row
+  const int64_t n_qt = (a->n + kge::TILE_Q - 1) / kge::TILE_Q;
+  const float nan_v = __builtin_nanf("");
+  KGE_CUDA_TRY(kge::launch_fill_f32(w.s_true + a->n, nan_v, n_qt * kge::TILE_Q - a->n, st),
+               "fill s_true pad");
+  const float* true_rows = a->side == KGE_SIDE_TAIL ? a->trows : a->hrows;
+  KGE_CUDA_TRY(kge::launch_true_scores(el, casc, a->dim, a->n, w.qplain, true_rows, w.perm, w.code,
+                                       w.s_true, st),
+               "true_scores");
+  if (a->true_score)
+    KGE_CUDA_TRY(cudaMemcpyAsync(a->true_score, w.s_true, (size_t)a->n * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st),
+                 "copy true_score");
+
+  if (a->n_rows > 0) {
+    kge::ScanParams p;
+    p.packed = a->packed;
+    p.qpacked = w.qpacked;
+    p.s_true = w.s_true;
+    p.code = w.code;
+    p.counts = a->raw_count;
+    p.scores = nullptr;
+    p.dim = a->dim;
+    p.n_q = a->n;
+    p.n_rows = a->n_rows;
+    p.n_ct = (a->n_rows + kge::TILE_C - 1) / kge::TILE_C;
+    p.n_qt = n_qt;
+    KGE_CUDA_TRY(kge::launch_scan(el, casc, p, st), "rank scan");
+
+    if (a->filt_offs && a->n_filt > 0)
+      KGE_CUDA_TRY(kge::launch_filter(el, casc, a->dim, a->n, a->n_filt, w.qplain, a->ent0, a->ent1,
+                                      a->ent_lo, a->n_rows, a->filt_offs, a->filt_ids, w.perm,
+                                      w.code, w.s_true, a->filt_sub, st),
+                   "filter pass");
+  }
+  return KGE_OK;
+}
+
+int kge_finalize_ranks(const int32_t* raw_count, const int32_t* filt_sub, int64_t n,
+                       int64_t* ranks, int64_t* filt_ranks, void* stream) {
+  if (n == 0) return KGE_OK;
+  if (!raw_count || !filt_sub || !ranks || !filt_ranks)
+    return fail(KGE_ERR_ARG, "kge_finalize_ranks: null pointer");
+  KGE_CUDA_TRY(kge::launch_finalize(raw_count, filt_sub, n, ranks, filt_ranks,
+                                    static_cast<cudaStream_t>(stream)),
+               "finalize");
+  return KGE_OK;
+}
+
+int kge_score_all(const kge_score_all_args_t* a) {
+  if (!a) return fail(KGE_ERR_ARG, "kge_score_all: null args");
+  const int el = kge::elem_kind_for(a->model, a->side);
+  if (el < 0) return fail(KGE_ERR_ARG, "kge_score_all: unknown model/side");
+  if (a->n == 0 || a->n_rows == 0) return KGE_OK;
+  if (!a->packed || !a->rel0 || !a->hrows || !a->trows || !a->r_idx || !a->scores ||
+      !a->workspace)
+    return fail(KGE_ERR_ARG, "kge_score_all: null pointer");
+  if (model_needs_rel1(a->model) && !a->rel1)
+    return fail(KGE_ERR_ARG, "kge_score_all: rel1 required");
+  const HostSchedule* hs = get_schedule(a->model, a->dim);
+  if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_score_all: unsupported dim");
+  const int qw = kge::elem_qw(el);
+  Workspace w = carve(a->workspace, qw, a->dim, a->n);
+  if (w.bytes > a->workspace_bytes) return fail(KGE_ERR_ARG, "kge_score_all: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  int rc = prepare_queries(a->model, a->side, a->dim, a->n, a->hrows, a->trows, a->rel0, a->rel1,
+                           a->r_idx, hs, w, el, st);
+  if (rc != KGE_OK) return rc;
+  const int64_t n_qt = (a->n + kge::TILE_Q - 1) / kge::TILE_Q;
+  KGE_CUDA_TRY(kge::launch_fill_f32(w.s_true, 0.f, n_qt * kge::TILE_Q, st), "fill s_true");
+  kge::ScanParams p;
+  p.packed = a->packed;
+  p.qpacked = w.qpacked;
+  p.s_true = w.s_true;
+  p.code = w.code;
+  p.counts = nullptr;
+  p.scores = a->scores;
+  p.dim = a->dim;
+  p.n_q = a->n;
+  p.n_rows = a->n_rows;
+  p.n_ct = (a->n_rows + kge::TILE_C - 1) / kge::TILE_C;
+  p.n_qt = n_qt;
+  KGE_CUDA_TRY(kge::launch_scan(el, hs->s.has_cascade, p, st), "score scan");
+  return KGE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+// Internal launch interface between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kge_b200.h"
+#include "reduce.cuh"
+
+namespace kge {
+
+constexpr int TILE_Q = KGE_TILE_Q;  // queries per CTA tile
+constexpr int TILE_C = KGE_TILE_C;  // candidates per CTA tile
+
+// model/side -> element kind (-1 if unsupported)
+int elem_kind_for(int model, int side);
+int elem_qw(int el);
+int elem_cw(int el);
+
+struct ScanParams {
+  const float* packed;   // [n_ct][dim][CW][TILE_C]
+  const float* qpacked;  // [n_qt][dim][QW][TILE_Q]
+  const float* s_true;   // [n_qt*TILE_Q], NaN padded
+  const uint8_t* code;   // [dim]
+  int32_t* counts;       // [n_q] (+=) or nullptr
+  float* scores;         // [n_q][n_rows] or nullptr
+  int dim;
+  int64_t n_q;
+  int64_t n_rows;
+  int64_t n_ct;
+  int64_t n_qt;
+};
+
+// dense scan: counts[q] += #{c < n_rows : score(q,c) >= s_true[q]}  (or writes scores)
+cudaError_t launch_scan(int el, bool cascade, const ScanParams& p, cudaStream_t stream);
+
+// packed[ct][pos][plane][TILE_C] <- ent_plane[row][perm[pos]]
+cudaError_t launch_pack_table(const float* ent0, const float* ent1, int planes, int64_t n_rows,
+                              int dim, const int32_t* inv_perm, float* packed,
+                              cudaStream_t stream);
+
+cudaError_t launch_gather_rows(const float* ent0, const float* ent1, int planes, int64_t ent_lo,
+                               int64_t n_rows, int dim, const int64_t* idx, int64_t n,
+                               float* out, cudaStream_t stream);
+
+// qplain[i][plane][dim] from the gathered head/tail rows and the relation tables
+cudaError_t launch_prep_queries(int model, int side, int dim, int64_t n, const float* hrows,
+                                const float* trows, const float* rel0, const float* rel1,
+                                const int64_t* r_idx, float* qplain, cudaStream_t stream);
+
+// qpacked[qt][pos][plane][TILE_Q] <- qplain[i][plane][perm[pos]] (zero padded)
+cudaError_t launch_pack_queries(const float* qplain, int qw, int dim, int64_t n,
+                                const int32_t* perm, float* qpacked, cudaStream_t stream);
+
+cudaError_t launch_fill_f32(float* dst, float value, int64_t n, cudaStream_t stream);
+
+// s_true[i] = score(query i, rows[i])   (rows = [n][CW][dim])
+cudaError_t launch_true_scores(int el, bool cascade, int dim, int64_t n, const float* qplain,
+                               const float* rows, const int32_t* perm, const uint8_t* code,
+                               float* s_true, cudaStream_t stream);
+
+// filt_sub[q] += [s(q,c) >= s_true[q]] - [s_true[q] == -inf] for every CSR entry c of q that
+// lies in [ent_lo, ent_lo + n_rows)
+cudaError_t launch_filter(int el, bool cascade, int dim, int64_t n, int64_t n_filt,
+                          const float* qplain,
+                          const float* ent0, const float* ent1, int64_t ent_lo, int64_t n_rows,
+                          const int64_t* offs, const int64_t* ids, const int32_t* perm,
+                          const uint8_t* code, const float* s_true, int32_t* filt_sub,
+                          cudaStream_t stream);
+
+cudaError_t launch_finalize(const int32_t* raw, const int32_t* sub, int64_t n, int64_t* ranks,
+                            int64_t* filt_ranks, cudaStream_t stream);
+
+}  // namespace kge
