@@ -137,7 +137,7 @@ typedef struct {
   const float* rel1;   /* im_rel_emb or NULL */
   const float* hrows;  /* [n][cand_planes][dim] rows of the heads (kge_gather_rows) */
   const float* trows;  /* [n][cand_planes][dim] rows of the tails */
-  const int64_t* r_idx;    /* [n] relation ids */
+  const int64_t* r_idx;    /* [n] relation ids; NULL: rel0/rel1 hold one row per triple */
   const int64_t* true_idx; /* [n] global id of the true entity on this side */
   /* CSR of the filter sets, true entity already removed, quirks of
    * get_true_targets already applied by the shim: */
@@ -172,7 +172,7 @@ typedef struct {
   const float* rel1;
   const float* hrows;
   const float* trows;
-  const int64_t* r_idx;
+  const int64_t* r_idx; /* NULL: rel0/rel1 hold one row per triple (already gathered) */
   float* scores; /* [n][n_rows] */
   void* workspace;
   size_t workspace_bytes;

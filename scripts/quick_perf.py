@@ -1,0 +1,45 @@
+"""Scratch perf probe: time the rank scan for one side on random tables (device-resident)."""
+import sys, time
+import torch
+sys.path.insert(0, '.')
+from torchkge_b200 import _lib
+from torchkge_b200.engine import ModelSpec, CudaEngine
+
+def run(code, d, n_ent, n_q, n_rel=1000, reps=3):
+    dev = torch.device('cuda:0')
+    g = torch.Generator(device=dev).manual_seed(0)
+    planes = 2 if code in (_lib.COMPLEX, _lib.ROTATE) else 1
+    ent0 = torch.randn(n_ent, d, device=dev, generator=g) * 0.07
+    ent1 = torch.randn(n_ent, d, device=dev, generator=g) * 0.07 if planes == 2 else None
+    rel0 = torch.randn(n_rel, d, device=dev, generator=g) * 0.07
+    rel1 = torch.randn(n_rel, d, device=dev, generator=g) * 0.07 if planes == 2 else None
+    spec = ModelSpec(code, d, n_ent, n_rel, ent0, ent1, rel0, rel1)
+    eng = CudaEngine()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(); packed = eng.pack(spec); t1.record(); torch.cuda.synchronize()
+    pack_ms = t0.elapsed_time(t1)
+    h = torch.randint(0, n_ent, (n_q,), device=dev, generator=g)
+    t = torch.randint(0, n_ent, (n_q,), device=dev, generator=g)
+    r = torch.randint(0, n_rel, (n_q,), device=dev, generator=g)
+    hrows = eng.gather_rows(spec, h); trows = eng.gather_rows(spec, t)
+    out = {}
+    for side in (0, 1):
+        raw = torch.zeros(n_q, dtype=torch.int32, device=dev); sub = torch.zeros_like(raw)
+        best = 1e9
+        for _ in range(reps):
+            raw.zero_()
+            t0.record()
+            ws = eng.rank_side(spec, packed, side, hrows, trows, r, t if side == 0 else h, None, raw, sub)
+            t1.record(); torch.cuda.synchronize()
+            best = min(best, t0.elapsed_time(t1))
+        out[side] = best
+        assert int(raw.min()) >= 1, 'true entity must count itself'
+    pairs = n_q * n_ent
+    print('%-10s d=%4d nE=%8d nq=%6d pack %.2f ms | tail %.2f ms (%.2f Tpair-dim/s) head %.2f ms (%.2f) | mean raw rank %.0f' % (
+        _lib.MODEL_NAMES[code], d, n_ent, n_q, pack_ms, out[0], pairs * d / out[0] / 1e9, out[1], pairs * d / out[1] / 1e9, raw.float().mean().item()), flush=True)
+
+if __name__ == '__main__':
+    n_ent = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+    n_q = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+    for code, d in ((_lib.TRANSE_L2, 200), (_lib.TRANSE_L1, 200), (_lib.DISTMULT, 200), (_lib.COMPLEX, 400), (_lib.ROTATE, 1000 if n_ent <= 200000 else 200)):
+        run(code, d, n_ent, n_q)

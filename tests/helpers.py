@@ -1,0 +1,68 @@
+"""Shared test utilities: synthetic graphs, model <-> oracle parameter mapping."""
+import torch
+
+import torchkge_b200 as tk
+from oracle import kge_oracle as oracle
+
+KIND_TO_CLASS = {
+    "transe_l1": lambda d, ne, nr: tk.TransEModel(d, ne, nr, dissimilarity_type="L1"),
+    "transe_l2": lambda d, ne, nr: tk.TransEModel(d, ne, nr, dissimilarity_type="L2"),
+    "distmult": lambda d, ne, nr: tk.DistMultModel(d, ne, nr),
+    "rescal": lambda d, ne, nr: tk.RESCALModel(d, ne, nr),
+    "complex": lambda d, ne, nr: tk.ComplExModel(d, ne, nr),
+    "rotate": lambda d, ne, nr: tk.RotatEModel(d, ne, nr),
+}
+
+
+def make_model(kind, d, n_ent, n_rel, seed=0):
+    torch.manual_seed(seed)
+    return KIND_TO_CLASS[kind](d, n_ent, n_rel)
+
+
+def oracle_params(kind, model):
+    """CPU fp32 copies of the model's tables under the oracle's key names.
+
+    For RotatE call this AFTER moving the model to its final device: the (cos, sin) relation
+    planes are computed there, and libm results differ between CPU and GPU in the last ulp."""
+    g = lambda w: w.detach().cpu().clone()  # noqa: E731
+    if kind in ("transe_l1", "transe_l2", "distmult"):
+        return {"ent": g(model.ent_emb.weight), "rel": g(model.rel_emb.weight)}
+    if kind == "rescal":
+        return {"ent": g(model.ent_emb.weight), "rel_mat": g(model.rel_mat.weight)}
+    if kind == "complex":
+        return {"re_ent": g(model.re_ent_emb.weight), "im_ent": g(model.im_ent_emb.weight),
+                "re_rel": g(model.re_rel_emb.weight), "im_rel": g(model.im_rel_emb.weight)}
+    if kind == "rotate":
+        re_r, im_r = model.relation_planes()  # computed on the model's device: same bits for both
+        return {"re_ent": g(model.re_ent_emb.weight), "im_ent": g(model.im_ent_emb.weight),
+                "re_rel": g(re_r), "im_rel": g(im_r)}
+    raise ValueError(kind)
+
+
+def random_graph(n_ent, n_rel, n_facts, seed=0, skew=True):
+    """Deduplicated random facts; with skew, a few (h, r) / (t, r) keys get large filter sets."""
+    g = torch.Generator().manual_seed(seed)
+    if skew:
+        w_e = 1.0 / torch.arange(1, n_ent + 1, dtype=torch.float64) ** 0.8
+        w_r = 1.0 / torch.arange(1, n_rel + 1, dtype=torch.float64)
+        h = torch.multinomial(w_e, n_facts, replacement=True, generator=g)
+        t = torch.multinomial(w_e, n_facts, replacement=True, generator=g)
+        r = torch.multinomial(w_r, n_facts, replacement=True, generator=g)
+    else:
+        h = torch.randint(0, n_ent, (n_facts,), generator=g)
+        t = torch.randint(0, n_ent, (n_facts,), generator=g)
+        r = torch.randint(0, n_rel, (n_facts,), generator=g)
+    trip = torch.unique(torch.stack([h, t, r], 1), dim=0)
+    perm = torch.randperm(trip.shape[0], generator=g)
+    trip = trip[perm]
+    return trip[:, 0].contiguous(), trip[:, 1].contiguous(), trip[:, 2].contiguous()
+
+
+def make_kg(n_ent, n_rel, n_facts, n_test, seed=0):
+    """(test KnowledgeGraph carrying full-graph filter dicts, (dict_of_heads, dict_of_tails))."""
+    h, t, r = random_graph(n_ent, n_rel, n_facts, seed)
+    dh, dt = oracle.build_filter_dicts(h, t, r)
+    n_test = min(n_test, h.shape[0])
+    kg = tk.KnowledgeGraph(h[:n_test], t[:n_test], r[:n_test], n_ent, n_rel,
+                           dict_of_heads=dh, dict_of_tails=dt)
+    return kg, dh, dt

@@ -1,0 +1,14 @@
+"""torchkge_b200 -- B200-native scoring and link-prediction ranking behind the torchkge API.
+
+Drop-in for the hot path of torchkge v0.17.7 (see DESIGN.md / INTEGRATION.md): the classes
+below keep the reference's names and signatures; their arithmetic runs in hand-written
+sm_100a CUDA kernels reached through the C ABI of ``lib/libkge_b200.so``.
+"""
+from .exceptions import (NotYetEvaluatedError, NotYetImplementedError, SanityError,  # noqa: F401
+                         SizeMismatchError, WrongArgumentsError, WrongDimensionError)
+from .data import KnowledgeGraph  # noqa: F401
+from .models import (ComplExModel, DistMultModel, RESCALModel, RotatEModel,  # noqa: F401
+                     TransEModel)
+from .evaluation import LinkPredictionEvaluator  # noqa: F401
+
+__version__ = "0.1.0"

@@ -189,8 +189,8 @@ int kge_rank_side(const kge_rank_args_t* a) {
   if (el < 0) return fail(KGE_ERR_ARG, "kge_rank_side: unknown model/side");
   if (a->n == 0) return KGE_OK;
   if (a->n < 0 || a->n_rows < 0 || a->dim < 1) return fail(KGE_ERR_ARG, "kge_rank_side: bad sizes");
-  if (!a->packed || !a->ent0 || !a->rel0 || !a->hrows || !a->trows || !a->r_idx ||
-      !a->raw_count || !a->workspace)
+  if (!a->packed || !a->ent0 || !a->rel0 || !a->hrows || !a->trows || !a->raw_count ||
+      !a->workspace)
     return fail(KGE_ERR_ARG, "kge_rank_side: null pointer");
   if (kge::elem_cw(el) == 2 && !a->ent1) return fail(KGE_ERR_ARG, "kge_rank_side: ent1 required");
   if (model_needs_rel1(a->model) && !a->rel1)
@@ -263,8 +263,7 @@ int kge_score_all(const kge_score_all_args_t* a) {
   const int el = kge::elem_kind_for(a->model, a->side);
   if (el < 0) return fail(KGE_ERR_ARG, "kge_score_all: unknown model/side");
   if (a->n == 0 || a->n_rows == 0) return KGE_OK;
-  if (!a->packed || !a->rel0 || !a->hrows || !a->trows || !a->r_idx || !a->scores ||
-      !a->workspace)
+  if (!a->packed || !a->rel0 || !a->hrows || !a->trows || !a->scores || !a->workspace)
     return fail(KGE_ERR_ARG, "kge_score_all: null pointer");
   if (model_needs_rel1(a->model) && !a->rel1)
     return fail(KGE_ERR_ARG, "kge_score_all: rel1 required");

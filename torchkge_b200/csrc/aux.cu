@@ -103,7 +103,7 @@ __global__ void prep_queries_kernel(int model, int side, int dim, long long n,
   if (gid >= n * dim) return;
   const long long i = gid / dim;
   const int k = (int)(gid - i * dim);
-  const long long r = r_idx[i];
+  const long long r = r_idx ? r_idx[i] : i;  // null r_idx: rel tables hold one row per query
   const bool tail = side == KGE_SIDE_TAIL;
   switch (model) {
     case KGE_TRANSE_L1:
@@ -160,7 +160,7 @@ __global__ void prep_rescal_kernel(int side, int dim, long long n,
   if (gid >= n * dim) return;
   const long long i = gid / dim;
   const int j = (int)(gid - i * dim);
-  const float* M = rel_mat + (size_t)r_idx[i] * dim * dim;
+  const float* M = rel_mat + (size_t)(r_idx ? r_idx[i] : i) * dim * dim;
   float acc = 0.f;
   if (side == KGE_SIDE_TAIL) {
     const float* h = hrows + (size_t)i * dim;

@@ -1,0 +1,272 @@
+"""Host-side driver of the CUDA engine: turns torch tensors into C-ABI calls.
+
+Nothing here computes scores: torch is used for device memory, streams and (when the entity
+table is range-partitioned) the two NCCL all-reduces.  The only engine is the CUDA one; tests
+may substitute an object with the same four methods (``pack``, ``gather_rows``,
+``rank_side``, ``score_all``) to exercise the sharding logic on CPU.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+#: default number of test triples ranked per kernel launch (bounds workspace memory only;
+#: results never depend on it)
+DEFAULT_CHUNK = 65536
+
+
+class ModelSpec:
+    """What the kernels read from a model: which score function, and raw fp32 tables.
+
+    Mirrors the state_dict contract of the reference models:
+    ``ent_emb.weight`` / ``rel_emb.weight`` (TransE models/translation.py:63-64, DistMult
+    models/bilinear.py:183-184), ``ent_emb.weight`` / ``rel_mat.weight`` (RESCAL
+    models/bilinear.py:55-56), ``re_/im_ent_emb.weight`` + ``re_/im_rel_emb.weight``
+    (ComplEx models/bilinear.py:455-458).
+    """
+
+    def __init__(self, code, dim, n_ent, n_rel, ent0, ent1, rel0, rel1, ent_lo=0):
+        self.code = code
+        self.dim = int(dim)
+        self.n_ent = int(n_ent)      # global number of entities
+        self.n_rel = int(n_rel)
+        self.ent0, self.ent1, self.rel0, self.rel1 = ent0, ent1, rel0, rel1
+        self.ent_lo = int(ent_lo)    # global id of row 0 of ent0/ent1
+        self.n_rows = int(ent0.shape[0])
+
+    @property
+    def cand_planes(self):
+        return 2 if self.code in (_lib.COMPLEX, _lib.ROTATE) else 1
+
+    def narrowed(self, lo, hi):
+        """Same model restricted to entity rows [lo, hi) (views, no copy)."""
+        a, b = lo - self.ent_lo, hi - self.ent_lo
+        if a < 0 or b > self.n_rows:
+            raise ValueError("shard [%d,%d) outside held rows" % (lo, hi))
+        e1 = None if self.ent1 is None else self.ent1[a:b]
+        return ModelSpec(self.code, self.dim, self.n_ent, self.n_rel, self.ent0[a:b], e1,
+                         self.rel0, self.rel1, ent_lo=lo)
+
+    @staticmethod
+    def _f32(t):
+        t = t.detach()
+        if t.dtype != torch.float32:
+            raise TypeError("embedding tables must be float32, got %s" % t.dtype)
+        return t.contiguous()
+
+    @classmethod
+    def from_model(cls, model):
+        """Accepts torchkge_b200 models and (duck-typed) the reference's own model classes."""
+        name = type(model).__name__
+        f = cls._f32
+        if name == "TransEModel":
+            dname = getattr(model.dissimilarity, "__name__", str(model.dissimilarity))
+            if dname == "l1_dissimilarity":
+                code = _lib.TRANSE_L1
+            elif dname == "l2_dissimilarity":
+                code = _lib.TRANSE_L2
+            else:
+                raise NotImplementedError("TransE dissimilarity %s is not on the CUDA path" % dname)
+            return cls(code, model.emb_dim, model.n_ent, model.n_rel,
+                       f(model.ent_emb.weight), None, f(model.rel_emb.weight), None)
+        if name == "DistMultModel":
+            return cls(_lib.DISTMULT, model.emb_dim, model.n_ent, model.n_rel,
+                       f(model.ent_emb.weight), None, f(model.rel_emb.weight), None)
+        if name == "RESCALModel":
+            return cls(_lib.RESCAL, model.emb_dim, model.n_ent, model.n_rel,
+                       f(model.ent_emb.weight), None, f(model.rel_mat.weight), None)
+        if name == "ComplExModel":
+            return cls(_lib.COMPLEX, model.emb_dim, model.n_ent, model.n_rel,
+                       f(model.re_ent_emb.weight), f(model.im_ent_emb.weight),
+                       f(model.re_rel_emb.weight), f(model.im_rel_emb.weight))
+        if name == "RotatEModel":
+            re_r, im_r = model.relation_planes()
+            return cls(_lib.ROTATE, model.emb_dim, model.n_ent, model.n_rel,
+                       f(model.re_ent_emb.weight), f(model.im_ent_emb.weight), f(re_r), f(im_r))
+        raise NotImplementedError(
+            "%s has no CUDA link-prediction path (supported: TransE L1/L2, DistMult, RESCAL, "
+            "ComplEx, RotatE)" % name)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.KgeLibraryError(
+                "the link-prediction engine runs on CUDA tensors only (got a %s tensor); "
+                "move the model to a GPU -- there is no CPU fallback" % t.device)
+
+
+class CudaEngine:
+    """Direct calls into libkge_b200.so on the current CUDA stream."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+        self.launches = 0  # kernels launched through this engine (bench.py reports it)
+
+    # ---- table packing: once per evaluate() ----
+    def pack(self, spec):
+        _need_cuda(spec.ent0, spec.ent1)
+        n_floats = self.lib.kge_packed_table_floats(spec.code, spec.n_rows, spec.dim)
+        packed = torch.empty(max(n_floats, 1), dtype=torch.float32, device=spec.ent0.device)
+        if spec.n_rows > 0:
+            _lib.check(self.lib.kge_pack_table(spec.code, _ptr(spec.ent0), _ptr(spec.ent1),
+                                               spec.n_rows, spec.dim, _ptr(packed),
+                                               _stream(packed.device)), "kge_pack_table")
+            self.launches += 1
+        return packed
+
+    def gather_rows(self, spec, idx):
+        _need_cuda(spec.ent0, idx)
+        n = idx.shape[0]
+        out = torch.empty((n, spec.cand_planes, spec.dim), dtype=torch.float32,
+                          device=spec.ent0.device)
+        _lib.check(self.lib.kge_gather_rows(spec.code, _ptr(spec.ent0), _ptr(spec.ent1),
+                                            spec.ent_lo, spec.n_rows, spec.dim, _ptr(idx), n,
+                                            _ptr(out), _stream(out.device)), "kge_gather_rows")
+        self.launches += 1
+        return out
+
+    def rank_side(self, spec, packed, side, hrows, trows, r_idx, true_idx, filt, raw_count,
+                  filt_sub, true_score=None):
+        """Adds this shard's counts for one side into raw_count / filt_sub (int32, device)."""
+        n = r_idx.shape[0]
+        dev = raw_count.device
+        ws_bytes = self.lib.kge_rank_workspace_bytes(spec.code, side, spec.dim, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        a = _lib.RankArgs()
+        a.model, a.side, a.dim = spec.code, side, spec.dim
+        a.n, a.n_ent, a.ent_lo, a.n_rows = n, spec.n_ent, spec.ent_lo, spec.n_rows
+        a.packed, a.ent0, a.ent1 = _ptr(packed), _ptr(spec.ent0), _ptr(spec.ent1)
+        a.rel0, a.rel1 = _ptr(spec.rel0), _ptr(spec.rel1)
+        a.hrows, a.trows, a.r_idx, a.true_idx = _ptr(hrows), _ptr(trows), _ptr(r_idx), _ptr(true_idx)
+        if filt is not None:
+            offs, ids = filt
+            a.filt_offs, a.filt_ids, a.n_filt = _ptr(offs), _ptr(ids), ids.shape[0]
+        a.raw_count, a.filt_sub, a.true_score = _ptr(raw_count), _ptr(filt_sub), _ptr(true_score)
+        a.workspace, a.workspace_bytes, a.stream = _ptr(ws), ws_bytes, _stream(dev)
+        _lib.check(self.lib.kge_rank_side(ctypes.byref(a)), "kge_rank_side")
+        # prep, pack_queries, pad fill, true scores, scan (+ filter)
+        self.launches += 5 + (1 if filt is not None and filt[1].shape[0] > 0 else 0)
+        return ws  # keep alive until the caller synchronises / reuses the stream
+
+    def score_all(self, spec, packed, side, hrows, trows, r_idx):
+        n = r_idx.shape[0]
+        dev = hrows.device
+        scores = torch.empty((n, spec.n_rows), dtype=torch.float32, device=dev)
+        ws_bytes = self.lib.kge_rank_workspace_bytes(spec.code, side, spec.dim, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        a = _lib.ScoreAllArgs()
+        a.model, a.side, a.dim = spec.code, side, spec.dim
+        a.n, a.n_rows = n, spec.n_rows
+        a.packed, a.rel0, a.rel1 = _ptr(packed), _ptr(spec.rel0), _ptr(spec.rel1)
+        a.hrows, a.trows, a.r_idx = _ptr(hrows), _ptr(trows), _ptr(r_idx)
+        a.scores, a.workspace, a.workspace_bytes = _ptr(scores), _ptr(ws), ws_bytes
+        a.stream = _stream(dev)
+        _lib.check(self.lib.kge_score_all(ctypes.byref(a)), "kge_score_all")
+        self.launches += 4
+        return scores
+
+    def finalize(self, raw_count, filt_sub):
+        n = raw_count.shape[0]
+        ranks = torch.empty(n, dtype=torch.int64, device=raw_count.device)
+        filt = torch.empty(n, dtype=torch.int64, device=raw_count.device)
+        _lib.check(self.lib.kge_finalize_ranks(_ptr(raw_count), _ptr(filt_sub), n, _ptr(ranks),
+                                               _ptr(filt), _stream(raw_count.device)),
+                   "kge_finalize_ranks")
+        self.launches += 1
+        return ranks, filt
+
+
+_default_engine = None
+
+
+def default_engine():
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = CudaEngine()
+    return _default_engine
+
+
+class EntityShard:
+    """Range partition of the entity table over the ranks of a process group
+    (SURVEY.md section 8e): rank g holds rows [g*ceil(nE/G), (g+1)*ceil(nE/G))."""
+
+    def __init__(self, n_ent, rank=0, world=1, group=None):
+        per = (n_ent + world - 1) // world
+        self.n_ent, self.rank, self.world, self.group = n_ent, rank, world, group
+        self.lo = min(n_ent, rank * per)
+        self.hi = min(n_ent, (rank + 1) * per)
+
+    @classmethod
+    def from_group(cls, n_ent, group=None):
+        import torch.distributed as dist
+        return cls(n_ent, dist.get_rank(group), dist.get_world_size(group), group)
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=None,
+                         engine=None, chunk=DEFAULT_CHUNK, packed=None):
+    """Rank every triple's true tail and head against all entities, raw and filtered.
+
+    spec       ModelSpec holding either the full entity table or exactly this rank's shard
+    h/t/r_idx  int64 device tensors (n,)
+    filt_*     (offs int64 (n+1,), ids int64 (m,)) device CSR of entities to discount, or None
+    shard      EntityShard when the table is range-partitioned over a process group
+    Returns (rank_heads, rank_tails, filt_rank_heads, filt_rank_tails), int64 device tensors.
+    """
+    engine = engine or default_engine()
+    n = h_idx.shape[0]
+    if shard is not None and shard.world > 1:
+        if (spec.ent_lo, spec.n_rows) != (shard.lo, shard.hi - shard.lo):
+            spec = spec.narrowed(shard.lo, shard.hi)
+            packed = None
+    if packed is None:
+        packed = engine.pack(spec)
+    dev = spec.ent0.device
+    counters = torch.zeros((4, n), dtype=torch.int32, device=dev)  # raw_t, sub_t, raw_h, sub_h
+    keep = []
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        h, t, r = h_idx[lo:hi], t_idx[lo:hi], r_idx[lo:hi]
+        hrows = engine.gather_rows(spec, h)
+        trows = engine.gather_rows(spec, t)
+        if shard is not None and shard.world > 1:
+            # every row is owned by exactly one rank; the others contribute zeros
+            shard.all_reduce_sum(hrows)
+            shard.all_reduce_sum(trows)
+        for side, true_idx, filt, raw, sub in (
+                (_lib.SIDE_TAIL, t, filt_tail, counters[0], counters[1]),
+                (_lib.SIDE_HEAD, h, filt_head, counters[2], counters[3])):
+            f = None
+            if filt is not None:
+                offs, ids = filt
+                # CSR slice for this chunk: offsets rebased to the chunk
+                if lo == 0 and hi == n:
+                    f = (offs, ids)
+                else:
+                    base = int(offs[lo].item())
+                    end = int(offs[hi].item())
+                    f = ((offs[lo:hi + 1] - base).contiguous(), ids[base:end].contiguous())
+            keep.append(engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, f,
+                                         raw[lo:hi], sub[lo:hi]))
+        keep.append((hrows, trows))
+    if shard is not None and shard.world > 1:
+        shard.all_reduce_sum(counters)  # the single collective on the rank counters
+    rank_t, filt_t = engine.finalize(counters[0], counters[1])
+    rank_h, filt_h = engine.finalize(counters[2], counters[3])
+    del keep
+    return rank_h, rank_t, filt_h, filt_t

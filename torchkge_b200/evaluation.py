@@ -1,0 +1,140 @@
+"""``LinkPredictionEvaluator`` with the reference's constructor, attributes and metric
+methods (torchkge/evaluation.py:207-425).  ``evaluate`` hands the whole job -- scoring every
+entity as head and as tail of every fact, discounting the filter sets, ranking -- to the
+CUDA engine; no (batch, n_entities) score matrix exists at any point.
+"""
+import torch
+
+from . import _lib
+from .data import filter_csr
+from .engine import DEFAULT_CHUNK, ModelSpec, default_engine, rank_link_prediction
+from .exceptions import NotYetEvaluatedError
+
+
+class LinkPredictionEvaluator(object):
+    """Evaluate an embedding model by link prediction (Bordes et al. 2013).
+
+    Parameters
+    ----------
+    model: a model of ``torchkge_b200.models`` (or the reference's class of the same name),
+        living on a CUDA device.
+    knowledge_graph: object exposing ``n_facts, head_idx, tail_idx, relations,
+        dict_of_heads, dict_of_tails`` (``torchkge.data_structures.KnowledgeGraph`` or
+        ``torchkge_b200.data.KnowledgeGraph``).
+    shard: ``torchkge_b200.engine.EntityShard``, optional (extension).  When given, every
+        rank of the group scans only its range of entity rows and the per-fact counters are
+        summed with one all-reduce; all ranks end up with the full rank vectors.
+
+    Attributes (as in the reference, evaluation.py:236-261)
+    ----------
+    rank_true_heads, rank_true_tails, filt_rank_true_heads, filt_rank_true_tails:
+        torch.LongTensor (n_facts,), on CPU after ``evaluate``.
+    evaluated: bool
+    """
+
+    def __init__(self, model, knowledge_graph, shard=None):
+        self.model = model
+        self.kg = knowledge_graph
+        n = knowledge_graph.n_facts
+        self.rank_true_heads = torch.empty(size=(n,)).long()
+        self.rank_true_tails = torch.empty(size=(n,)).long()
+        self.filt_rank_true_heads = torch.empty(size=(n,)).long()
+        self.filt_rank_true_tails = torch.empty(size=(n,)).long()
+        self.evaluated = False
+        self.shard = shard
+        self.last_stats = {}
+
+    def evaluate(self, b_size, verbose=True):
+        """Rank all facts of the graph.
+
+        ``b_size`` is accepted for signature compatibility; as in the reference it never
+        changes the result.  Here it does not bound memory either (nothing of size
+        b_size x n_entities is allocated); facts are processed in chunks of
+        ``engine.DEFAULT_CHUNK``.  ``verbose`` is accepted and ignored (no per-batch loop to
+        report on).
+        """
+        if b_size is None or int(b_size) < 1:
+            raise ValueError("b_size must be a positive integer")
+        spec = ModelSpec.from_model(self.model)
+        if not spec.ent0.is_cuda:
+            raise _lib.KgeLibraryError(
+                "LinkPredictionEvaluator.evaluate needs the model on a CUDA device "
+                "(model.cuda()); this package has no CPU execution path")
+        dev = spec.ent0.device
+        kg = self.kg
+        heads, tails, rels = kg.head_idx, kg.tail_idx, kg.relations
+        # filter sets -> CSR on the host (same per-row semantics as get_true_targets)
+        csr_t = filter_csr(kg.dict_of_tails, heads, rels, tails)
+        csr_h = filter_csr(kg.dict_of_heads, tails, rels, heads)
+        h_d = heads.to(dev, non_blocking=True)
+        t_d = tails.to(dev, non_blocking=True)
+        r_d = rels.to(dev, non_blocking=True)
+        csr_t = tuple(x.to(dev, non_blocking=True) for x in csr_t)
+        csr_h = tuple(x.to(dev, non_blocking=True) for x in csr_h)
+        self.last_stats = {
+            "h2d_bytes": 8 * (3 * kg.n_facts + sum(x.numel() for x in csr_t + csr_h)),
+            "d2h_bytes": 8 * 4 * kg.n_facts,
+        }
+        engine = default_engine()
+        rh, rt, frh, frt = rank_link_prediction(spec, h_d, t_d, r_d, csr_t, csr_h,
+                                                shard=self.shard, engine=engine,
+                                                chunk=DEFAULT_CHUNK)
+        self.rank_true_heads = rh.cpu()
+        self.rank_true_tails = rt.cpu()
+        self.filt_rank_true_heads = frh.cpu()
+        self.filt_rank_true_tails = frt.cpu()
+        self.evaluated = True
+
+    def _check(self):
+        if not self.evaluated:
+            raise NotYetEvaluatedError('Evaluator not evaluated call '
+                                       'LinkPredictionEvaluator.evaluate')
+
+    def mean_rank(self):
+        """(mean rank, filtered mean rank), heads and tails averaged (evaluation.py:310-330)."""
+        self._check()
+        raw = (self.rank_true_heads.float().mean() + self.rank_true_tails.float().mean()).item()
+        filt = (self.filt_rank_true_heads.float().mean()
+                + self.filt_rank_true_tails.float().mean()).item()
+        return raw / 2, filt / 2
+
+    def hit_at_k_heads(self, k=10):
+        self._check()
+        return ((self.rank_true_heads <= k).float().mean().item(),
+                (self.filt_rank_true_heads <= k).float().mean().item())
+
+    def hit_at_k_tails(self, k=10):
+        self._check()
+        return ((self.rank_true_tails <= k).float().mean().item(),
+                (self.filt_rank_true_tails <= k).float().mean().item())
+
+    def hit_at_k(self, k=10):
+        """(Hits@k, filtered Hits@k), heads and tails averaged (evaluation.py:354-374)."""
+        self._check()
+        hh, fhh = self.hit_at_k_heads(k=k)
+        th, fth = self.hit_at_k_tails(k=k)
+        return (hh + th) / 2, (fhh + fth) / 2
+
+    def mrr(self):
+        """(MRR, filtered MRR), heads and tails averaged (evaluation.py:376-397)."""
+        self._check()
+        head = (self.rank_true_heads.float() ** (-1)).mean()
+        tail = (self.rank_true_tails.float() ** (-1)).mean()
+        fhead = (self.filt_rank_true_heads.float() ** (-1)).mean()
+        ftail = (self.filt_rank_true_tails.float() ** (-1)).mean()
+        return (head + tail).item() / 2, (fhead + ftail).item() / 2
+
+    def print_results(self, k=None, n_digits=3):
+        """Same report as the reference (evaluation.py:399-425)."""
+        if k is None:
+            k = 10
+        if type(k) == int:
+            k = [k]
+        for i in k:
+            print('Hit@{} : {} \t\t Filt. Hit@{} : {}'.format(
+                i, round(self.hit_at_k(k=i)[0], n_digits),
+                i, round(self.hit_at_k(k=i)[1], n_digits)))
+        print('Mean Rank : {} \t Filt. Mean Rank : {}'.format(
+            int(self.mean_rank()[0]), int(self.mean_rank()[1])))
+        print('MRR : {} \t\t Filt. MRR : {}'.format(
+            round(self.mrr()[0], n_digits), round(self.mrr()[1], n_digits)))

@@ -1,0 +1,326 @@
+"""Embedding models with the reference's class names, constructor arguments, parameter names
+and method signatures (torchkge/models/interfaces.py, translation.py:18-125,
+bilinear.py:14-267, 414-556), whose scoring bodies are calls into the CUDA engine.
+
+Only what lies on the hot path is here: TransE (L1 / L2), DistMult, RESCAL, ComplEx and the
+RotatE addition.  ``state_dict`` keys equal the reference's, so weights move freely between
+the two packages.  The pre-0.17 method names ``lp_prep_cands`` / ``lp_scoring_function``
+(docs/history.rst:37-42) are kept as aliases.
+"""
+import math
+
+import torch
+from torch import nn
+from torch.nn.functional import normalize
+
+from . import _lib
+from .engine import ModelSpec, default_engine
+
+
+def init_embedding(n_vectors, dim):
+    """nn.Embedding with Xavier-uniform weights (torchkge/utils/modeling.py:21-28).  Same RNG
+    calls in the same order as the reference, so equal seeds give equal weights."""
+    emb = nn.Embedding(n_vectors, dim)
+    nn.init.xavier_uniform_(emb.weight.data)
+    return emb
+
+
+def l1_dissimilarity(a, b):
+    """Selector for the L1 translational kernels (torchkge/utils/dissimilarities.py:11)."""
+    raise RuntimeError("dissimilarity functions are kernel selectors here, not callables")
+
+
+def l2_dissimilarity(a, b):
+    """Selector for the L2 translational kernels (torchkge/utils/dissimilarities.py:19)."""
+    raise RuntimeError("dissimilarity functions are kernel selectors here, not callables")
+
+
+class Model(nn.Module):
+    """Interface of every model (torchkge/models/interfaces.py:13-174)."""
+
+    def __init__(self, n_entities, n_relations):
+        super().__init__()
+        self.n_ent = n_entities
+        self.n_rel = n_relations
+        self._packed_cache = None  # (key, packed tensor) of the last table packed for inference
+
+    # ---- training-side API -------------------------------------------------------------
+    def forward(self, heads, tails, relations, negative_heads, negative_tails,
+                negative_relations=None):
+        """(pos, neg) scores; several negatives per fact are laid out as n_neg blocks of the
+        batch (interfaces.py:39-82)."""
+        pos = self.scoring_function(heads, tails, relations)
+        if negative_relations is None:
+            negative_relations = relations
+        if negative_heads.shape[0] > negative_relations.shape[0]:
+            n_neg = int(negative_heads.shape[0] / negative_relations.shape[0])
+            pos = pos.repeat(n_neg)
+            neg = self.scoring_function(negative_heads, negative_tails,
+                                        negative_relations.repeat(n_neg))
+        else:
+            neg = self.scoring_function(negative_heads, negative_tails, negative_relations)
+        return pos, neg
+
+    def scoring_function(self, h_idx, t_idx, r_idx):
+        raise NotImplementedError
+
+    def normalize_parameters(self):
+        raise NotImplementedError
+
+    def get_embeddings(self):
+        raise NotImplementedError
+
+    # ---- inference-side API ------------------------------------------------------------
+    def inference_prepare_candidates(self, h_idx, t_idx, r_idx, entities=True):
+        raise NotImplementedError
+
+    def inference_scoring_function(self, h, t, r):
+        """Scores of (h, r, c) or (c, r, t) for every candidate c, shape (b, n_candidates).
+
+        Exactly one of ``h`` / ``t`` is the 3-D candidates tensor returned by
+        ``inference_prepare_candidates`` (a stride-0 expansion of the entity table); the
+        scores come from the same CUDA scan the evaluator uses, written out densely.
+        """
+        return _dense_scores(self, h, t, r)
+
+    # pre-0.17 names
+    def lp_prep_cands(self, h_idx, t_idx, r_idx, entities=True):
+        return self.inference_prepare_candidates(h_idx, t_idx, r_idx, entities=entities)
+
+    def lp_scoring_function(self, h, t, r):
+        return self.inference_scoring_function(h, t, r)
+
+    # ---- helpers -----------------------------------------------------------------------
+    def _kernel_code(self):
+        return ModelSpec.from_model(self).code
+
+    def _expand(self, weight, b_size):
+        n, d = weight.shape
+        return weight.data.view(1, n, d).expand(b_size, n, d)
+
+
+def _as_planes(x):
+    """Tensor or (re, im) tuple -> list of tensors."""
+    return list(x) if isinstance(x, (tuple, list)) else [x]
+
+
+def _dense_scores(model, h, t, r):
+    hp, tp, rp = _as_planes(h), _as_planes(t), _as_planes(r)
+    if rp[0].dim() != 2 and not (type(model).__name__ == "RESCALModel" and rp[0].dim() == 3):
+        raise NotImplementedError("relation-prediction scoring (candidate relations) is not on "
+                                  "the CUDA path")
+    if tp[0].dim() == 3 and hp[0].dim() == 2:
+        side, cand, ent = _lib.SIDE_TAIL, tp, hp
+    elif hp[0].dim() == 3 and tp[0].dim() == 2:
+        side, cand, ent = _lib.SIDE_HEAD, hp, tp
+    else:
+        raise ValueError("exactly one of h / t must be the 3-D candidates tensor")
+    for c in cand:
+        if c.shape[0] > 1 and c.stride(0) != 0:
+            raise NotImplementedError("per-row candidate tensors are not supported: pass the "
+                                      "tensor returned by inference_prepare_candidates")
+    if not ent[0].is_cuda:
+        raise _lib.KgeLibraryError("inference_scoring_function needs CUDA tensors; there is no "
+                                   "CPU fallback")
+    b, n_cand, d = cand[0].shape
+    tables = [c[0].detach().contiguous() for c in cand]
+    code = model._kernel_code()
+    rel = [x.detach().contiguous().view(b, -1) for x in rp]
+    if code == _lib.ROTATE:
+        # inference_prepare_candidates hands out (cos, sin) planes for RotatE
+        pass
+    spec = ModelSpec(code, d, n_cand, b, tables[0], tables[1] if len(tables) > 1 else None,
+                     rel[0], rel[1] if len(rel) > 1 else None)
+    eng = default_engine()
+    key = tuple((tb.data_ptr(), tb._version, tuple(tb.shape)) for tb in tables) + (code,)
+    if model._packed_cache is None or model._packed_cache[0] != key:
+        model._packed_cache = (key, eng.pack(spec))
+    packed = model._packed_cache[1]
+    rows = torch.stack([x.detach().contiguous() for x in ent], dim=1).contiguous()  # (b, planes, d)
+    return eng.score_all(spec, packed, side, rows, rows, None)
+
+
+class TranslationModel(Model):
+    """torchkge/models/interfaces.py:177-272; only 'L1' and 'L2' have kernels."""
+
+    def __init__(self, n_entities, n_relations, dissimilarity_type):
+        super().__init__(n_entities, n_relations)
+        assert dissimilarity_type in ['L1', 'L2', 'torus_L1', 'torus_L2', 'torus_eL2']
+        if dissimilarity_type == 'L1':
+            self.dissimilarity = l1_dissimilarity
+        elif dissimilarity_type == 'L2':
+            self.dissimilarity = l2_dissimilarity
+        else:
+            raise NotImplementedError("torus dissimilarities (TorusE) are outside the CUDA path")
+
+
+class BilinearModel(Model):
+    """torchkge/models/interfaces.py:275-330"""
+
+    def __init__(self, emb_dim, n_entities, n_relations):
+        super().__init__(n_entities, n_relations)
+        self.emb_dim = emb_dim
+
+
+class TransEModel(TranslationModel):
+    """TransE (Bordes et al. 2013) -- torchkge/models/translation.py:18-125."""
+
+    def __init__(self, emb_dim, n_entities, n_relations, dissimilarity_type='L2'):
+        super().__init__(n_entities, n_relations, dissimilarity_type)
+        self.emb_dim = emb_dim
+        self.ent_emb = init_embedding(self.n_ent, self.emb_dim)
+        self.rel_emb = init_embedding(self.n_rel, self.emb_dim)
+        self.normalize_parameters()
+        self.rel_emb.weight.data = normalize(self.rel_emb.weight.data, p=2, dim=1)
+
+    def scoring_function(self, h_idx, t_idx, r_idx):
+        from .training import score_triples
+        return score_triples(self, h_idx, t_idx, r_idx)
+
+    def normalize_parameters(self):
+        self.ent_emb.weight.data = normalize(self.ent_emb.weight.data, p=2, dim=1)
+
+    def get_embeddings(self):
+        self.normalize_parameters()
+        return self.ent_emb.weight.data, self.rel_emb.weight.data
+
+    def inference_prepare_candidates(self, h_idx, t_idx, r_idx, entities=True):
+        b = h_idx.shape[0]
+        h, t, r = self.ent_emb(h_idx), self.ent_emb(t_idx), self.rel_emb(r_idx)
+        cands = self._expand(self.ent_emb.weight if entities else self.rel_emb.weight, b)
+        return h, t, r, cands
+
+
+class DistMultModel(BilinearModel):
+    """DistMult (Yang et al. 2014) -- torchkge/models/bilinear.py:146-267."""
+
+    def __init__(self, emb_dim, n_entities, n_relations):
+        super().__init__(emb_dim, n_entities, n_relations)
+        self.ent_emb = init_embedding(self.n_ent, self.emb_dim)
+        self.rel_emb = init_embedding(self.n_rel, self.emb_dim)
+        self.normalize_parameters()
+
+    def scoring_function(self, h_idx, t_idx, r_idx):
+        from .training import score_triples
+        return score_triples(self, h_idx, t_idx, r_idx)
+
+    def normalize_parameters(self):
+        self.ent_emb.weight.data = normalize(self.ent_emb.weight.data, p=2, dim=1)
+
+    def get_embeddings(self):
+        self.normalize_parameters()
+        return self.ent_emb.weight.data, self.rel_emb.weight.data
+
+    def inference_prepare_candidates(self, h_idx, t_idx, r_idx, entities=True):
+        b = h_idx.shape[0]
+        h, t, r = self.ent_emb(h_idx), self.ent_emb(t_idx), self.rel_emb(r_idx)
+        cands = self._expand(self.ent_emb.weight if entities else self.rel_emb.weight, b)
+        return h, t, r, cands
+
+
+class RESCALModel(BilinearModel):
+    """RESCAL (Nickel et al. 2011) -- torchkge/models/bilinear.py:14-143."""
+
+    def __init__(self, emb_dim, n_entities, n_relations):
+        super().__init__(emb_dim, n_entities, n_relations)
+        self.ent_emb = init_embedding(self.n_ent, self.emb_dim)
+        self.rel_mat = init_embedding(self.n_rel, self.emb_dim * self.emb_dim)
+        self.normalize_parameters()
+
+    def scoring_function(self, h_idx, t_idx, r_idx):
+        from .training import score_triples
+        return score_triples(self, h_idx, t_idx, r_idx)
+
+    def normalize_parameters(self):
+        self.ent_emb.weight.data = normalize(self.ent_emb.weight.data, p=2, dim=1)
+
+    def get_embeddings(self):
+        self.normalize_parameters()
+        return (self.ent_emb.weight.data,
+                self.rel_mat.weight.data.view(-1, self.emb_dim, self.emb_dim))
+
+    def inference_prepare_candidates(self, h_idx, t_idx, r_idx, entities=True):
+        b = h_idx.shape[0]
+        h, t = self.ent_emb(h_idx), self.ent_emb(t_idx)
+        r_mat = self.rel_mat(r_idx).view(-1, self.emb_dim, self.emb_dim)
+        if entities:
+            cands = self._expand(self.ent_emb.weight, b)
+        else:
+            cands = self.rel_mat.weight.data.view(1, self.n_rel, self.emb_dim, self.emb_dim)
+            cands = cands.expand(b, self.n_rel, self.emb_dim, self.emb_dim)
+        return h, t, r_mat, cands
+
+
+class ComplExModel(BilinearModel):
+    """ComplEx (Trouillon et al. 2016) -- torchkge/models/bilinear.py:414-556."""
+
+    def __init__(self, emb_dim, n_entities, n_relations):
+        super().__init__(emb_dim, n_entities, n_relations)
+        self.re_ent_emb = init_embedding(self.n_ent, self.emb_dim)
+        self.im_ent_emb = init_embedding(self.n_ent, self.emb_dim)
+        self.re_rel_emb = init_embedding(self.n_rel, self.emb_dim)
+        self.im_rel_emb = init_embedding(self.n_rel, self.emb_dim)
+
+    def scoring_function(self, h_idx, t_idx, r_idx):
+        from .training import score_triples
+        return score_triples(self, h_idx, t_idx, r_idx)
+
+    def normalize_parameters(self):
+        pass
+
+    def get_embeddings(self):
+        return (self.re_ent_emb.weight.data, self.im_ent_emb.weight.data,
+                self.re_rel_emb.weight.data, self.im_rel_emb.weight.data)
+
+    def inference_prepare_candidates(self, h_idx, t_idx, r_idx, entities=True):
+        b = h_idx.shape[0]
+        h = (self.re_ent_emb(h_idx), self.im_ent_emb(h_idx))
+        t = (self.re_ent_emb(t_idx), self.im_ent_emb(t_idx))
+        r = (self.re_rel_emb(r_idx), self.im_rel_emb(r_idx))
+        if entities:
+            cands = (self._expand(self.re_ent_emb.weight, b), self._expand(self.im_ent_emb.weight, b))
+        else:
+            cands = (self._expand(self.re_rel_emb.weight, b), self._expand(self.im_rel_emb.weight, b))
+        return h, t, r, cands
+
+
+class RotatEModel(BilinearModel):
+    """RotatE (Sun et al. 2019): score = -sum_k |h_k r_k - t_k|, r_k = exp(i theta_k).
+
+    Not part of the reference; laid out like ``ComplExModel`` (separate real / imaginary
+    entity tables, tuple-returning ``inference_prepare_candidates``) with relation phases in
+    ``rel_emb``.  The oracle for it is oracle/kge_oracle.py:rotate_scores_all.
+    """
+
+    def __init__(self, emb_dim, n_entities, n_relations):
+        super().__init__(emb_dim, n_entities, n_relations)
+        self.re_ent_emb = init_embedding(self.n_ent, self.emb_dim)
+        self.im_ent_emb = init_embedding(self.n_ent, self.emb_dim)
+        self.rel_emb = nn.Embedding(self.n_rel, self.emb_dim)
+        nn.init.uniform_(self.rel_emb.weight.data, -math.pi, math.pi)
+
+    def relation_planes(self):
+        """(cos theta, sin theta) tables, shape (n_rel, emb_dim)."""
+        ph = self.rel_emb.weight.detach()
+        return torch.cos(ph), torch.sin(ph)
+
+    def scoring_function(self, h_idx, t_idx, r_idx):
+        from .training import score_triples
+        return score_triples(self, h_idx, t_idx, r_idx)
+
+    def normalize_parameters(self):
+        pass
+
+    def get_embeddings(self):
+        return self.re_ent_emb.weight.data, self.im_ent_emb.weight.data, self.rel_emb.weight.data
+
+    def inference_prepare_candidates(self, h_idx, t_idx, r_idx, entities=True):
+        if not entities:
+            raise NotImplementedError("RotatE relation prediction is not implemented")
+        b = h_idx.shape[0]
+        h = (self.re_ent_emb(h_idx), self.im_ent_emb(h_idx))
+        t = (self.re_ent_emb(t_idx), self.im_ent_emb(t_idx))
+        ph = self.rel_emb(r_idx)
+        r = (torch.cos(ph), torch.sin(ph))
+        cands = (self._expand(self.re_ent_emb.weight, b), self._expand(self.im_ent_emb.weight, b))
+        return h, t, r, cands
