@@ -66,3 +66,57 @@ def make_kg(n_ent, n_rel, n_facts, n_test, seed=0):
     kg = tk.KnowledgeGraph(h[:n_test], t[:n_test], r[:n_test], n_ent, n_rel,
                            dict_of_heads=dh, dict_of_tails=dt)
     return kg, dh, dt
+
+
+# ---------------------------------------------------------------------------- golden fixtures
+import os  # noqa: E402
+from collections import defaultdict  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_CASES = ["toy_transe_l1", "toy_transe_l2", "toy_distmult", "toy_rescal", "toy_complex",
+                "syn_transe_l1", "syn_transe_l2", "syn_distmult", "syn_rescal", "syn_complex"]
+
+_STATE_TO_ORACLE = {
+    "ent_emb.weight": "ent", "rel_emb.weight": "rel", "rel_mat.weight": "rel_mat",
+    "re_ent_emb.weight": "re_ent", "im_ent_emb.weight": "im_ent",
+    "re_rel_emb.weight": "re_rel", "im_rel_emb.weight": "im_rel",
+}
+
+
+def _arrays_to_dict(keys, offs, vals):
+    d = defaultdict(set)
+    for i, (a, b) in enumerate(keys.tolist()):
+        d[(a, b)] = set(vals[offs[i]:offs[i + 1]].tolist())
+    return d
+
+
+def load_golden(name):
+    """dict with: kind, dim, n_ent, n_rel, b_size, P (oracle params), state (state_dict arrays),
+    heads/tails/rels (test facts), dh/dt (filter dicts) and every reference output array."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    g = {k: z[k] for k in z.files}
+    out = {"kind": str(g["kind"]), "dim": int(g["dim"]), "n_ent": int(g["n_ent"]),
+           "n_rel": int(g["n_rel"]), "b_size": int(g["b_size"]), "raw": g}
+    out["state"] = {k[2:]: torch.from_numpy(v.copy()) for k, v in g.items() if k.startswith("w:")}
+    out["grads"] = {k[2:]: torch.from_numpy(v.copy()) for k, v in g.items() if k.startswith("g:")}
+    out["P"] = {_STATE_TO_ORACLE[k]: v for k, v in out["state"].items()}
+    for k in ("heads", "tails", "rels", "all_heads", "all_tails", "all_rels", "neg_heads", "neg_tails"):
+        out[k] = torch.from_numpy(g[k].copy()).long()
+    out["dh"] = _arrays_to_dict(g["dh_keys"], g["dh_offs"], g["dh_vals"])
+    out["dt"] = _arrays_to_dict(g["dt_keys"], g["dt_offs"], g["dt_vals"])
+    return out
+
+
+def model_from_golden(g):
+    model = KIND_TO_CLASS[g["kind"]](g["dim"], g["n_ent"], g["n_rel"])
+    model.load_state_dict(g["state"])
+    return model
+
+
+def bits_equal(a, b):
+    """Element-wise: same fp32 bit pattern, or numerically equal (+0 == -0)."""
+    a = a.detach().cpu().float().contiguous()
+    b = b.detach().cpu().float().contiguous()
+    return (a.numpy().view(np.uint32) == b.numpy().view(np.uint32)) | (a == b).numpy()

@@ -1,0 +1,86 @@
+"""Host-side logic of the shim: filter CSR construction, shard ranges, loud failure on CPU."""
+import pytest
+import torch
+
+import torchkge_b200 as tk
+from oracle import kge_oracle as oracle
+from tests import helpers
+from torchkge_b200 import _lib
+from torchkge_b200.data import filter_csr
+from torchkge_b200.engine import EntityShard, ModelSpec
+
+
+def test_filter_csr_matches_get_true_targets_semantics():
+    h, t, r = helpers.random_graph(60, 4, 900, seed=3)
+    dh, dt = oracle.build_filter_dicts(h, t, r)
+    # quirk 1: true entity missing from its set -> row unfiltered
+    for i in range(0, 50, 5):
+        dt[(h[i].item(), r[i].item())].discard(t[i].item())
+    # quirk 2: unknown key
+    hq = torch.cat([h[:200], torch.tensor([59])])
+    rq = torch.cat([r[:200], torch.tensor([3])])
+    tq = torch.cat([t[:200], torch.tensor([0])])
+    dt.pop((59, 3), None)
+    offs, ids = filter_csr(dt, hq, rq, tq)
+    assert offs.dtype == torch.int64 and offs.shape == (202,)
+    for i in range(201):
+        want = oracle.filter_targets(dt, hq[i].item(), rq[i].item(), tq[i].item())
+        got = ids[offs[i]:offs[i + 1]].tolist()
+        assert sorted(got) == sorted(want or [])
+        assert tq[i].item() not in got
+
+
+def test_filter_csr_accepts_list_valued_dicts():
+    # the reference's own fixture uses lists (tests/test_utils.py:57)
+    d = {(0, 0): [0, 1, 2], (0, 1): [1]}
+    offs, ids = filter_csr(d, torch.tensor([0, 0, 0]), torch.tensor([0, 0, 1]), torch.tensor([1, 2, 1]))
+    assert offs.tolist() == [0, 2, 4, 4]
+    assert sorted(ids[:2].tolist()) == [0, 2] and sorted(ids[2:4].tolist()) == [0, 1]
+
+
+@pytest.mark.parametrize("n_ent,world", [(10, 1), (10, 3), (1000000, 8), (7, 8), (5000000, 8)])
+def test_entity_shard_ranges_partition_the_table(n_ent, world):
+    shards = [EntityShard(n_ent, g, world) for g in range(world)]
+    assert shards[0].lo == 0 and shards[-1].hi == n_ent
+    for a, b in zip(shards, shards[1:]):
+        assert a.hi == b.lo
+    assert sum(s.hi - s.lo for s in shards) == n_ent
+
+
+def test_model_spec_reads_reference_parameter_names():
+    m = tk.ComplExModel(8, 12, 3)
+    s = ModelSpec.from_model(m)
+    assert s.code == _lib.COMPLEX and s.n_rows == 12 and s.cand_planes == 2
+    assert s.ent0.data_ptr() == m.re_ent_emb.weight.data_ptr()  # no copy
+    sub = s.narrowed(4, 9)
+    assert sub.ent_lo == 4 and sub.n_rows == 5 and sub.n_ent == 12
+    assert ModelSpec.from_model(tk.TransEModel(8, 12, 3, "L1")).code == _lib.TRANSE_L1
+    assert ModelSpec.from_model(tk.TransEModel(8, 12, 3)).code == _lib.TRANSE_L2
+
+
+def test_state_dict_keys_match_reference_contract():
+    assert set(tk.TransEModel(4, 5, 2).state_dict()) == {"ent_emb.weight", "rel_emb.weight"}
+    assert set(tk.RESCALModel(4, 5, 2).state_dict()) == {"ent_emb.weight", "rel_mat.weight"}
+    assert set(tk.ComplExModel(4, 5, 2).state_dict()) == {
+        "re_ent_emb.weight", "im_ent_emb.weight", "re_rel_emb.weight", "im_rel_emb.weight"}
+    assert tk.RESCALModel(4, 5, 2).rel_mat.weight.shape == (2, 16)
+
+
+def test_constructor_weights_equal_reference_distribution():
+    """Entity rows are unit-norm for TransE / DistMult / RESCAL; ComplEx is raw Xavier."""
+    torch.manual_seed(0)
+    m = tk.TransEModel(50, 40, 6)
+    assert torch.allclose(m.ent_emb.weight.norm(dim=1), torch.ones(40), atol=1e-6)
+    assert torch.allclose(m.rel_emb.weight.norm(dim=1), torch.ones(6), atol=1e-6)
+    c = tk.ComplExModel(50, 40, 6)
+    bound = (6.0 / (40 + 50)) ** 0.5
+    assert c.re_ent_emb.weight.abs().max() <= bound
+
+
+def test_evaluator_refuses_cpu_models_loudly():
+    kg, _, _ = helpers.make_kg(30, 3, 100, 10)
+    ev = tk.LinkPredictionEvaluator(tk.DistMultModel(8, 30, 3), kg)
+    with pytest.raises(_lib.KgeLibraryError, match="no CPU"):
+        ev.evaluate(b_size=4, verbose=False)
+    with pytest.raises(tk.NotYetEvaluatedError):
+        ev.mrr()
