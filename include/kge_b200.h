@@ -180,6 +180,15 @@ typedef struct {
 } kge_score_all_args_t;
 int kge_score_all(const kge_score_all_args_t* args);
 
+/* ---- measurement hook ------------------------------------------------------------------
+ * When enabled, every dense-scan launch (the dominant kernel of kge_rank_side /
+ * kge_score_all) is bracketed by CUDA events recorded on the launch stream.
+ * kge_scan_timing_read() synchronises those events, returns the number of launches and
+ * their summed device time since the last read, and clears the record.  Used by bench.py
+ * for the roofline figure; off by default (no events are created). */
+int kge_scan_timing_enable(int on);
+int kge_scan_timing_read(int64_t* launches, double* total_ms);
+
 #ifdef __cplusplus
 }
 #endif

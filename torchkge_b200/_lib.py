@@ -67,6 +67,8 @@ SIGNATURES = {
     "kge_rank_side": (_c.c_int, [_c.POINTER(RankArgs)]),
     "kge_finalize_ranks": (_c.c_int, [_p, _p, _c.c_int64, _p, _p, _p]),
     "kge_score_all": (_c.c_int, [_c.POINTER(ScoreAllArgs)]),
+    "kge_scan_timing_enable": (_c.c_int, [_c.c_int]),
+    "kge_scan_timing_read": (_c.c_int, [_c.POINTER(_c.c_int64), _c.POINTER(_c.c_double)]),
 }
 
 _lock = threading.Lock()
@@ -117,3 +119,14 @@ def build_schedule(model, dim):
     code = np.zeros(dim, dtype=np.uint8)
     check(lib.kge_build_schedule(model, dim, perm.ctypes.data, code.ctypes.data), "kge_build_schedule")
     return perm, code
+
+
+def scan_timing_enable(on=True):
+    check(load().kge_scan_timing_enable(1 if on else 0), "kge_scan_timing_enable")
+
+
+def scan_timing_read():
+    """(launches, total_ms) of the dense-scan kernel since the last read."""
+    n, ms = ctypes.c_int64(0), ctypes.c_double(0.0)
+    check(load().kge_scan_timing_read(ctypes.byref(n), ctypes.byref(ms)), "kge_scan_timing_read")
+    return n.value, ms.value

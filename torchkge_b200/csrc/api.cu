@@ -4,6 +4,7 @@
 #include <memory>
 #include <stdio.h>
 #include <string.h>
+#include <vector>
 
 #include "../../include/kge_b200.h"
 #include "kernels.h"
@@ -104,6 +105,31 @@ int prepare_queries(int model, int side, int dim, int64_t n, const float* hrows,
 }
 
 bool model_needs_rel1(int model) { return model == KGE_COMPLEX || model == KGE_ROTATE; }
+
+// Optional CUDA-event bracketing of the scan launches (kge_scan_timing_*).
+std::mutex g_timing_mu;
+bool g_timing_on = false;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timing_events;
+
+cudaError_t timed_scan(int el, bool casc, const kge::ScanParams& p, cudaStream_t st) {
+  bool on;
+  {
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    on = g_timing_on;
+  }
+  if (!on) return kge::launch_scan(el, casc, p, st);
+  cudaEvent_t a, b;
+  cudaError_t e = cudaEventCreate(&a);
+  if (e != cudaSuccess) return e;
+  e = cudaEventCreate(&b);
+  if (e != cudaSuccess) return e;
+  cudaEventRecord(a, st);
+  e = kge::launch_scan(el, casc, p, st);
+  cudaEventRecord(b, st);
+  std::lock_guard<std::mutex> lock(g_timing_mu);
+  g_timing_events.emplace_back(a, b);
+  return e;
+}
 
 }  // namespace
 
@@ -236,7 +262,7 @@ int kge_rank_side(const kge_rank_args_t* a) {
     p.n_rows = a->n_rows;
     p.n_ct = (a->n_rows + kge::TILE_C - 1) / kge::TILE_C;
     p.n_qt = n_qt;
-    KGE_CUDA_TRY(kge::launch_scan(el, casc, p, st), "rank scan");
+    KGE_CUDA_TRY(timed_scan(el, casc, p, st), "rank scan");
 
     if (a->filt_offs && a->n_filt > 0)
       KGE_CUDA_TRY(kge::launch_filter(el, casc, a->dim, a->n, a->n_filt, w.qplain, a->ent0, a->ent1,
@@ -290,8 +316,36 @@ int kge_score_all(const kge_score_all_args_t* a) {
   p.n_rows = a->n_rows;
   p.n_ct = (a->n_rows + kge::TILE_C - 1) / kge::TILE_C;
   p.n_qt = n_qt;
-  KGE_CUDA_TRY(kge::launch_scan(el, hs->s.has_cascade, p, st), "score scan");
+  KGE_CUDA_TRY(timed_scan(el, hs->s.has_cascade, p, st), "score scan");
   return KGE_OK;
+}
+
+int kge_scan_timing_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_timing_mu);
+  g_timing_on = on != 0;
+  return KGE_OK;
+}
+
+int kge_scan_timing_read(int64_t* launches, double* total_ms) {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  {
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    ev.swap(g_timing_events);
+  }
+  double total = 0.0;
+  int rc = KGE_OK;
+  for (auto& pr : ev) {
+    cudaError_t e = cudaEventSynchronize(pr.second);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, pr.first, pr.second);
+    if (e != cudaSuccess) rc = fail_cuda(e, "scan timing");
+    total += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  if (launches) *launches = (int64_t)ev.size();
+  if (total_ms) *total_ms = total;
+  return rc;
 }
 
 }  // extern "C"

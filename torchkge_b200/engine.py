@@ -200,16 +200,19 @@ class EntityShard:
     """Range partition of the entity table over the ranks of a process group
     (SURVEY.md section 8e): rank g holds rows [g*ceil(nE/G), (g+1)*ceil(nE/G))."""
 
-    def __init__(self, n_ent, rank=0, world=1, group=None):
+    def __init__(self, n_ent, rank=0, world=1, group=None, local_storage=False):
         per = (n_ent + world - 1) // world
         self.n_ent, self.rank, self.world, self.group = n_ent, rank, world, group
+        #: True when the model on this rank HOLDS only rows [lo, hi) (its row 0 is entity lo);
+        #: False when every rank holds the full table and merely scans its own range
+        self.local_storage = local_storage
         self.lo = min(n_ent, rank * per)
         self.hi = min(n_ent, (rank + 1) * per)
 
     @classmethod
-    def from_group(cls, n_ent, group=None):
+    def from_group(cls, n_ent, group=None, local_storage=False):
         import torch.distributed as dist
-        return cls(n_ent, dist.get_rank(group), dist.get_world_size(group), group)
+        return cls(n_ent, dist.get_rank(group), dist.get_world_size(group), group, local_storage)
 
     def all_reduce_sum(self, t):
         if self.world > 1:

@@ -56,6 +56,8 @@ class LinkPredictionEvaluator(object):
         if b_size is None or int(b_size) < 1:
             raise ValueError("b_size must be a positive integer")
         spec = ModelSpec.from_model(self.model)
+        if self.shard is not None and self.shard.local_storage:
+            spec.ent_lo, spec.n_ent = self.shard.lo, self.shard.n_ent
         if not spec.ent0.is_cuda:
             raise _lib.KgeLibraryError(
                 "LinkPredictionEvaluator.evaluate needs the model on a CUDA device "
