@@ -137,7 +137,9 @@ def rotate_scores_all(P, h_idx, t_idx, r_idx, side):
         im_q = re_r * im_e - im_r * re_e
     dre = re_q.view(b, 1, d) - re_c
     dim_ = im_q.view(b, 1, d) - im_c
-    return -torch.sqrt(dre * dre + dim_ * dim_).sum(dim=2)
+    # complex modulus as in the authors' code: stack + norm over the stacked axis.  (ATen's
+    # element-wise torch.sqrt is not correctly rounded on CPU; the norm kernel's sqrt is.)
+    return -torch.stack([dre, dim_], dim=0).norm(dim=0).sum(dim=2)
 
 
 # --------------------------------------------------------------------------- filter + rank
@@ -236,7 +238,7 @@ def score_triples(kind, P, h_idx, t_idx, r_idx):
         re_r, im_r = re_rel[r_idx], im_rel[r_idx]
         dre = (re_h * re_r - im_h * im_r) - re_t
         dim_ = (re_h * im_r + im_h * re_r) - im_t
-        return -torch.sqrt(dre * dre + dim_ * dim_).sum(dim=1)
+        return -torch.stack([dre, dim_], dim=0).norm(dim=0).sum(dim=1)
     raise ValueError(kind)
 
 

@@ -41,5 +41,9 @@ def run(code, d, n_ent, n_q, n_rel=1000, reps=3):
 if __name__ == '__main__':
     n_ent = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
     n_q = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
-    for code, d in ((_lib.TRANSE_L2, 200), (_lib.TRANSE_L1, 200), (_lib.DISTMULT, 200), (_lib.COMPLEX, 400), (_lib.ROTATE, 1000 if n_ent <= 200000 else 200)):
-        run(code, d, n_ent, n_q)
+    import os
+    sel = os.environ.get("QP_MODELS", "l2,l1,dm,cx,rot").split(",")
+    table = {"l2": (_lib.TRANSE_L2, 200), "l1": (_lib.TRANSE_L1, 200), "dm": (_lib.DISTMULT, 200),
+             "cx": (_lib.COMPLEX, 400), "rot": (_lib.ROTATE, 200)}
+    for k in sel:
+        run(table[k][0], table[k][1], n_ent, n_q)

@@ -254,7 +254,7 @@ int kge_rank_side(const kge_rank_args_t* a) {
     p.packed = a->packed;
     p.qpacked = w.qpacked;
     p.s_true = w.s_true;
-    p.code = w.code;
+    p.code_host = hs->s.code.data();
     p.counts = a->raw_count;
     p.scores = nullptr;
     p.dim = a->dim;
@@ -308,7 +308,7 @@ int kge_score_all(const kge_score_all_args_t* a) {
   p.packed = a->packed;
   p.qpacked = w.qpacked;
   p.s_true = w.s_true;
-  p.code = w.code;
+  p.code_host = hs->s.code.data();
   p.counts = nullptr;
   p.scores = a->scores;
   p.dim = a->dim;

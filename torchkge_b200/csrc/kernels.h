@@ -16,11 +16,17 @@ int elem_kind_for(int model, int side);
 int elem_qw(int el);
 int elem_cw(int el);
 
+constexpr int SCAN_KC = 32;          // schedule positions per pipeline stage of the scan
+constexpr int SCAN_MAX_DIM = 8192;   // schedule bytes carried in the kernel parameters
+
+// Passed BY VALUE as the kernel parameter (about 9 KB; CUDA >= 12.1 allows 32 KB): the
+// schedule then lives in the constant bank, indexed with uniform registers, so that every
+// test on it is a uniform branch (no convergence barriers, no shared-memory latency).
 struct ScanParams {
   const float* packed;   // [n_ct][dim][CW][TILE_C]
   const float* qpacked;  // [n_qt][dim][QW][TILE_Q]
   const float* s_true;   // [n_qt*TILE_Q], NaN padded
-  const uint8_t* code;   // [dim]
+  const uint8_t* code_host;  // [dim] schedule codes (HOST pointer; copied into `code` at launch)
   int32_t* counts;       // [n_q] (+=) or nullptr
   float* scores;         // [n_q][n_rows] or nullptr
   int dim;
@@ -28,6 +34,8 @@ struct ScanParams {
   int64_t n_rows;
   int64_t n_ct;
   int64_t n_qt;
+  uint32_t mask[SCAN_MAX_DIM / SCAN_KC];  // per stage: bit kk set <=> position needs the slow path
+  uint8_t code[SCAN_MAX_DIM];
 };
 
 // dense scan: counts[q] += #{c < n_rows : score(q,c) >= s_true[q]}  (or writes scores)

@@ -85,8 +85,7 @@ __device__ __forceinline__ void acc_step_fast(Acc& r, float q0, float q1, float 
     r.a = __fadd_rn(r.a, v);
 }
 
-// General path: any code byte.  `code` must be warp-uniform for speed (it is: the schedule
-// is shared by all pairs).
+// General path for ONE pair (sparse pair scorer).  `code` is uniform across the warp there too.
 template <int EL, bool CASC>
 __device__ __forceinline__ void acc_step(Acc& r, uint8_t code, float q0, float q1, float c0,
                                          float c1) {
@@ -114,6 +113,35 @@ __device__ __forceinline__ void acc_step(Acc& r, uint8_t code, float q0, float q
   if (code & SC_T_ADD_P) { r.t = __fadd_rn(r.t, r.p); }
   if (code & SC_T_ADD_A) { r.t = __fadd_rn(r.t, r.a); r.a = 0.f; }
 }
+
+// The same step split for register tiles: the element part for one pair under a given
+// (uniform) mode, and the combine part for one pair under a given (uniform) op.  The dense
+// scan hoists the uniform tests out of its pair loops, so no per-pair selects are generated.
+template <int EL>
+__device__ __forceinline__ void acc_elem_mode(Acc& r, uint8_t mode, float q0, float q1, float c0,
+                                              float c1) {
+  const float v = elem_value<EL>(q0, q1, c0, c1);
+  if constexpr (elem_is_l2<EL>()) {
+    if (mode == SC_MODE_A)
+      r.a = __fadd_rn(r.a, __fmul_rn(v, v));
+    else if (mode == SC_MODE_T)
+      r.t = __fadd_rn(r.t, __fmul_rn(v, v));
+    else
+      r.t = __fmaf_rn(v, v, r.t);
+  } else {
+    if (mode == SC_MODE_A)
+      r.a = __fadd_rn(r.a, v);
+    else
+      r.t = __fadd_rn(r.t, v);
+  }
+}
+
+__device__ __forceinline__ void acc_casc1(Acc& r) { r.a1 = __fadd_rn(r.a1, r.a); r.a = 0.f; }
+__device__ __forceinline__ void acc_fold1(Acc& r) { r.a = __fadd_rn(r.a, r.a1); r.a1 = 0.f; }
+__device__ __forceinline__ void acc_p_set(Acc& r) { r.p = r.a; r.a = 0.f; }
+__device__ __forceinline__ void acc_p_add(Acc& r) { r.p = __fadd_rn(r.p, r.a); r.a = 0.f; }
+__device__ __forceinline__ void acc_t_add_p(Acc& r) { r.t = __fadd_rn(r.t, r.p); }
+__device__ __forceinline__ void acc_t_add_a(Acc& r) { r.t = __fadd_rn(r.t, r.a); r.a = 0.f; }
 
 // Reduction result -> score, with the reference's sign and the L2 sqrt-then-square
 // (dissimilarities.py:25 computes norm(p=2)**2; interfaces.py:254,260 negate).

@@ -6,12 +6,16 @@
 // candidates x dim, of which only  #{c : S[q][c] >= s_true[q]}  per query is kept.  With
 // tens of thousands of queries sharing every streamed candidate tile the kernel is bound by
 // fp32 issue, not by HBM, so it is organised like an SGEMM: a persistent CTA per SM walks
-// (query tile, candidate tile) pairs; a producer warp streams schedule-ordered k-chunks of
-// both operands into a 4-stage shared-memory ring with 1-D bulk async copies (UBLKCP)
-// signalled on mbarriers; 8 consumer warps hold a 4 x 8 register tile of running reductions
-// per thread.  Both operands are pre-laid out k-major ("packed") so every shared-memory read
-// is a conflict-free 128-bit load and the reduction schedule is walked front to back.
+// (query tile, candidate tile) pairs; one elected thread streams schedule-ordered k-chunks of
+// both operands into a shared-memory ring with 1-D bulk async copies (UBLKCP) signalled on
+// mbarriers, two stages ahead; all warps hold a register tile of running reductions per thread.  Both
+// operands are pre-laid out k-major ("packed") so every shared-memory read is a conflict-free
+// 128-bit load and the reduction schedule is walked front to back.  Positions that need a
+// combine step are flagged in a per-stage bit mask, so the common positions run in branch-free
+// unrolled runs.
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -20,33 +24,36 @@ namespace kge {
 
 namespace {
 
-constexpr int KC = 16;           // schedule positions per pipeline stage
-constexpr int STAGES = 4;
-constexpr int CONSUMER_WARPS = 8;
-constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
-constexpr int TQ = 4;            // queries per thread
-constexpr int TC = 8;            // candidates per thread (two groups of 4)
-constexpr int CODE_BYTES = 8192;
+constexpr int KC = SCAN_KC;  // schedule positions per pipeline stage (one 32-bit special mask)
+constexpr int STAGES = 3;
+constexpr int TQ = 4;   // queries per thread
 
-template <int EL>
-struct StageLayout {
+// G = groups of 4 candidates per thread (thread tile 4 x 4G); consumer warps = 16 / G.
+template <int EL, int G>
+struct Cfg {
   static constexpr int QW = ElemTraits<EL>::QW;
   static constexpr int CW = ElemTraits<EL>::CW;
+  static constexpr int TC = 4 * G;
+  static constexpr int WARPS_C = TILE_C / (32 * G);      // warps along candidates
+  static constexpr int WARPS_Q = TILE_Q / 16;            // warps along queries
+  static constexpr int CONSUMER_WARPS = WARPS_C * WARPS_Q;
+  static constexpr int THREADS = CONSUMER_WARPS * 32;
   static constexpr int C_FLOATS = KC * CW * TILE_C;
   static constexpr int Q_FLOATS = KC * QW * TILE_Q;
   static constexpr int STAGE_FLOATS = C_FLOATS + Q_FLOATS;
   static constexpr size_t SMEM_BYTES =
-      (size_t)STAGES * STAGE_FLOATS * sizeof(float) + CODE_BYTES + 2 * STAGES * sizeof(uint64_t);
+      (size_t)STAGES * STAGE_FLOATS * sizeof(float) + 2 * STAGES * sizeof(uint64_t);
 };
 
-template <int EL, bool CASC>
-__global__ void __launch_bounds__(THREADS, 1) scan_kernel(const ScanParams p) {
-  using L = StageLayout<EL>;
-  constexpr int QW = L::QW, CW = L::CW;
+template <int EL, bool CASC, int G>
+__global__ void __launch_bounds__(Cfg<EL, G>::THREADS, 1)
+    scan_kernel(const __grid_constant__ ScanParams p) {
+  using L = Cfg<EL, G>;
+  constexpr int QW = L::QW, CW = L::CW, TC = L::TC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  uint8_t* s_code = smem_raw + (size_t)STAGES * L::STAGE_FLOATS * sizeof(float);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_code + CODE_BYTES);
+  uint64_t* full_bar =
+      reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * L::STAGE_FLOATS * sizeof(float));
   uint64_t* empty_bar = full_bar + STAGES;
 
   const int warp = threadIdx.x >> 5;
@@ -55,50 +62,50 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const ScanParams p) {
   const int n_kc = (dim + KC - 1) / KC;
   const long long total_tiles = (long long)p.n_qt * (long long)p.n_ct;
 
-  for (int i = threadIdx.x; i < dim; i += THREADS) s_code[i] = p.code[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], CONSUMER_WARPS);
+      ptx::mbar_init(&empty_bar[s], L::CONSUMER_WARPS);
     }
     ptx::fence_mbar_init();
   }
   __syncthreads();
 
-  if (warp == CONSUMER_WARPS) {
-    // ------------------------------ producer warp ------------------------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const long long qt = tile / p.n_ct;
-        const long long ct = tile - qt * p.n_ct;
-        const float* csrc = p.packed + (size_t)ct * dim * (CW * TILE_C);
-        const float* qsrc = p.qpacked + (size_t)qt * dim * (QW * TILE_Q);
-        for (int kc = 0; kc < n_kc; ++kc) {
-          const int kn = min(KC, dim - kc * KC);
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-          float* sc = stage_base + (size_t)stage * L::STAGE_FLOATS;
-          float* sq = sc + L::C_FLOATS;
-          const uint32_t cbytes = (uint32_t)kn * CW * TILE_C * sizeof(float);
-          const uint32_t qbytes = (uint32_t)kn * QW * TILE_Q * sizeof(float);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], cbytes + qbytes);
-          ptx::bulk_g2s(sc, csrc + (size_t)kc * KC * (CW * TILE_C), cbytes, &full_bar[stage]);
-          ptx::bulk_g2s(sq, qsrc + (size_t)kc * KC * (QW * TILE_Q), qbytes, &full_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-    return;
-  }
+  // ---- producer duty: one elected thread (lane 0 of the last warp) keeps the ring STAGES-1
+  // stages ahead of the consumers.  Stage number g counts (tile, k-chunk) pairs of this CTA.
+  const long long my_tiles = (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const long long total_stages = my_tiles * n_kc;
+  const bool is_producer = (warp == L::CONSUMER_WARPS - 1) && (lane == 0);
+  long long prod_tile = blockIdx.x;  // tile of the next stage to issue
+  int prod_kc = 0;
+  long long prod_g = 0;
+  auto issue_next = [&]() {
+    const int slot = (int)(prod_g % STAGES);
+    const long long use = prod_g / STAGES;
+    if (use > 0) ptx::mbar_wait(&empty_bar[slot], (uint32_t)((use - 1) & 1));
+    const long long qt = prod_tile / p.n_ct;
+    const long long ct = prod_tile - qt * p.n_ct;
+    const int kn = min(KC, dim - prod_kc * KC);
+    float* sc = stage_base + (size_t)slot * L::STAGE_FLOATS;
+    float* sq = sc + L::C_FLOATS;
+    const uint32_t cbytes = (uint32_t)kn * CW * TILE_C * sizeof(float);
+    const uint32_t qbytes = (uint32_t)kn * QW * TILE_Q * sizeof(float);
+    ptx::mbar_arrive_expect_tx(&full_bar[slot], cbytes + qbytes);
+    ptx::bulk_g2s(sc, p.packed + ((size_t)ct * dim + (size_t)prod_kc * KC) * (CW * TILE_C), cbytes,
+                  &full_bar[slot]);
+    ptx::bulk_g2s(sq, p.qpacked + ((size_t)qt * dim + (size_t)prod_kc * KC) * (QW * TILE_Q), qbytes,
+                  &full_bar[slot]);
+    ++prod_g;
+    if (++prod_kc == n_kc) { prod_kc = 0; prod_tile += gridDim.x; }
+  };
+  if (is_producer)
+    for (int g = 0; g < STAGES - 1 && prod_g < total_stages; ++g) issue_next();
 
   // -------------------------------- consumer warps --------------------------------
-  const int wq = warp >> 1, wc = warp & 1;  // 4 x 2 warps over the 64 x 128 CTA tile
-  const int tq = lane >> 3, tc = lane & 7;  // 4 x 8 threads over the 16 x 64 warp tile
+  const int wq = warp / L::WARPS_C, wc = warp % L::WARPS_C;
+  const int tq = lane >> 3, tc = lane & 7;  // 4 x 8 threads per warp
   const int q_off = wq * 16 + tq * TQ;
-  const int c_off0 = wc * 64 + tc * 4;
-  const int c_off1 = c_off0 + 32;
-  constexpr uint8_t FAST = fast_code<EL>();
+  const int c_off = wc * (32 * G) + tc * 4;  // group g adds 32 * g
 
   int stage = 0;
   uint32_t phase = 0;
@@ -140,49 +147,88 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const ScanParams p) {
 
     for (int kc = 0; kc < n_kc; ++kc) {
       const int kn = min(KC, dim - kc * KC);
+      const uint32_t special = p.mask[kc];
+      if (is_producer && prod_g < total_stages) issue_next();
       ptx::mbar_wait(&full_bar[stage], phase);
-      const float* sc = stage_base + (size_t)stage * L::STAGE_FLOATS;
-      const float* sq = sc + L::C_FLOATS;
-      const uint8_t* codes = s_code + kc * KC;
-#pragma unroll 2
-      for (int kk = 0; kk < kn; ++kk) {
-        float qv[QW][TQ];
-        float cv[CW][TC];
+      const float* sc = stage_base + (size_t)stage * L::STAGE_FLOATS + c_off;
+      const float* sq = stage_base + (size_t)stage * L::STAGE_FLOATS + L::C_FLOATS + q_off;
+
+      auto load_operands = [&](int kk, float (&qv)[QW][TQ], float (&cv)[CW][TC]) {
 #pragma unroll
         for (int w = 0; w < QW; ++w) {
-          const float4 v = *reinterpret_cast<const float4*>(sq + (kk * QW + w) * TILE_Q + q_off);
+          const float4 v = *reinterpret_cast<const float4*>(sq + (kk * QW + w) * TILE_Q);
           qv[w][0] = v.x; qv[w][1] = v.y; qv[w][2] = v.z; qv[w][3] = v.w;
         }
 #pragma unroll
-        for (int w = 0; w < CW; ++w) {
-          const float4 v0 = *reinterpret_cast<const float4*>(sc + (kk * CW + w) * TILE_C + c_off0);
-          const float4 v1 = *reinterpret_cast<const float4*>(sc + (kk * CW + w) * TILE_C + c_off1);
-          cv[w][0] = v0.x; cv[w][1] = v0.y; cv[w][2] = v0.z; cv[w][3] = v0.w;
-          cv[w][4] = v1.x; cv[w][5] = v1.y; cv[w][6] = v1.z; cv[w][7] = v1.w;
-        }
-        const uint8_t code = codes[kk];
-        if (code == FAST) {
+        for (int w = 0; w < CW; ++w)
 #pragma unroll
-          for (int i = 0; i < TQ; ++i)
-#pragma unroll
-            for (int j = 0; j < TC; ++j)
-              acc_step_fast<EL>(acc[i][j], qv[0][i], qv[QW - 1][i], cv[0][j], cv[CW - 1][j]);
+          for (int g = 0; g < G; ++g) {
+            const float4 v = *reinterpret_cast<const float4*>(sc + (kk * CW + w) * TILE_C + 32 * g);
+            cv[w][4 * g + 0] = v.x; cv[w][4 * g + 1] = v.y;
+            cv[w][4 * g + 2] = v.z; cv[w][4 * g + 3] = v.w;
+          }
+      };
+
+      // One schedule position: ordinary element step for all pairs, then -- only if the
+      // position is flagged in the stage mask -- the combine steps, each behind a uniform test.
+      // Operands of the NEXT position are fetched before the current one is consumed (explicit
+      // two-deep register pipeline; the loop is unrolled by two so no register copies remain).
+#define KGE_FOR_PAIRS(stmt)                       \
+  _Pragma("unroll") for (int i = 0; i < TQ; ++i)  \
+  _Pragma("unroll") for (int c = 0; c < TC; ++c) { stmt; }
+      auto consume = [&](int kk, float (&qv)[QW][TQ], float (&cv)[CW][TC]) {
+        if (!((special >> kk) & 1u)) {
+          KGE_FOR_PAIRS(acc_step_fast<EL>(acc[i][c], qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c]))
         } else {
-#pragma unroll
-          for (int i = 0; i < TQ; ++i)
-#pragma unroll
-            for (int j = 0; j < TC; ++j)
-              acc_step<EL, CASC>(acc[i][j], code, qv[0][i], qv[QW - 1][i], cv[0][j],
-                                 cv[CW - 1][j]);
+          const uint8_t code = p.code[kc * KC + kk];
+          const uint8_t mode = code & SC_MODE_MASK;
+          if (mode == SC_MODE_A) {
+            KGE_FOR_PAIRS(acc_elem_mode<EL>(acc[i][c], SC_MODE_A, qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c]))
+          } else if (mode == SC_MODE_T) {
+            KGE_FOR_PAIRS(acc_elem_mode<EL>(acc[i][c], SC_MODE_T, qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c]))
+          } else {
+            KGE_FOR_PAIRS(acc_elem_mode<EL>(acc[i][c], SC_MODE_T_FMA, qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c]))
+          }
+          if constexpr (CASC) {
+            if (code & SC_CASC1) { KGE_FOR_PAIRS(acc_casc1(acc[i][c])) }
+            if (code & SC_FOLD1) { KGE_FOR_PAIRS(acc_fold1(acc[i][c])) }
+          }
+          if (code & SC_P_SET) { KGE_FOR_PAIRS(acc_p_set(acc[i][c])) }
+          if (code & SC_P_ADD) { KGE_FOR_PAIRS(acc_p_add(acc[i][c])) }
+          if (code & SC_T_ADD_P) { KGE_FOR_PAIRS(acc_t_add_p(acc[i][c])) }
+          if (code & SC_T_ADD_A) { KGE_FOR_PAIRS(acc_t_add_a(acc[i][c])) }
+        }
+      };
+      {
+        // run-length form: branch-free unrolled runs of ordinary positions between flagged ones
+        uint32_t m = special;
+        int kk = 0;
+        while (kk < kn) {
+          const int run = m ? min(kn - kk, __ffs(m) - 1) : kn - kk;
+#pragma unroll 4
+          for (int j = 0; j < run; ++j) {
+            float qv[QW][TQ], cv[CW][TC];
+            load_operands(kk + j, qv, cv);
+            KGE_FOR_PAIRS(acc_step_fast<EL>(acc[i][c], qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c]))
+          }
+          kk += run;
+          if (kk < kn) {
+            float qv[QW][TQ], cv[CW][TC];
+            load_operands(kk, qv, cv);
+            consume(kk, qv, cv);  // flagged by construction
+            ++kk;
+            m = (run + 1 >= 32) ? 0u : (m >> (run + 1));
+          }
         }
       }
+#undef KGE_FOR_PAIRS
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
 
-    // ---- epilogue: finish the 32 scores, count or store ----
-    const long long c_base = ct * TILE_C;
+    // ---- epilogue: finish the scores, count or store ----
+    const long long c_base = ct * TILE_C + c_off;
     if (p.scores != nullptr) {
 #pragma unroll
       for (int i = 0; i < TQ; ++i) {
@@ -191,15 +237,15 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const ScanParams p) {
         float* row = p.scores + (size_t)q * p.n_rows;
 #pragma unroll
         for (int j = 0; j < TC; ++j) {
-          const long long c = c_base + (j < 4 ? c_off0 + j : c_off1 + j - 4);
+          const long long c = c_base + 32 * (j / 4) + (j % 4);
           if (c < p.n_rows) row[c] = acc_finish<EL>(acc[i][j]);
         }
       }
     } else {
-      const bool edge = (c_base + TILE_C > p.n_rows);
+      const bool edge = (ct * TILE_C + TILE_C > p.n_rows);
 #pragma unroll
       for (int j = 0; j < TC; ++j) {
-        const long long c = c_base + (j < 4 ? c_off0 + j : c_off1 + j - 4);
+        const long long c = c_base + 32 * (j / 4) + (j % 4);
         const bool valid = !edge || (c < p.n_rows);
 #pragma unroll
         for (int i = 0; i < TQ; ++i) {
@@ -212,11 +258,20 @@ __global__ void __launch_bounds__(THREADS, 1) scan_kernel(const ScanParams p) {
   flush_counts(cur_qt);
 }
 
-template <int EL, bool CASC>
-cudaError_t launch_one(const ScanParams& p, cudaStream_t stream) {
-  using L = StageLayout<EL>;
+template <int EL, bool CASC, int G>
+cudaError_t launch_one(ScanParams& p, cudaStream_t stream) {
+  using L = Cfg<EL, G>;
+  // stage masks: which positions are NOT the plain "accumulate" code of this reduction kind
+  constexpr uint8_t FAST = ElemTraits<EL>::RED == RED_SEQ ? SC_MODE_T : SC_MODE_A;
+  const int n_kc = (p.dim + KC - 1) / KC;
+  for (int kc = 0; kc < n_kc; ++kc) {
+    uint32_t m = 0;
+    for (int kk = 0; kk < KC && kc * KC + kk < p.dim; ++kk)
+      if (p.code[kc * KC + kk] != FAST) m |= 1u << kk;
+    p.mask[kc] = m;
+  }
   static bool configured = false;  // benign race: attribute set is idempotent
-  auto kern = scan_kernel<EL, CASC>;
+  auto kern = scan_kernel<EL, CASC, G>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)L::SMEM_BYTES);
@@ -231,27 +286,36 @@ cudaError_t launch_one(const ScanParams& p, cudaStream_t stream) {
   const long long total = (long long)p.n_qt * (long long)p.n_ct;
   if (total <= 0) return cudaSuccess;
   const int grid = (int)(total < sms ? total : sms);
-  kern<<<grid, THREADS, L::SMEM_BYTES, stream>>>(p);
+  kern<<<grid, L::THREADS, L::SMEM_BYTES, stream>>>(p);
   return cudaGetLastError();
+}
+
+template <int G>
+cudaError_t launch_scan_g(int el, bool cascade, ScanParams& p, cudaStream_t stream) {
+  switch (el) {
+    case EL_DOT1:
+      return cascade ? launch_one<EL_DOT1, true, G>(p, stream) : launch_one<EL_DOT1, false, G>(p, stream);
+    case EL_DOT2:
+      return cascade ? launch_one<EL_DOT2, true, G>(p, stream) : launch_one<EL_DOT2, false, G>(p, stream);
+    case EL_ROT:
+      return cascade ? launch_one<EL_ROT, true, G>(p, stream) : launch_one<EL_ROT, false, G>(p, stream);
+    case EL_L1_TAIL: return launch_one<EL_L1_TAIL, false, G>(p, stream);
+    case EL_L1_HEAD: return launch_one<EL_L1_HEAD, false, G>(p, stream);
+    case EL_L2_TAIL: return launch_one<EL_L2_TAIL, false, G>(p, stream);
+    case EL_L2_HEAD: return launch_one<EL_L2_HEAD, false, G>(p, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace
 
-cudaError_t launch_scan(int el, bool cascade, const ScanParams& p, cudaStream_t stream) {
-  if (p.dim < 1 || p.dim > CODE_BYTES - 1) return cudaErrorInvalidValue;
-  switch (el) {
-    case EL_DOT1:
-      return cascade ? launch_one<EL_DOT1, true>(p, stream) : launch_one<EL_DOT1, false>(p, stream);
-    case EL_DOT2:
-      return cascade ? launch_one<EL_DOT2, true>(p, stream) : launch_one<EL_DOT2, false>(p, stream);
-    case EL_ROT:
-      return cascade ? launch_one<EL_ROT, true>(p, stream) : launch_one<EL_ROT, false>(p, stream);
-    case EL_L1_TAIL: return launch_one<EL_L1_TAIL, false>(p, stream);
-    case EL_L1_HEAD: return launch_one<EL_L1_HEAD, false>(p, stream);
-    case EL_L2_TAIL: return launch_one<EL_L2_TAIL, false>(p, stream);
-    case EL_L2_HEAD: return launch_one<EL_L2_HEAD, false>(p, stream);
-    default: return cudaErrorInvalidValue;
-  }
+cudaError_t launch_scan(int el, bool cascade, const ScanParams& p_in, cudaStream_t stream) {
+  if (p_in.dim < 1 || p_in.dim > SCAN_MAX_DIM - 1 || p_in.code_host == nullptr)
+    return cudaErrorInvalidValue;
+  ScanParams p = p_in;
+  memcpy(p.code, p_in.code_host, (size_t)p.dim);
+  // Thread tile 4 x 4 pairs, 16 warps per CTA (measured best on B200; G = 2 gives 4 x 8 / 8 warps).
+  return launch_scan_g<1>(el, cascade, p, stream);
 }
 
 }  // namespace kge

@@ -159,7 +159,7 @@ class CudaEngine:
         return ws  # keep alive until the caller synchronises / reuses the stream
 
     def score_all(self, spec, packed, side, hrows, trows, r_idx):
-        n = r_idx.shape[0]
+        n = hrows.shape[0]
         dev = hrows.device
         scores = torch.empty((n, spec.n_rows), dtype=torch.float32, device=dev)
         ws_bytes = self.lib.kge_rank_workspace_bytes(spec.code, side, spec.dim, n)
