@@ -180,6 +180,68 @@ typedef struct {
 } kge_score_all_args_t;
 int kge_score_all(const kge_score_all_args_t* args);
 
+/* ---- training side ----------------------------------------------------------------------
+ * Tables as in ModelSpec order: ent0/ent1 entity planes (n_ent, dim), rel0/rel1 relation
+ * planes (n_rel, dim) -- RESCAL: rel0 = rel_mat (n_rel, dim*dim); RotatE: (cos, sin) of the
+ * phases.  Gradient tables have the same shapes, are zero-initialised by the caller and are
+ * accumulated into with atomics (dense gradients, as nn.Embedding produces). */
+typedef struct {
+  int32_t model, dim;
+  const float* ent0; const float* ent1; const float* rel0; const float* rel1;
+} kge_tables_t;
+typedef struct {
+  float* ent0; float* ent1; float* rel0; float* rel1;
+} kge_grads_t;
+
+/* Model.scoring_function (models/translation.py:69-81, models/bilinear.py:60-71, 188-199,
+ * 460-473): scores[i] of triple (h[i], r[i], t[i]); TransE / DistMult / RESCAL L2-normalise
+ * the gathered entity rows first (eps 1e-12). */
+int kge_score_triples_fwd(const kge_tables_t* tb, const int64_t* h, const int64_t* t,
+                          const int64_t* r, int64_t n, float* scores, void* stream);
+/* accumulates d(sum_i grad_scores[i] * scores[i]) / d(tables) into g */
+int kge_score_triples_bwd(const kge_tables_t* tb, const kge_grads_t* g, const int64_t* h,
+                          const int64_t* t, const int64_t* r, int64_t n, const float* grad_scores,
+                          void* stream);
+
+/* BernoulliNegativeSampler.corrupt_batch (sampling.py:278-327): nh/nt of length b*n_neg laid
+ * out as n_neg blocks of the batch; negative j of fact i corrupts the head with probability
+ * bern_probs[r[i]] else the tail, replacement uniform on [1, n_ent).  Counter-based RNG
+ * (Philox4x32-10, key = seed, counter = (j*b+i, offset)). */
+int kge_corrupt_batch(const int64_t* h, const int64_t* t, const int64_t* r, int64_t b,
+                      int32_t n_neg, const float* bern_probs, int64_t n_ent, uint64_t seed,
+                      uint64_t offset, int64_t* nh, int64_t* nt, void* stream);
+
+/* MarginLoss (utils/losses.py:12-44): loss += sum_i max(0, margin - pos[i] + neg[i]). */
+int kge_margin_loss_fwd(const float* pos, const float* neg, int64_t n, float margin, float* loss,
+                        void* stream);
+int kge_margin_loss_bwd(const float* pos, const float* neg, int64_t n, float margin,
+                        const float* grad_loss, float* grad_pos, float* grad_neg, void* stream);
+
+/* Fused training step = corrupt_batch + Model.forward (models/interfaces.py:39-82) +
+ * MarginLoss in one kernel: one warp per positive triple scores it and its n_neg negatives;
+ * no (b*n_neg) index or score tensor is materialised unless the optional outputs are given.
+ * Negatives: nh/nt if non-NULL (deterministic mode), else drawn in-kernel exactly as
+ * kge_corrupt_batch would with the same (seed, offset). */
+typedef struct {
+  kge_tables_t tb;
+  int32_t n_neg;
+  float margin;
+  int64_t b;
+  int64_t n_ent;
+  const int64_t* h; const int64_t* t; const int64_t* r;
+  const int64_t* nh; const int64_t* nt; /* optional external negatives */
+  const float* bern_probs;              /* required when nh == NULL */
+  uint64_t seed, offset;
+  float* loss;                          /* 1 float, += */
+  float* pos_out; float* neg_out;       /* optional */
+  int64_t* nh_out; int64_t* nt_out;     /* optional */
+  void* stream;
+} kge_margin_step_args_t;
+int kge_margin_step_fwd(const kge_margin_step_args_t* a);
+/* grad_loss: device pointer to the upstream gradient of the scalar loss */
+int kge_margin_step_bwd(const kge_margin_step_args_t* a, const kge_grads_t* g,
+                        const float* grad_loss);
+
 /* ---- measurement hook ------------------------------------------------------------------
  * When enabled, every dense-scan launch (the dominant kernel of kge_rank_side /
  * kge_score_all) is bracketed by CUDA events recorded on the launch stream.

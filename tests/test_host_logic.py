@@ -84,3 +84,28 @@ def test_evaluator_refuses_cpu_models_loudly():
         ev.evaluate(b_size=4, verbose=False)
     with pytest.raises(tk.NotYetEvaluatedError):
         ev.mrr()
+
+
+@pytest.mark.parametrize("case", ["toy_distmult", "syn_transe_l2"])
+def test_bernoulli_probs_match_golden(case):
+    """get_bernoulli_probs / evaluate_probabilities (host side) against the reference's values."""
+    import numpy as np
+    from torchkge_b200.sampling import BernoulliNegativeSampler
+    g = helpers.load_golden(case)
+    kg = tk.KnowledgeGraph(g["all_heads"], g["all_tails"], g["all_rels"], g["n_ent"], g["n_rel"],
+                           dict_of_heads={}, dict_of_tails={})
+    s = BernoulliNegativeSampler(kg, n_neg=3, seed=0)
+    assert s.bern_probs.dtype == torch.float32 and s.bern_probs.shape == (g["n_rel"],)
+    assert np.allclose(s.bern_probs.numpy(), g["raw"]["bern_probs"], rtol=0, atol=1e-7)
+    assert s.n_ent == g["n_ent"] and s.n_neg == 3
+
+
+def test_sampler_and_training_refuse_cpu_tensors():
+    h, t, r = helpers.random_graph(50, 3, 200, seed=1)
+    kg = tk.KnowledgeGraph(h, t, r, 50, 3, dict_of_heads={}, dict_of_tails={})
+    s = tk.BernoulliNegativeSampler(kg, seed=0)
+    with pytest.raises(_lib.KgeLibraryError):
+        s.corrupt_batch(h[:10], t[:10], r[:10])
+    m = tk.DistMultModel(8, 50, 3)
+    with pytest.raises(_lib.KgeLibraryError):
+        m.scoring_function(h[:10], t[:10], r[:10])

@@ -10,5 +10,7 @@ from .data import KnowledgeGraph  # noqa: F401
 from .models import (ComplExModel, DistMultModel, RESCALModel, RotatEModel,  # noqa: F401
                      TransEModel)
 from .evaluation import LinkPredictionEvaluator  # noqa: F401
+from .losses import MarginLoss  # noqa: F401
+from .sampling import BernoulliNegativeSampler  # noqa: F401
 
 __version__ = "0.1.0"

@@ -52,6 +52,29 @@ class ScoreAllArgs(ctypes.Structure):
     ]
 
 
+class Tables(ctypes.Structure):
+    """kge_tables_t"""
+    _fields_ = [("model", _c.c_int32), ("dim", _c.c_int32),
+                ("ent0", _p), ("ent1", _p), ("rel0", _p), ("rel1", _p)]
+
+
+class Grads(ctypes.Structure):
+    """kge_grads_t"""
+    _fields_ = [("ent0", _p), ("ent1", _p), ("rel0", _p), ("rel1", _p)]
+
+
+class MarginStepArgs(ctypes.Structure):
+    """kge_margin_step_args_t"""
+    _fields_ = [
+        ("tb", Tables), ("n_neg", _c.c_int32), ("margin", _c.c_float),
+        ("b", _c.c_int64), ("n_ent", _c.c_int64),
+        ("h", _p), ("t", _p), ("r", _p), ("nh", _p), ("nt", _p), ("bern_probs", _p),
+        ("seed", _c.c_uint64), ("offset", _c.c_uint64),
+        ("loss", _p), ("pos_out", _p), ("neg_out", _p), ("nh_out", _p), ("nt_out", _p),
+        ("stream", _p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/kge_b200.h declares
 SIGNATURES = {
     "kge_abi_version": (_c.c_int, []),
@@ -67,6 +90,15 @@ SIGNATURES = {
     "kge_rank_side": (_c.c_int, [_c.POINTER(RankArgs)]),
     "kge_finalize_ranks": (_c.c_int, [_p, _p, _c.c_int64, _p, _p, _p]),
     "kge_score_all": (_c.c_int, [_c.POINTER(ScoreAllArgs)]),
+    "kge_score_triples_fwd": (_c.c_int, [_c.POINTER(Tables), _p, _p, _p, _c.c_int64, _p, _p]),
+    "kge_score_triples_bwd": (_c.c_int, [_c.POINTER(Tables), _c.POINTER(Grads), _p, _p, _p,
+                                         _c.c_int64, _p, _p]),
+    "kge_corrupt_batch": (_c.c_int, [_p, _p, _p, _c.c_int64, _c.c_int32, _p, _c.c_int64,
+                                     _c.c_uint64, _c.c_uint64, _p, _p, _p]),
+    "kge_margin_loss_fwd": (_c.c_int, [_p, _p, _c.c_int64, _c.c_float, _p, _p]),
+    "kge_margin_loss_bwd": (_c.c_int, [_p, _p, _c.c_int64, _c.c_float, _p, _p, _p, _p]),
+    "kge_margin_step_fwd": (_c.c_int, [_c.POINTER(MarginStepArgs)]),
+    "kge_margin_step_bwd": (_c.c_int, [_c.POINTER(MarginStepArgs), _c.POINTER(Grads), _p]),
     "kge_scan_timing_enable": (_c.c_int, [_c.c_int]),
     "kge_scan_timing_read": (_c.c_int, [_c.POINTER(_c.c_int64), _c.POINTER(_c.c_double)]),
 }

@@ -9,6 +9,7 @@
 #include "../../include/kge_b200.h"
 #include "kernels.h"
 #include "schedule.h"
+#include "train.h"
 
 namespace {
 
@@ -317,6 +318,115 @@ int kge_score_all(const kge_score_all_args_t* a) {
   p.n_ct = (a->n_rows + kge::TILE_C - 1) / kge::TILE_C;
   p.n_qt = n_qt;
   KGE_CUDA_TRY(timed_scan(el, hs->s.has_cascade, p, st), "score scan");
+  return KGE_OK;
+}
+
+// ------------------------------------ training side ------------------------------------
+namespace {
+bool tables_ok(const kge_tables_t* tb) {
+  if (!tb || !tb->ent0 || !tb->rel0 || tb->dim < 1) return false;
+  if (tb->model < KGE_TRANSE_L1 || tb->model > KGE_ROTATE) return false;
+  if ((tb->model == KGE_COMPLEX || tb->model == KGE_ROTATE) && (!tb->ent1 || !tb->rel1)) return false;
+  return true;
+}
+bool grads_ok(const kge_tables_t* tb, const kge_grads_t* g) {
+  if (!g || !g->ent0 || !g->rel0) return false;
+  if ((tb->model == KGE_COMPLEX || tb->model == KGE_ROTATE) && (!g->ent1 || !g->rel1)) return false;
+  return true;
+}
+kge::TrainTables to_tables(const kge_tables_t* tb) {
+  return kge::TrainTables{tb->ent0, tb->ent1, tb->rel0, tb->rel1};
+}
+kge::TrainGrads to_grads(const kge_grads_t* g) { return kge::TrainGrads{g->ent0, g->ent1, g->rel0, g->rel1}; }
+kge::MarginStepParams to_step(const kge_margin_step_args_t* a) {
+  kge::MarginStepParams p;
+  p.model = a->tb.model; p.dim = a->tb.dim; p.n_neg = a->n_neg; p.margin = a->margin;
+  p.b = a->b; p.n_ent = a->n_ent; p.tb = to_tables(&a->tb);
+  p.h = a->h; p.t = a->t; p.r = a->r; p.nh = a->nh; p.nt = a->nt; p.probs = a->bern_probs;
+  p.seed = a->seed; p.offset = a->offset; p.loss = a->loss; p.pos_out = a->pos_out;
+  p.neg_out = a->neg_out; p.nh_out = a->nh_out; p.nt_out = a->nt_out;
+  return p;
+}
+bool step_ok(const kge_margin_step_args_t* a) {
+  if (!a || !tables_ok(&a->tb) || a->b < 0 || a->n_neg < 1 || !a->loss) return false;
+  if (a->b > 0 && (!a->h || !a->t || !a->r)) return false;
+  if ((a->nh == nullptr) != (a->nt == nullptr)) return false;
+  if (!a->nh && !a->bern_probs) return false;
+  if ((a->nh_out == nullptr) != (a->nt_out == nullptr)) return false;
+  return true;
+}
+}  // namespace
+
+int kge_score_triples_fwd(const kge_tables_t* tb, const int64_t* h, const int64_t* t,
+                          const int64_t* r, int64_t n, float* scores, void* stream) {
+  if (!tables_ok(tb)) return fail(KGE_ERR_ARG, "kge_score_triples_fwd: bad tables");
+  if (n == 0) return KGE_OK;
+  if (n < 0 || !h || !t || !r || !scores) return fail(KGE_ERR_ARG, "kge_score_triples_fwd: null pointer");
+  KGE_CUDA_TRY(kge::launch_score_triples_fwd(tb->model, tb->dim, to_tables(tb), h, t, r, n, scores,
+                                             static_cast<cudaStream_t>(stream)),
+               "score_triples_fwd");
+  return KGE_OK;
+}
+
+int kge_score_triples_bwd(const kge_tables_t* tb, const kge_grads_t* g, const int64_t* h,
+                          const int64_t* t, const int64_t* r, int64_t n, const float* grad_scores,
+                          void* stream) {
+  if (!tables_ok(tb) || !grads_ok(tb, g)) return fail(KGE_ERR_ARG, "kge_score_triples_bwd: bad tables");
+  if (n == 0) return KGE_OK;
+  if (n < 0 || !h || !t || !r || !grad_scores)
+    return fail(KGE_ERR_ARG, "kge_score_triples_bwd: null pointer");
+  KGE_CUDA_TRY(kge::launch_score_triples_bwd(tb->model, tb->dim, to_tables(tb), to_grads(g), h, t, r, n,
+                                             grad_scores, static_cast<cudaStream_t>(stream)),
+               "score_triples_bwd");
+  return KGE_OK;
+}
+
+int kge_corrupt_batch(const int64_t* h, const int64_t* t, const int64_t* r, int64_t b,
+                      int32_t n_neg, const float* bern_probs, int64_t n_ent, uint64_t seed,
+                      uint64_t offset, int64_t* nh, int64_t* nt, void* stream) {
+  if (b == 0) return KGE_OK;
+  if (b < 0 || n_neg < 1 || n_ent < 1 || !h || !t || !r || !bern_probs || !nh || !nt)
+    return fail(KGE_ERR_ARG, "kge_corrupt_batch: bad argument");
+  KGE_CUDA_TRY(kge::launch_corrupt_batch(h, t, r, b, n_neg, bern_probs, n_ent, seed, offset, nh, nt,
+                                         static_cast<cudaStream_t>(stream)),
+               "corrupt_batch");
+  return KGE_OK;
+}
+
+int kge_margin_loss_fwd(const float* pos, const float* neg, int64_t n, float margin, float* loss,
+                        void* stream) {
+  if (n == 0) return KGE_OK;
+  if (n < 0 || !pos || !neg || !loss) return fail(KGE_ERR_ARG, "kge_margin_loss_fwd: bad argument");
+  KGE_CUDA_TRY(kge::launch_margin_loss_fwd(pos, neg, n, margin, loss, static_cast<cudaStream_t>(stream)),
+               "margin_loss_fwd");
+  return KGE_OK;
+}
+
+int kge_margin_loss_bwd(const float* pos, const float* neg, int64_t n, float margin,
+                        const float* grad_loss, float* grad_pos, float* grad_neg, void* stream) {
+  if (n == 0) return KGE_OK;
+  if (n < 0 || !pos || !neg || !grad_loss || !grad_pos || !grad_neg)
+    return fail(KGE_ERR_ARG, "kge_margin_loss_bwd: bad argument");
+  KGE_CUDA_TRY(kge::launch_margin_loss_bwd(pos, neg, n, margin, grad_loss, grad_pos, grad_neg,
+                                           static_cast<cudaStream_t>(stream)),
+               "margin_loss_bwd");
+  return KGE_OK;
+}
+
+int kge_margin_step_fwd(const kge_margin_step_args_t* a) {
+  if (!step_ok(a)) return fail(KGE_ERR_ARG, "kge_margin_step_fwd: bad argument");
+  KGE_CUDA_TRY(kge::launch_margin_step_fwd(to_step(a), static_cast<cudaStream_t>(a->stream)),
+               "margin_step_fwd");
+  return KGE_OK;
+}
+
+int kge_margin_step_bwd(const kge_margin_step_args_t* a, const kge_grads_t* g,
+                        const float* grad_loss) {
+  if (!step_ok(a) || !grads_ok(&a->tb, g) || !grad_loss)
+    return fail(KGE_ERR_ARG, "kge_margin_step_bwd: bad argument");
+  KGE_CUDA_TRY(kge::launch_margin_step_bwd(to_step(a), to_grads(g), grad_loss,
+                                           static_cast<cudaStream_t>(a->stream)),
+               "margin_step_bwd");
   return KGE_OK;
 }
 

@@ -1,0 +1,412 @@
+// Training-side kernels: per-triple scoring (Model.scoring_function), Bernoulli corruption
+// (BernoulliNegativeSampler.corrupt_batch), margin loss (MarginLoss) and the fused
+// sample + score + hinge step, each with its backward.
+//
+// Reference bodies replaced: models/translation.py:69-81, models/bilinear.py:60-71, 188-199,
+// 460-473, models/interfaces.py:39-82, sampling.py:278-327, utils/losses.py:12-44.
+//
+// These paths are gather-bound (a few 4d-byte rows per triple, random rows): one warp owns
+// one triple (or one positive with all its negatives), lanes stride over the embedding
+// index so every row read is a run of coalesced 128-B segments, and the per-triple
+// reductions (L2 norms, dot products) are warp-shuffle trees.  Parity with the reference is
+// by tolerance here (1e-5 relative on scores / loss), so fused
+// multiply-adds and tree reductions are allowed, unlike in the ranking kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/kge_b200.h"
+#include "train.h"
+
+namespace kge {
+
+namespace {
+
+constexpr float NORM_EPS = 1e-12f;  // torch.nn.functional.normalize default eps
+constexpr int WARPS_PER_BLOCK = 4;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ bool model_normalises(int model) {
+  return model == KGE_TRANSE_L1 || model == KGE_TRANSE_L2 || model == KGE_DISTMULT ||
+         model == KGE_RESCAL;
+}
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter = (idx, offset), key = seed -------------
+__device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t offset, uint64_t idx) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32);
+  uint32_t c2 = (uint32_t)offset, c3 = (uint32_t)(offset >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// One corrupted triple: Bernoulli(p_r) decides head vs tail, the replacement is uniform on
+// [1, n_ent) -- entity 0 is never drawn and true triples are not rejected, as in
+// sampling.py:318-325.
+__device__ __forceinline__ void corrupt_one(uint64_t seed, uint64_t offset, uint64_t idx, float p,
+                                            long long n_ent, long long h, long long t,
+                                            long long* nh, long long* nt) {
+  const uint4 rnd = philox4x32(seed, offset, idx);
+  const float u = (rnd.x >> 8) * (1.0f / 16777216.0f);  // [0, 1)
+  const long long span = n_ent - 1;
+  long long e = 1;
+  if (span > 0) e = 1 + (long long)(((unsigned long long)rnd.y * (unsigned long long)span) >> 32);
+  const bool head = u < p;
+  *nh = head ? e : h;
+  *nt = head ? t : e;
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-lane view of one triple.  Lane l owns embedding indices l, l+32, ...; `cnt` of them.
+// ------------------------------------------------------------------------------------------
+struct RowPtrs {
+  const float* h0; const float* h1;  // head planes
+  const float* t0; const float* t1;  // tail planes
+  const float* r0; const float* r1;  // relation planes (RESCAL: r0 = matrix)
+};
+
+__device__ __forceinline__ float inv_norm_of(const float* row, int dim, int lane) {
+  float s = 0.f;
+  for (int k = lane; k < dim; k += 32) { const float v = row[k]; s = fmaf(v, v, s); }
+  s = warp_sum(s);
+  return 1.0f / fmaxf(sqrtf(s), NORM_EPS);
+}
+
+// score of one triple; all lanes return the same value
+__device__ float triple_score(int model, int dim, const RowPtrs& p, int lane, float* inv_h_out,
+                              float* inv_t_out) {
+  float inv_h = 1.f, inv_t = 1.f;
+  if (model_normalises(model)) {
+    inv_h = inv_norm_of(p.h0, dim, lane);
+    inv_t = inv_norm_of(p.t0, dim, lane);
+  }
+  if (inv_h_out) *inv_h_out = inv_h;
+  if (inv_t_out) *inv_t_out = inv_t;
+  float s = 0.f;
+  switch (model) {
+    case KGE_TRANSE_L1:
+      for (int k = lane; k < dim; k += 32) s += fabsf(p.h0[k] * inv_h + p.r0[k] - p.t0[k] * inv_t);
+      return -warp_sum(s);
+    case KGE_TRANSE_L2:
+      for (int k = lane; k < dim; k += 32) {
+        const float x = p.h0[k] * inv_h + p.r0[k] - p.t0[k] * inv_t;
+        s = fmaf(x, x, s);
+      }
+      return -warp_sum(s);
+    case KGE_DISTMULT:
+      for (int k = lane; k < dim; k += 32) s = fmaf(p.h0[k] * inv_h * p.r0[k], p.t0[k] * inv_t, s);
+      return warp_sum(s);
+    case KGE_RESCAL:
+      // s = sum_j (sum_i h_i M_ij) t_j ; lanes stride over j so M rows are read coalesced
+      for (int j = lane; j < dim; j += 32) {
+        float q = 0.f;
+        for (int i = 0; i < dim; ++i) q = fmaf(p.h0[i] * inv_h, p.r0[(size_t)i * dim + j], q);
+        s = fmaf(q, p.t0[j] * inv_t, s);
+      }
+      return warp_sum(s);
+    case KGE_COMPLEX:
+      for (int k = lane; k < dim; k += 32) {
+        const float rh = p.h0[k], ih = p.h1[k], rt = p.t0[k], it = p.t1[k], rr = p.r0[k], ir = p.r1[k];
+        s += rh * (rr * rt + ir * it) + ih * (rr * it - ir * rt);
+      }
+      return warp_sum(s);
+    case KGE_ROTATE:
+      for (int k = lane; k < dim; k += 32) {
+        const float rh = p.h0[k], ih = p.h1[k], rt = p.t0[k], it = p.t1[k], rr = p.r0[k], ir = p.r1[k];
+        const float a = rh * rr - ih * ir - rt, b = rh * ir + ih * rr - it;
+        s += sqrtf(a * a + b * b);
+      }
+      return -warp_sum(s);
+    default: return 0.f;
+  }
+}
+
+__device__ __forceinline__ RowPtrs make_rows(int model, int dim, const TrainTables& tb, long long h,
+                                             long long t, long long r) {
+  RowPtrs p;
+  p.h0 = tb.ent0 + (size_t)h * dim;
+  p.t0 = tb.ent0 + (size_t)t * dim;
+  p.h1 = tb.ent1 ? tb.ent1 + (size_t)h * dim : nullptr;
+  p.t1 = tb.ent1 ? tb.ent1 + (size_t)t * dim : nullptr;
+  const size_t rstride = model == KGE_RESCAL ? (size_t)dim * dim : (size_t)dim;
+  p.r0 = tb.rel0 + (size_t)r * rstride;
+  p.r1 = tb.rel1 ? tb.rel1 + (size_t)r * rstride : nullptr;
+  return p;
+}
+
+// Gradient of one triple's score, scaled by g, scattered into the dense gradient tables.
+// Through F.normalize:  d/dh = (G - h~ (h~ . G)) / max(|h|, eps)  with G = dscore/dh~.
+__device__ void triple_backward(int model, int dim, const RowPtrs& p, const TrainGrads& gr,
+                                long long h, long long t, long long r, float g, int lane) {
+  if (g == 0.f) return;
+  float* gh0 = gr.ent0 + (size_t)h * dim;
+  float* gt0 = gr.ent0 + (size_t)t * dim;
+  const size_t rstride = model == KGE_RESCAL ? (size_t)dim * dim : (size_t)dim;
+  float* gr0 = gr.rel0 + (size_t)r * rstride;
+  if (model == KGE_COMPLEX || model == KGE_ROTATE) {
+    float* gh1 = gr.ent1 + (size_t)h * dim;
+    float* gt1 = gr.ent1 + (size_t)t * dim;
+    float* gr1 = gr.rel1 + (size_t)r * dim;
+    for (int k = lane; k < dim; k += 32) {
+      const float rh = p.h0[k], ih = p.h1[k], rt = p.t0[k], it = p.t1[k], rr = p.r0[k], ir = p.r1[k];
+      float d_rh, d_ih, d_rt, d_it, d_rr, d_ir;
+      if (model == KGE_COMPLEX) {
+        d_rh = rr * rt + ir * it; d_ih = rr * it - ir * rt;
+        d_rt = rh * rr - ih * ir; d_it = rh * ir + ih * rr;
+        d_rr = rh * rt + ih * it; d_ir = rh * it - ih * rt;
+      } else {
+        const float a = rh * rr - ih * ir - rt, b = rh * ir + ih * rr - it;
+        const float m = sqrtf(a * a + b * b);
+        const float da = m > 0.f ? -a / m : 0.f, db = m > 0.f ? -b / m : 0.f;
+        d_rh = da * rr + db * ir; d_ih = -da * ir + db * rr;
+        d_rt = -da; d_it = -db;
+        d_rr = da * rh + db * ih; d_ir = -da * ih + db * rh;
+      }
+      atomicAdd(gh0 + k, g * d_rh); atomicAdd(gh1 + k, g * d_ih);
+      atomicAdd(gt0 + k, g * d_rt); atomicAdd(gt1 + k, g * d_it);
+      atomicAdd(gr0 + k, g * d_rr); atomicAdd(gr1 + k, g * d_ir);
+    }
+    return;
+  }
+  // normalising models
+  const float inv_h = inv_norm_of(p.h0, dim, lane), inv_t = inv_norm_of(p.t0, dim, lane);
+  // pass 1: G . h~ and G . t~
+  float dot_h = 0.f, dot_t = 0.f;
+  for (int k = lane; k < dim; k += 32) {
+    const float hn = p.h0[k] * inv_h, tn = p.t0[k] * inv_t;
+    float Gh, Gt;
+    if (model == KGE_DISTMULT) {
+      Gh = p.r0[k] * tn; Gt = hn * p.r0[k];
+    } else if (model == KGE_RESCAL) {
+      float a = 0.f, b = 0.f;  // Gh_k = sum_j M_kj t_j ; Gt_k = sum_i h_i M_ik
+      for (int j = 0; j < dim; ++j) {
+        a = fmaf(p.r0[(size_t)k * dim + j], p.t0[j] * inv_t, a);
+        b = fmaf(p.h0[j] * inv_h, p.r0[(size_t)j * dim + k], b);
+      }
+      Gh = a; Gt = b;
+    } else {
+      const float x = hn + p.r0[k] - tn;
+      const float dx = model == KGE_TRANSE_L2 ? -2.f * x : (x > 0.f ? -1.f : (x < 0.f ? 1.f : 0.f));
+      Gh = dx; Gt = -dx;
+    }
+    dot_h = fmaf(Gh, hn, dot_h); dot_t = fmaf(Gt, tn, dot_t);
+  }
+  dot_h = warp_sum(dot_h); dot_t = warp_sum(dot_t);
+  // pass 2: scatter
+  for (int k = lane; k < dim; k += 32) {
+    const float hn = p.h0[k] * inv_h, tn = p.t0[k] * inv_t;
+    float Gh, Gt;
+    if (model == KGE_DISTMULT) {
+      Gh = p.r0[k] * tn; Gt = hn * p.r0[k];
+      atomicAdd(gr0 + k, g * hn * tn);
+    } else if (model == KGE_RESCAL) {
+      float a = 0.f, b = 0.f;
+      for (int j = 0; j < dim; ++j) {
+        a = fmaf(p.r0[(size_t)k * dim + j], p.t0[j] * inv_t, a);
+        b = fmaf(p.h0[j] * inv_h, p.r0[(size_t)j * dim + k], b);
+        atomicAdd(gr0 + (size_t)k * dim + j, g * hn * (p.t0[j] * inv_t));  // dM_kj = h_k t_j
+      }
+      Gh = a; Gt = b;
+    } else {
+      const float x = hn + p.r0[k] - tn;
+      const float dx = model == KGE_TRANSE_L2 ? -2.f * x : (x > 0.f ? -1.f : (x < 0.f ? 1.f : 0.f));
+      Gh = dx; Gt = -dx;
+      atomicAdd(gr0 + k, g * dx);
+    }
+    atomicAdd(gh0 + k, g * (Gh - hn * dot_h) * inv_h);
+    atomicAdd(gt0 + k, g * (Gt - tn * dot_t) * inv_t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void score_triples_fwd_kernel(int model, int dim, TrainTables tb,
+                                         const int64_t* __restrict__ h,
+                                         const int64_t* __restrict__ t,
+                                         const int64_t* __restrict__ r, long long n,
+                                         float* __restrict__ out) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const RowPtrs p = make_rows(model, dim, tb, h[w], t[w], r[w]);
+  const float s = triple_score(model, dim, p, lane, nullptr, nullptr);
+  if (lane == 0) out[w] = s;
+}
+
+__global__ void score_triples_bwd_kernel(int model, int dim, TrainTables tb, TrainGrads gr,
+                                         const int64_t* __restrict__ h,
+                                         const int64_t* __restrict__ t,
+                                         const int64_t* __restrict__ r, long long n,
+                                         const float* __restrict__ gout) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const long long hi = h[w], ti = t[w], ri = r[w];
+  const RowPtrs p = make_rows(model, dim, tb, hi, ti, ri);
+  triple_backward(model, dim, p, gr, hi, ti, ri, gout[w], lane);
+}
+
+__global__ void corrupt_batch_kernel(const int64_t* __restrict__ h, const int64_t* __restrict__ t,
+                                     const int64_t* __restrict__ r, long long b, int n_neg,
+                                     const float* __restrict__ probs, long long n_ent,
+                                     uint64_t seed, uint64_t offset, int64_t* __restrict__ nh,
+                                     int64_t* __restrict__ nt) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= b * n_neg) return;
+  const long long i = gid % b;  // layout: n_neg blocks of the batch (sampling.py:313-314)
+  long long a, c;
+  corrupt_one(seed, offset, (uint64_t)gid, probs[r[i]], n_ent, h[i], t[i], &a, &c);
+  nh[gid] = a; nt[gid] = c;
+}
+
+// Fused step, forward: one warp per positive triple.
+//   loss += sum_j max(0, margin - pos_i + neg_ij)         (MarginRankingLoss, target +1, sum)
+// Negatives come from (nh, nt) if given, else from Philox; optionally written out.
+__global__ void margin_step_fwd_kernel(MarginStepParams a) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= a.b) return;
+  const long long hi = a.h[w], ti = a.t[w], ri = a.r[w];
+  const RowPtrs pp = make_rows(a.model, a.dim, a.tb, hi, ti, ri);
+  const float pos = triple_score(a.model, a.dim, pp, lane, nullptr, nullptr);
+  if (lane == 0 && a.pos_out) a.pos_out[w] = pos;
+  const float p_head = a.nh ? 0.f : a.probs[ri];
+  float loss = 0.f;
+  for (int j = 0; j < a.n_neg; ++j) {
+    const long long idx = (long long)j * a.b + w;
+    long long nh, nt;
+    if (a.nh) { nh = a.nh[idx]; nt = a.nt[idx]; }
+    else corrupt_one(a.seed, a.offset, (uint64_t)idx, p_head, a.n_ent, hi, ti, &nh, &nt);
+    const RowPtrs pn = make_rows(a.model, a.dim, a.tb, nh, nt, ri);
+    const float neg = triple_score(a.model, a.dim, pn, lane, nullptr, nullptr);
+    if (lane == 0) {
+      if (a.neg_out) a.neg_out[idx] = neg;
+      if (a.nh_out) { a.nh_out[idx] = nh; a.nt_out[idx] = nt; }
+      loss += fmaxf(0.f, a.margin - pos + neg);
+    }
+  }
+  if (lane == 0) atomicAdd(a.loss, loss);
+}
+
+// Fused step, backward: recompute the same negatives and scores; every active hinge term
+// sends -g to the positive triple and +g to the negative one.
+__global__ void margin_step_bwd_kernel(MarginStepParams a, TrainGrads gr, const float* gloss) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= a.b) return;
+  const float g = *gloss;
+  const long long hi = a.h[w], ti = a.t[w], ri = a.r[w];
+  const RowPtrs pp = make_rows(a.model, a.dim, a.tb, hi, ti, ri);
+  const float pos = triple_score(a.model, a.dim, pp, lane, nullptr, nullptr);
+  const float p_head = a.nh ? 0.f : a.probs[ri];
+  int active = 0;
+  for (int j = 0; j < a.n_neg; ++j) {
+    const long long idx = (long long)j * a.b + w;
+    long long nh, nt;
+    if (a.nh) { nh = a.nh[idx]; nt = a.nt[idx]; }
+    else corrupt_one(a.seed, a.offset, (uint64_t)idx, p_head, a.n_ent, hi, ti, &nh, &nt);
+    const RowPtrs pn = make_rows(a.model, a.dim, a.tb, nh, nt, ri);
+    const float neg = triple_score(a.model, a.dim, pn, lane, nullptr, nullptr);
+    if (a.margin - pos + neg > 0.f) {  // same sub-gradient as torch: zero at the kink
+      ++active;
+      triple_backward(a.model, a.dim, pn, gr, nh, nt, ri, g, lane);
+    }
+  }
+  if (active) triple_backward(a.model, a.dim, pp, gr, hi, ti, ri, -g * (float)active, lane);
+}
+
+__global__ void margin_loss_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ neg,
+                                       long long n, float margin, float* __restrict__ loss) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    s += fmaxf(0.f, margin - pos[i] + neg[i]);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(loss, s);
+}
+
+__global__ void margin_loss_bwd_kernel(const float* __restrict__ pos, const float* __restrict__ neg,
+                                       long long n, float margin, const float* __restrict__ gloss,
+                                       float* __restrict__ gpos, float* __restrict__ gneg) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float g = (margin - pos[i] + neg[i] > 0.f) ? *gloss : 0.f;
+  gpos[i] = -g;
+  gneg[i] = g;
+}
+
+inline unsigned blocks_for_warps(long long warps) {
+  return (unsigned)((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+}
+
+}  // namespace
+
+cudaError_t launch_score_triples_fwd(int model, int dim, const TrainTables& tb, const int64_t* h,
+                                     const int64_t* t, const int64_t* r, int64_t n, float* out,
+                                     cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  score_triples_fwd_kernel<<<blocks_for_warps(n), WARPS_PER_BLOCK * 32, 0, st>>>(model, dim, tb, h, t,
+                                                                                 r, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_score_triples_bwd(int model, int dim, const TrainTables& tb, const TrainGrads& gr,
+                                     const int64_t* h, const int64_t* t, const int64_t* r, int64_t n,
+                                     const float* gout, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  score_triples_bwd_kernel<<<blocks_for_warps(n), WARPS_PER_BLOCK * 32, 0, st>>>(model, dim, tb, gr, h,
+                                                                                 t, r, n, gout);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_corrupt_batch(const int64_t* h, const int64_t* t, const int64_t* r, int64_t b,
+                                 int n_neg, const float* probs, int64_t n_ent, uint64_t seed,
+                                 uint64_t offset, int64_t* nh, int64_t* nt, cudaStream_t st) {
+  const long long n = (long long)b * n_neg;
+  if (n <= 0) return cudaSuccess;
+  corrupt_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h, t, r, b, n_neg, probs, n_ent,
+                                                                     seed, offset, nh, nt);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_margin_step_fwd(const MarginStepParams& a, cudaStream_t st) {
+  if (a.b <= 0) return cudaSuccess;
+  margin_step_fwd_kernel<<<blocks_for_warps(a.b), WARPS_PER_BLOCK * 32, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_margin_step_bwd(const MarginStepParams& a, const TrainGrads& gr, const float* gloss,
+                                   cudaStream_t st) {
+  if (a.b <= 0) return cudaSuccess;
+  margin_step_bwd_kernel<<<blocks_for_warps(a.b), WARPS_PER_BLOCK * 32, 0, st>>>(a, gr, gloss);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_margin_loss_fwd(const float* pos, const float* neg, int64_t n, float margin,
+                                   float* loss, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  margin_loss_fwd_kernel<<<blocks, 256, 0, st>>>(pos, neg, n, margin, loss);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_margin_loss_bwd(const float* pos, const float* neg, int64_t n, float margin,
+                                   const float* gloss, float* gpos, float* gneg, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  margin_loss_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pos, neg, n, margin, gloss,
+                                                                      gpos, gneg);
+  return cudaGetLastError();
+}
+
+}  // namespace kge
