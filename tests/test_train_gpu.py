@@ -18,6 +18,14 @@ def _close(a, b, rtol, atol):
     torch.testing.assert_close(a.detach().cpu().float(), b.detach().cpu().float(), rtol=rtol, atol=atol)
 
 
+def _close_grad(a, b, rtol=1e-4):
+    """Gradient tables are sums of hundreds of signed terms accumulated by atomics in arbitrary
+    order: rtol on the element plus an absolute floor of 1e-5 of the table's largest entry
+    (elements that are small only by cancellation cannot be held to a relative bound)."""
+    b = b.detach().cpu().float()
+    _close(a, b, rtol, 1e-5 * float(b.abs().max()) + 1e-9)
+
+
 @pytest.mark.parametrize("case", helpers.GOLDEN_CASES)
 def test_scoring_function_matches_reference(case, cuda_device):
     g = helpers.load_golden(case)
@@ -42,7 +50,7 @@ def test_forward_loss_and_gradients_match_reference(case, cuda_device):
     assert loss.item() == pytest.approx(float(g["raw"]["loss_margin_0p5"]), rel=1e-5)
     loss.backward()
     for name, p in model.named_parameters():
-        _close(p.grad, g["grads"][name], 1e-4, 2e-6)
+        _close_grad(p.grad, g["grads"][name])
 
 
 @pytest.mark.parametrize("case", helpers.GOLDEN_CASES)
@@ -55,7 +63,7 @@ def test_fused_step_with_given_negatives_matches_reference(case, cuda_device):
     assert loss.item() == pytest.approx(float(g["raw"]["loss_margin_0p5"]), rel=1e-5)
     loss.backward()
     for name, p in model.named_parameters():
-        _close(p.grad, g["grads"][name], 1e-4, 2e-6)
+        _close_grad(p.grad, g["grads"][name])
 
 
 @pytest.mark.parametrize("kind", ["transe_l2", "distmult", "complex", "rotate", "transe_l1", "rescal"])
@@ -105,7 +113,7 @@ def test_gradients_match_torch_autograd_of_the_oracle(kind, cuda_device):
     assert loss.item() == pytest.approx(ref_loss.item(), rel=2e-5)
     loss.backward()
     for name, p in model.named_parameters():
-        _close(p.grad, leaves[name].grad, 1e-3, 5e-6)
+        _close_grad(p.grad, leaves[name].grad, rtol=2e-4)
 
 
 def test_sampler_probabilities_match_reference():
@@ -169,7 +177,7 @@ def test_fused_step_draws_the_negatives_corrupt_batch_draws(cuda_device):
     model.zero_grad()
     fused.backward()
     for n, p in model.named_parameters():
-        _close(p.grad, g1[n], 1e-4, 1e-6)
+        _close_grad(p.grad, g1[n])
 
 
 def test_training_loop_reduces_loss(cuda_device):
