@@ -154,6 +154,11 @@ typedef struct {
 
 size_t kge_rank_workspace_bytes(int model, int side, int dim, int64_t n);
 int kge_rank_side(const kge_rank_args_t* args);
+/* Only the sparse filter pass of kge_rank_side, for callers that enqueue the dense scan first
+ * (filt_offs = NULL) and build the filter CSR on the host while it runs: `args` must be the
+ * arguments of that earlier kge_rank_side call -- same workspace, still intact -- now with
+ * filt_offs / filt_ids / n_filt / filt_sub set. */
+int kge_filter_side(const kge_rank_args_t* args);
 
 /* ranks[i] = raw_count[i] (int32 -> int64); filt_ranks[i] = raw_count[i] - filt_sub[i]
  * (evaluation.py:294-300 store int64). */

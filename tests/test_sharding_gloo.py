@@ -58,7 +58,16 @@ class OracleEngine:
                     if spec.ent_lo <= c < spec.ent_lo + rows:
                         sc = shard_scores[i, c - spec.ent_lo]
                         sub[i] += int(sc >= s_true[i]) - int(s_true[i] == float("-inf"))
-        return None
+        return (side, s_true, shard_scores, spec)
+
+    def filter_side(self, handle, filt, sub):
+        side, s_true, shard_scores, spec = handle
+        offs, ids = filt
+        for i in range(s_true.shape[0]):
+            for c in ids[offs[i]:offs[i + 1]].tolist():
+                if spec.ent_lo <= c < spec.ent_lo + spec.n_rows:
+                    sc = shard_scores[i, c - spec.ent_lo]
+                    sub[i] += int(sc >= s_true[i]) - int(s_true[i] == float("-inf"))
 
     def finalize(self, raw, sub):
         return raw.long(), raw.long() - sub.long()

@@ -88,6 +88,7 @@ SIGNATURES = {
                                    _c.c_int64, _p, _p]),
     "kge_rank_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int64]),
     "kge_rank_side": (_c.c_int, [_c.POINTER(RankArgs)]),
+    "kge_filter_side": (_c.c_int, [_c.POINTER(RankArgs)]),
     "kge_finalize_ranks": (_c.c_int, [_p, _p, _c.c_int64, _p, _p, _p]),
     "kge_score_all": (_c.c_int, [_c.POINTER(ScoreAllArgs)]),
     "kge_score_triples_fwd": (_c.c_int, [_c.POINTER(Tables), _p, _p, _p, _c.c_int64, _p, _p]),

@@ -274,6 +274,25 @@ int kge_rank_side(const kge_rank_args_t* a) {
   return KGE_OK;
 }
 
+int kge_filter_side(const kge_rank_args_t* a) {
+  if (!a) return fail(KGE_ERR_ARG, "kge_filter_side: null args");
+  const int el = kge::elem_kind_for(a->model, a->side);
+  if (el < 0) return fail(KGE_ERR_ARG, "kge_filter_side: unknown model/side");
+  if (a->n == 0 || a->n_filt == 0 || a->n_rows == 0) return KGE_OK;
+  if (!a->ent0 || !a->filt_offs || !a->filt_ids || !a->filt_sub || !a->workspace)
+    return fail(KGE_ERR_ARG, "kge_filter_side: null pointer");
+  if (kge::elem_cw(el) == 2 && !a->ent1) return fail(KGE_ERR_ARG, "kge_filter_side: ent1 required");
+  const HostSchedule* hs = get_schedule(a->model, a->dim);
+  if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_filter_side: unsupported dim");
+  Workspace w = carve(a->workspace, kge::elem_qw(el), a->dim, a->n);
+  if (w.bytes > a->workspace_bytes) return fail(KGE_ERR_ARG, "kge_filter_side: workspace too small");
+  KGE_CUDA_TRY(kge::launch_filter(el, hs->s.has_cascade, a->dim, a->n, a->n_filt, w.qplain, a->ent0,
+                                  a->ent1, a->ent_lo, a->n_rows, a->filt_offs, a->filt_ids, w.perm,
+                                  w.code, w.s_true, a->filt_sub, static_cast<cudaStream_t>(a->stream)),
+               "filter pass");
+  return KGE_OK;
+}
+
 int kge_finalize_ranks(const int32_t* raw_count, const int32_t* filt_sub, int64_t n,
                        int64_t* ranks, int64_t* filt_ranks, void* stream) {
   if (n == 0) return KGE_OK;

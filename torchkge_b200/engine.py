@@ -156,7 +156,20 @@ class CudaEngine:
         _lib.check(self.lib.kge_rank_side(ctypes.byref(a)), "kge_rank_side")
         # prep, pack_queries, pad fill, true scores, scan (+ filter)
         self.launches += 5 + (1 if filt is not None and filt[1].shape[0] > 0 else 0)
-        return ws  # keep alive until the caller synchronises / reuses the stream
+        return (a, ws, packed, hrows, trows)  # handle for filter_side; keeps the buffers alive
+
+    def filter_side(self, handle, filt, filt_sub):
+        """Sparse filter pass for a side whose dense scan was enqueued earlier by rank_side
+        (with filt=None); ``handle`` is what that call returned."""
+        a = handle[0]
+        offs, ids = filt
+        if ids.shape[0] == 0:
+            return
+        a.filt_offs, a.filt_ids, a.n_filt = _ptr(offs), _ptr(ids), ids.shape[0]
+        a.filt_sub = _ptr(filt_sub)
+        a.stream = _stream(filt_sub.device)
+        _lib.check(self.lib.kge_filter_side(ctypes.byref(a)), "kge_filter_side")
+        self.launches += 1
 
     def score_all(self, spec, packed, side, hrows, trows, r_idx):
         n = hrows.shape[0]
@@ -221,13 +234,26 @@ class EntityShard:
         return t
 
 
+def _csr_slice(filt, lo, hi, n):
+    """CSR rows [lo, hi) with offsets rebased to 0."""
+    offs, ids = filt
+    if lo == 0 and hi == n:
+        return offs, ids
+    base = int(offs[lo].item())
+    end = int(offs[hi].item())
+    return (offs[lo:hi + 1] - base).contiguous(), ids[base:end].contiguous()
+
+
 def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=None,
                          engine=None, chunk=DEFAULT_CHUNK, packed=None):
     """Rank every triple's true tail and head against all entities, raw and filtered.
 
     spec       ModelSpec holding either the full entity table or exactly this rank's shard
     h/t/r_idx  int64 device tensors (n,)
-    filt_*     (offs int64 (n+1,), ids int64 (m,)) device CSR of entities to discount, or None
+    filt_*     (offs int64 (n+1,), ids int64 (m,)) device CSR of entities to discount, None,
+               or a zero-argument callable returning such a CSR -- callables are invoked only
+               after every dense scan has been enqueued, so that building the CSR on the host
+               overlaps with the scans on the device
     shard      EntityShard when the table is range-partitioned over a process group
     Returns (rank_heads, rank_tails, filt_rank_heads, filt_rank_tails), int64 device tensors.
     """
@@ -241,7 +267,7 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
         packed = engine.pack(spec)
     dev = spec.ent0.device
     counters = torch.zeros((4, n), dtype=torch.int32, device=dev)  # raw_t, sub_t, raw_h, sub_h
-    keep = []
+    pending = []
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)
         h, t, r = h_idx[lo:hi], t_idx[lo:hi], r_idx[lo:hi]
@@ -251,25 +277,21 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
             # every row is owned by exactly one rank; the others contribute zeros
             shard.all_reduce_sum(hrows)
             shard.all_reduce_sum(trows)
-        for side, true_idx, filt, raw, sub in (
-                (_lib.SIDE_TAIL, t, filt_tail, counters[0], counters[1]),
-                (_lib.SIDE_HEAD, h, filt_head, counters[2], counters[3])):
-            f = None
-            if filt is not None:
-                offs, ids = filt
-                # CSR slice for this chunk: offsets rebased to the chunk
-                if lo == 0 and hi == n:
-                    f = (offs, ids)
-                else:
-                    base = int(offs[lo].item())
-                    end = int(offs[hi].item())
-                    f = ((offs[lo:hi + 1] - base).contiguous(), ids[base:end].contiguous())
-            keep.append(engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, f,
-                                         raw[lo:hi], sub[lo:hi]))
-        keep.append((hrows, trows))
+        for side, true_idx, which, raw, sub in ((_lib.SIDE_TAIL, t, 0, counters[0], counters[1]),
+                                                (_lib.SIDE_HEAD, h, 1, counters[2], counters[3])):
+            handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
+                                      raw[lo:hi], sub[lo:hi])
+            pending.append((handle, which, lo, hi, sub))
+    filts = [filt_tail, filt_head]
+    for k in (0, 1):
+        if callable(filts[k]):
+            filts[k] = filts[k]()
+    for handle, which, lo, hi, sub in pending:
+        if filts[which] is not None:
+            engine.filter_side(handle, _csr_slice(filts[which], lo, hi, n), sub[lo:hi])
+    del pending
     if shard is not None and shard.world > 1:
         shard.all_reduce_sum(counters)  # the single collective on the rank counters
     rank_t, filt_t = engine.finalize(counters[0], counters[1])
     rank_h, filt_h = engine.finalize(counters[2], counters[3])
-    del keep
     return rank_h, rank_t, filt_h, filt_t

@@ -65,22 +65,27 @@ class LinkPredictionEvaluator(object):
         dev = spec.ent0.device
         kg = self.kg
         heads, tails, rels = kg.head_idx, kg.tail_idx, kg.relations
-        # filter sets -> CSR on the host (same per-row semantics as get_true_targets)
-        csr_t = filter_csr(kg.dict_of_tails, heads, rels, tails)
-        csr_h = filter_csr(kg.dict_of_heads, tails, rels, heads)
         h_d = heads.to(dev, non_blocking=True)
         t_d = tails.to(dev, non_blocking=True)
         r_d = rels.to(dev, non_blocking=True)
-        csr_t = tuple(x.to(dev, non_blocking=True) for x in csr_t)
-        csr_h = tuple(x.to(dev, non_blocking=True) for x in csr_h)
-        self.last_stats = {
-            "h2d_bytes": 8 * (3 * kg.n_facts + sum(x.numel() for x in csr_t + csr_h)),
-            "d2h_bytes": 8 * 4 * kg.n_facts,
-        }
+        stats = {"h2d_bytes": 8 * 3 * kg.n_facts, "d2h_bytes": 8 * 4 * kg.n_facts}
+
+        # Filter sets -> CSR on the host (same per-row semantics as get_true_targets).  Built
+        # lazily: the engine asks for them after the dense scans are enqueued, so this Python
+        # work overlaps with the GPU.
+        def lazy_csr(dictionary, k1, k2, true_idx):
+            def build():
+                csr = filter_csr(dictionary, k1, k2, true_idx)
+                stats["h2d_bytes"] += 8 * sum(x.numel() for x in csr)
+                return tuple(x.to(dev, non_blocking=True) for x in csr)
+            return build
+
         engine = default_engine()
-        rh, rt, frh, frt = rank_link_prediction(spec, h_d, t_d, r_d, csr_t, csr_h,
-                                                shard=self.shard, engine=engine,
-                                                chunk=DEFAULT_CHUNK)
+        rh, rt, frh, frt = rank_link_prediction(
+            spec, h_d, t_d, r_d, lazy_csr(kg.dict_of_tails, heads, rels, tails),
+            lazy_csr(kg.dict_of_heads, tails, rels, heads), shard=self.shard, engine=engine,
+            chunk=DEFAULT_CHUNK)
+        self.last_stats = stats
         self.rank_true_heads = rh.cpu()
         self.rank_true_tails = rt.cpu()
         self.filt_rank_true_heads = frh.cpu()
