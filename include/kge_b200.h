@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 1
+#define KGE_ABI_VERSION 2
 
 /* error codes */
 #define KGE_OK 0
@@ -94,6 +94,18 @@ int kge_build_schedule(int model, int dim, int32_t* perm_host, uint8_t* code_hos
  * so that one pipeline stage of the scan is a single contiguous bulk copy.
  * Replaces the zero-copy `expand` of ent_emb.weight in inference_prepare_candidates
  * (translation.py:105-125, bilinear.py:123-143, 247-267, 530-556). */
+/* ---- tensor-core operand image of a table shard (optional, see kge_rank_args_t.flags) ----
+ * For models whose score is a dot product or a squared L2 distance (DistMult, RESCAL, ComplEx,
+ * TransE-L2) the dense scan can run as a bf16x3 split GEMM on the tensor cores that decides
+ * every (query, candidate) pair whose approximate score differs from the true score by more
+ * than a rigorous error bound, the remaining near-ties being re-scored exactly -- ranks are
+ * unchanged.  kge_tc_pack_table writes the operand image that path streams:
+ * [hi/lo bf16 planes in 128-byte-swizzled shared-memory order | per-row norm bounds].
+ * kge_tc_packed_bytes returns 0 for models without such a path (TransE-L1, RotatE). */
+size_t kge_tc_packed_bytes(int model, int64_t n_rows, int dim);
+int kge_tc_pack_table(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
+                      void* tc_packed, void* stream);
+
 size_t kge_packed_table_floats(int model, int64_t n_rows, int dim);
 int kge_pack_table(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
                    float* packed, void* stream);
@@ -125,7 +137,7 @@ typedef struct {
   int32_t model; /* kge_model_t */
   int32_t side;  /* kge_side_t */
   int32_t dim;
-  int32_t reserved0;
+  int32_t flags;  /* KGE_FLAG_* */
   int64_t n;      /* triples in this call */
   int64_t n_ent;  /* global number of entities */
   int64_t ent_lo; /* first global entity id held in `packed` / ent0 / ent1 */
@@ -150,9 +162,18 @@ typedef struct {
   void* workspace;          /* kge_rank_workspace_bytes() bytes, 256-B aligned */
   size_t workspace_bytes;
   void* stream;
+  const void* tc_packed;    /* kge_tc_pack_table output (required with KGE_FLAG_TENSOR_CORE) */
+  uint64_t* tc_stats;       /* optional device out [2]: near-tie pairs found, list capacity;
+                               found > capacity means the list overflowed and the counters of
+                               this call are INVALID: redo the call without the flag */
+  float* tc_dump;           /* debug / tests: if set, the tensor-core pass writes its approximate
+                               scores [n][n_rows] here and counts nothing */
 } kge_rank_args_t;
 
-size_t kge_rank_workspace_bytes(int model, int side, int dim, int64_t n);
+#define KGE_FLAG_TENSOR_CORE 1 /* use the tensor-core bound-and-refine scan when the model has one */
+
+/* n_rows / flags only matter for the tensor-core path (near-tie list capacity). */
+size_t kge_rank_workspace_bytes(int model, int side, int dim, int64_t n, int64_t n_rows, int flags);
 int kge_rank_side(const kge_rank_args_t* args);
 /* Only the sparse filter pass of kge_rank_side, for callers that enqueue the dense scan first
  * (filt_offs = NULL) and build the filter CSR on the host while it runs: `args` must be the

@@ -42,9 +42,16 @@ def test_size_queries():
     assert lib.kge_packed_table_floats(_lib.DISTMULT, 1000, 200) == 8 * 200 * 128
     assert lib.kge_packed_table_floats(_lib.COMPLEX, 1000, 200) == 8 * 200 * 2 * 128
     assert lib.kge_packed_table_floats(_lib.DISTMULT, 0, 200) == 0
-    small = lib.kge_rank_workspace_bytes(_lib.TRANSE_L2, _lib.SIDE_TAIL, 200, 64)
-    big = lib.kge_rank_workspace_bytes(_lib.TRANSE_L2, _lib.SIDE_HEAD, 200, 64)
+    small = lib.kge_rank_workspace_bytes(_lib.TRANSE_L2, _lib.SIDE_TAIL, 200, 64, 0, 0)
+    big = lib.kge_rank_workspace_bytes(_lib.TRANSE_L2, _lib.SIDE_HEAD, 200, 64, 0, 0)
     assert 0 < small < big  # head side carries two query planes
+    with_tc = lib.kge_rank_workspace_bytes(_lib.TRANSE_L2, _lib.SIDE_TAIL, 200, 64, 100000,
+                                           _lib.FLAG_TENSOR_CORE)
+    assert with_tc > small + (1 << 23)  # near-tie list (>= 1 Mi pairs) + operand image
+    # tensor-core operand image: 4 k-blocks x (hi, lo) x 256 rows x 128 B per 256-row tile + norms
+    assert lib.kge_tc_packed_bytes(_lib.DISTMULT, 1000, 200) == 4 * (4 * 2 * 256 * 128) + 2 * 1024 * 4
+    assert lib.kge_tc_packed_bytes(_lib.TRANSE_L1, 1000, 200) == 0   # no tensor-core path
+    assert lib.kge_tc_packed_bytes(_lib.ROTATE, 1000, 200) == 0
 
 
 def test_bad_arguments_return_error_codes():

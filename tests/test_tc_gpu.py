@@ -1,0 +1,122 @@
+"""Tensor-core bound-and-refine path (csrc/tc.cu): the approximate scores must stay inside
+their error bound, and ranks must remain bit-identical to the oracle's."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import torchkge_b200 as tk
+from oracle import kge_oracle as oracle
+from tests import helpers
+from torchkge_b200 import _lib
+from torchkge_b200.engine import CudaEngine, ModelSpec, rank_link_prediction
+from torchkge_b200.data import filter_csr
+
+pytestmark = pytest.mark.gpu
+TC_KINDS = ["transe_l2", "distmult", "complex", "rescal"]
+
+
+def _approx_scores(eng, spec, side, h, t, r):
+    hrows, trows = eng.gather_rows(spec, h), eng.gather_rows(spec, t)
+    packed, tcp = eng.pack(spec), eng.pack_tc(spec)
+    assert tcp is not None
+    n = h.shape[0]
+    dump = torch.full((n, spec.n_rows), float("nan"), device=h.device)
+    raw = torch.zeros(n, dtype=torch.int32, device=h.device)
+    sub = torch.zeros_like(raw)
+    eng.rank_side(spec, packed, side, hrows, trows, r, t if side == 0 else h, None, raw, sub,
+                  tc_packed=tcp, tc_dump=dump)
+    torch.cuda.synchronize()
+    return dump.cpu()
+
+
+@pytest.mark.parametrize("kind", TC_KINDS)
+@pytest.mark.parametrize("d", [13, 50, 64, 200])
+def test_approximate_scores_within_half_the_bound(kind, d, cuda_device):
+    if kind == "rescal" and d > 64:
+        pytest.skip("rescal d^2 tables: small dims only")
+    n_ent, n_rel, b = 1300, 7, 150
+    model = helpers.make_model(kind, d, n_ent, n_rel, seed=d)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(1.0 + torch.rand(p.shape[0], 1))
+    model = model.to(cuda_device)
+    P = helpers.oracle_params(kind, model)
+    g = torch.Generator().manual_seed(3)
+    h = torch.randint(0, n_ent, (b,), generator=g)
+    t = torch.randint(0, n_ent, (b,), generator=g)
+    r = torch.randint(0, n_rel, (b,), generator=g)
+    eng = CudaEngine(tensor_core=True)
+    spec = ModelSpec.from_model(model)
+    for side, name in ((0, "tail"), (1, "head")):
+        got = _approx_scores(eng, spec, side, h.to(cuda_device), t.to(cuda_device), r.to(cuda_device))
+        want = oracle.scores_all(kind, P, h, t, r, name).double()
+        assert not torch.isnan(got).any()
+        # the bound the kernel uses: gamma * |a| |b|  (dot) or gamma * (|a| + |b|)^2  (L2)
+        k_total = 2 * d if kind == "complex" else d
+        l2 = kind == "transe_l2"
+        split, accum = 3.0 * 2.0 ** -16, (3.0 * ((k_total + 15) // 16) + 2.0) * 2.0 ** -22
+        gamma = 2.0 * (split + accum + (k_total + 4.0) * 2.0 ** -24 + 8.0 * 2.0 ** -24) * (1.5 if l2 else 1.0)
+        # operand norms
+        if kind == "complex":
+            cand = torch.cat([P["re_ent"], P["im_ent"]], 1).double()
+            re_h, im_h, re_t, im_t = P["re_ent"][h], P["im_ent"][h], P["re_ent"][t], P["im_ent"][t]
+            re_r, im_r = P["re_rel"][r], P["im_rel"][r]
+            q = (torch.cat([re_h * re_r - im_h * im_r, re_h * im_r + im_h * re_r], 1) if side == 0 else
+                 torch.cat([re_r * re_t + im_r * im_t, re_r * im_t - im_r * re_t], 1)).double()
+        elif kind == "distmult":
+            cand = P["ent"].double()
+            q = ((P["ent"][h] * P["rel"][r]) if side == 0 else (P["rel"][r] * P["ent"][t])).double()
+        elif kind == "rescal":
+            cand = P["ent"].double()
+            m = P["rel_mat"][r].view(-1, d, d)
+            q = (torch.matmul(P["ent"][h].view(b, 1, d), m).view(b, d) if side == 0 else
+                 torch.matmul(m, P["ent"][t].view(b, d, 1)).view(b, d)).double()
+        else:
+            cand = P["ent"].double()
+            q = ((P["ent"][h] + P["rel"][r]) if side == 0 else (P["ent"][t] - P["rel"][r])).double()
+        na, nb = q.norm(dim=1).view(-1, 1), cand.norm(dim=1).view(1, -1)
+        bound = gamma * ((na + nb) ** 2 if l2 else na * nb)
+        ratio = ((got.double() - want).abs() / bound).max().item()
+        assert ratio < 0.5, "%s %s d=%d: error / bound = %.3f" % (kind, name, d, ratio)
+
+
+@pytest.mark.parametrize("kind", TC_KINDS)
+@pytest.mark.parametrize("d", [13, 50, 100])
+def test_ranks_equal_oracle_with_tensor_cores(kind, d, cuda_device):
+    if kind == "rescal":
+        pytest.skip("rescal ranks are tolerance-parity (MKL query prep); covered by score tests")
+    n_ent, n_rel = 1500, 9
+    kg, dh, dt = helpers.make_kg(n_ent, n_rel, n_facts=7000, n_test=300, seed=100 + d)
+    model = helpers.make_model(kind, d, n_ent, n_rel, seed=d).to(cuda_device)
+    P = helpers.oracle_params(kind, model)
+    ref = oracle.link_prediction(kind, P, kg.head_idx, kg.tail_idx, kg.relations, dh, dt, 64)
+    eng = CudaEngine(tensor_core=True)
+    spec = ModelSpec.from_model(model)
+    dev = cuda_device
+    csr_t = tuple(x.to(dev) for x in filter_csr(dt, kg.head_idx, kg.relations, kg.tail_idx))
+    csr_h = tuple(x.to(dev) for x in filter_csr(dh, kg.tail_idx, kg.relations, kg.head_idx))
+    got = rank_link_prediction(spec, kg.head_idx.to(dev), kg.tail_idx.to(dev), kg.relations.to(dev),
+                               csr_t, csr_h, engine=eng)
+    assert len(eng.tc_stats) == 2
+    for a, b in zip(got, ref):
+        assert torch.equal(a.cpu(), b)
+    found = sum(int(s[0]) for s in eng.tc_stats)
+    assert found < 0.02 * 2 * 300 * n_ent      # the near-tie band is a small fraction
+
+
+def test_exact_ties_and_duplicates_with_tensor_cores(cuda_device):
+    n_ent, n_rel, d = 600, 5, 32
+    kg, dh, dt = helpers.make_kg(n_ent, n_rel, n_facts=3000, n_test=200, seed=9)
+    model = helpers.make_model("distmult", d, n_ent, n_rel, seed=9)
+    with torch.no_grad():
+        model.ent_emb.weight[100:300] = model.ent_emb.weight[0:200]   # exact ties
+        model.ent_emb.weight[500:] = 0.0
+    P = helpers.oracle_params("distmult", model)
+    ref = oracle.link_prediction("distmult", P, kg.head_idx, kg.tail_idx, kg.relations, dh, dt, 50)
+    ev = tk.LinkPredictionEvaluator(model.to(cuda_device), kg)
+    ev.evaluate(b_size=64, verbose=False)
+    for a, b in zip((ev.rank_true_heads, ev.rank_true_tails, ev.filt_rank_true_heads,
+                     ev.filt_rank_true_tails), ref):
+        assert torch.equal(a, b)

@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libkge_b200.so")
 TRANSE_L1, TRANSE_L2, DISTMULT, RESCAL, COMPLEX, ROTATE = range(6)
 SIDE_TAIL, SIDE_HEAD = 0, 1
 TILE_C, TILE_Q = 128, 64
-ABI_VERSION = 1
+ABI_VERSION = 2
+FLAG_TENSOR_CORE = 1
 
 MODEL_NAMES = {TRANSE_L1: "TransE-L1", TRANSE_L2: "TransE-L2", DISTMULT: "DistMult",
                RESCAL: "RESCAL", COMPLEX: "ComplEx", ROTATE: "RotatE"}
@@ -32,13 +33,14 @@ _p = ctypes.c_void_p
 class RankArgs(ctypes.Structure):
     """kge_rank_args_t"""
     _fields_ = [
-        ("model", _c.c_int32), ("side", _c.c_int32), ("dim", _c.c_int32), ("reserved0", _c.c_int32),
+        ("model", _c.c_int32), ("side", _c.c_int32), ("dim", _c.c_int32), ("flags", _c.c_int32),
         ("n", _c.c_int64), ("n_ent", _c.c_int64), ("ent_lo", _c.c_int64), ("n_rows", _c.c_int64),
         ("packed", _p), ("ent0", _p), ("ent1", _p), ("rel0", _p), ("rel1", _p),
         ("hrows", _p), ("trows", _p), ("r_idx", _p), ("true_idx", _p),
         ("filt_offs", _p), ("filt_ids", _p), ("n_filt", _c.c_int64),
         ("raw_count", _p), ("filt_sub", _p), ("true_score", _p),
         ("workspace", _p), ("workspace_bytes", _c.c_size_t), ("stream", _p),
+        ("tc_packed", _p), ("tc_stats", _p), ("tc_dump", _p),
     ]
 
 
@@ -86,7 +88,10 @@ SIGNATURES = {
     "kge_pack_table": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _c.c_int, _p, _p]),
     "kge_gather_rows": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _c.c_int64, _c.c_int, _p,
                                    _c.c_int64, _p, _p]),
-    "kge_rank_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int64]),
+    "kge_rank_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64,
+                                               _c.c_int]),
+    "kge_tc_packed_bytes": (_c.c_size_t, [_c.c_int, _c.c_int64, _c.c_int]),
+    "kge_tc_pack_table": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _c.c_int, _p, _p]),
     "kge_rank_side": (_c.c_int, [_c.POINTER(RankArgs)]),
     "kge_filter_side": (_c.c_int, [_c.POINTER(RankArgs)]),
     "kge_finalize_ranks": (_c.c_int, [_p, _p, _c.c_int64, _p, _p, _p]),

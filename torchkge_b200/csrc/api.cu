@@ -9,6 +9,7 @@
 #include "../../include/kge_b200.h"
 #include "kernels.h"
 #include "schedule.h"
+#include "tc.h"
 #include "train.h"
 
 namespace {
@@ -64,10 +65,23 @@ struct Workspace {
   float* s_true;
   int32_t* perm;
   uint8_t* code;
+  // tensor-core path
+  unsigned char* apack;
+  float* qbound;
+  float* qnorm2;
+  unsigned long long* amb_count;
+  int2* amb_pairs;
+  unsigned long long amb_cap;
   size_t bytes;
 };
 
-Workspace carve(void* base, int qw, int dim, int64_t n) {
+bool tc_supported(int el) {
+  return el == kge::EL_DOT1 || el == kge::EL_DOT2 || el == kge::EL_L2_TAIL || el == kge::EL_L2_HEAD;
+}
+int tc_k_total(int el, int dim) { return el == kge::EL_DOT2 ? 2 * dim : dim; }
+
+Workspace carve(void* base, int qw, int dim, int64_t n, int el = -1, int64_t n_rows = 0,
+                int flags = 0) {
   const int64_t n_qt = (n + kge::TILE_Q - 1) / kge::TILE_Q;
   Workspace w;
   size_t off = 0;
@@ -81,6 +95,21 @@ Workspace carve(void* base, int qw, int dim, int64_t n) {
   w.s_true = static_cast<float*>(take((size_t)n_qt * kge::TILE_Q * sizeof(float)));
   w.perm = static_cast<int32_t*>(take((size_t)dim * sizeof(int32_t)));
   w.code = static_cast<uint8_t*>(take((size_t)dim));
+  w.apack = nullptr; w.qbound = w.qnorm2 = nullptr; w.amb_count = nullptr; w.amb_pairs = nullptr;
+  w.amb_cap = 0;
+  if ((flags & KGE_FLAG_TENSOR_CORE) && el >= 0 && tc_supported(el) && n_rows > 0) {
+    const int n_kb = (tc_k_total(el, dim) + kge::tc::TC_BK - 1) / kge::tc::TC_BK;
+    w.apack = static_cast<unsigned char*>(take(kge::tc::a_image_bytes(n, n_kb)));
+    w.qbound = static_cast<float*>(take((size_t)n * sizeof(float)));
+    w.qnorm2 = static_cast<float*>(take((size_t)n * sizeof(float)));
+    w.amb_count = static_cast<unsigned long long*>(take(sizeof(unsigned long long)));
+    // near-tie list: room for 1/256 of all pairs (the band is ~0.1 %), 1 Mi..128 Mi entries
+    unsigned long long cap = (unsigned long long)n * (unsigned long long)n_rows / 256ull;
+    if (cap < (1ull << 20)) cap = 1ull << 20;
+    if (cap > (1ull << 27)) cap = 1ull << 27;
+    w.amb_cap = cap;
+    w.amb_pairs = static_cast<int2*>(take((size_t)cap * sizeof(int2)));
+  }
   w.bytes = off;
   return w;
 }
@@ -204,10 +233,37 @@ int kge_gather_rows(int model, const float* ent0, const float* ent1, int64_t ent
   return KGE_OK;
 }
 
-size_t kge_rank_workspace_bytes(int model, int side, int dim, int64_t n) {
+size_t kge_rank_workspace_bytes(int model, int side, int dim, int64_t n, int64_t n_rows, int flags) {
   const int el = kge::elem_kind_for(model, side);
   if (el < 0 || dim < 1 || n < 0) return 0;
-  return carve(nullptr, kge::elem_qw(el), dim, n).bytes;
+  return carve(nullptr, kge::elem_qw(el), dim, n, el, n_rows, flags).bytes;
+}
+
+size_t kge_tc_packed_bytes(int model, int64_t n_rows, int dim) {
+  const int el = kge::elem_kind_for(model, KGE_SIDE_TAIL);
+  if (el < 0 || !tc_supported(el) || n_rows <= 0 || dim < 1) return 0;
+  const int n_kb = (tc_k_total(el, dim) + kge::tc::TC_BK - 1) / kge::tc::TC_BK;
+  const int64_t n_ct = (n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
+  return kge::tc::b_image_bytes(n_rows, n_kb) + 2 * (size_t)n_ct * kge::tc::TC_BN * sizeof(float);
+}
+
+int kge_tc_pack_table(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
+                      void* tc_packed, void* stream) {
+  const int el = kge::elem_kind_for(model, KGE_SIDE_TAIL);
+  if (el < 0 || !tc_supported(el)) return fail(KGE_ERR_UNSUPPORTED, "kge_tc_pack_table: model has no tensor-core path");
+  if (n_rows <= 0) return KGE_OK;
+  if (!ent0 || !tc_packed || (kge::elem_cw(el) == 2 && !ent1))
+    return fail(KGE_ERR_ARG, "kge_tc_pack_table: null pointer");
+  const int k_total = tc_k_total(el, dim);
+  const int n_kb = (k_total + kge::tc::TC_BK - 1) / kge::tc::TC_BK;
+  const int64_t n_ct = (n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
+  unsigned char* bpack = static_cast<unsigned char*>(tc_packed);
+  float* cbound = reinterpret_cast<float*>(bpack + kge::tc::b_image_bytes(n_rows, n_kb));
+  float* cnorm2 = cbound + (size_t)n_ct * kge::tc::TC_BN;
+  KGE_CUDA_TRY(kge::tc::launch_pack_b(ent0, ent1, n_rows, dim, k_total, n_kb, bpack, cbound, cnorm2,
+                                      static_cast<cudaStream_t>(stream)),
+               "tc pack table");
+  return KGE_OK;
 }
 
 int kge_rank_side(const kge_rank_args_t* a) {
@@ -227,7 +283,9 @@ int kge_rank_side(const kge_rank_args_t* a) {
   const HostSchedule* hs = get_schedule(a->model, a->dim);
   if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_rank_side: unsupported dim");
   const int qw = kge::elem_qw(el);
-  Workspace w = carve(a->workspace, qw, a->dim, a->n);
+  const bool use_tc = (a->flags & KGE_FLAG_TENSOR_CORE) && tc_supported(el) && a->n_rows > 0;
+  if (use_tc && !a->tc_packed) return fail(KGE_ERR_ARG, "kge_rank_side: tc_packed required with KGE_FLAG_TENSOR_CORE");
+  Workspace w = carve(a->workspace, qw, a->dim, a->n, el, a->n_rows, use_tc ? KGE_FLAG_TENSOR_CORE : 0);
   if (w.bytes > a->workspace_bytes) return fail(KGE_ERR_ARG, "kge_rank_side: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   const bool casc = hs->s.has_cascade;
@@ -250,7 +308,45 @@ int kge_rank_side(const kge_rank_args_t* a) {
                                  cudaMemcpyDeviceToDevice, st),
                  "copy true_score");
 
-  if (a->n_rows > 0) {
+  if (use_tc) {
+    // tensor-core bound-and-refine: approximate scores decide all but the near-tie band,
+    // which is re-scored exactly (same device functions as the scalar scan)
+    const int k_total = tc_k_total(el, a->dim);
+    const int n_kb = (k_total + kge::tc::TC_BK - 1) / kge::tc::TC_BK;
+    const int64_t n_ct = (a->n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
+    const bool l2 = el == kge::EL_L2_TAIL || el == kge::EL_L2_HEAD;
+    KGE_CUDA_TRY(kge::tc::launch_pack_a(w.qplain, qw, a->n, a->dim, k_total, n_kb,
+                                        el == kge::EL_L2_HEAD ? 1 : 0, w.apack, w.qbound, w.qnorm2, st),
+                 "tc pack queries");
+    KGE_CUDA_TRY(cudaMemsetAsync(w.amb_count, 0, sizeof(unsigned long long), st), "tc reset list");
+    const unsigned char* bpack = static_cast<const unsigned char*>(a->tc_packed);
+    const float* cbound = reinterpret_cast<const float*>(bpack + kge::tc::b_image_bytes(a->n_rows, n_kb));
+    kge::tc::TcScanParams tp;
+    tp.apack = w.apack; tp.bpack = bpack; tp.s_true = w.s_true;
+    tp.qbound = w.qbound; tp.qnorm2 = w.qnorm2;
+    tp.cbound = cbound; tp.cnorm2 = cbound + (size_t)n_ct * kge::tc::TC_BN;
+    tp.counts = a->raw_count; tp.amb_count = w.amb_count; tp.amb_pairs = w.amb_pairs;
+    tp.amb_cap = w.amb_cap; tp.dump = a->tc_dump;
+    tp.gamma = kge::tc::tc_gamma(k_total, l2); tp.l2 = l2 ? 1 : 0;
+    tp.n_kb = n_kb; tp.k_total = k_total;
+    tp.n_q = a->n; tp.n_rows = a->n_rows;
+    tp.n_qt = (a->n + kge::tc::TC_BM - 1) / kge::tc::TC_BM; tp.n_ct = n_ct;
+    KGE_CUDA_TRY(kge::tc::launch_tc_scan(tp, st), "tc scan");
+    KGE_CUDA_TRY(kge::tc::launch_recheck(el, casc, a->dim, w.amb_count, w.amb_cap, w.amb_pairs, w.qplain,
+                                         a->ent0, a->ent1, w.perm, w.code, w.s_true, a->raw_count, st),
+                 "tc recheck");
+    if (a->tc_stats) {
+      KGE_CUDA_TRY(cudaMemcpyAsync(a->tc_stats, w.amb_count, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st),
+                   "tc stats");
+      KGE_CUDA_TRY(cudaMemcpyAsync(a->tc_stats + 1, &w.amb_cap, sizeof(uint64_t), cudaMemcpyHostToDevice, st),
+                   "tc stats cap");
+    }
+    if (a->filt_offs && a->n_filt > 0)
+      KGE_CUDA_TRY(kge::launch_filter(el, casc, a->dim, a->n, a->n_filt, w.qplain, a->ent0, a->ent1,
+                                      a->ent_lo, a->n_rows, a->filt_offs, a->filt_ids, w.perm,
+                                      w.code, w.s_true, a->filt_sub, st),
+                   "filter pass");
+  } else if (a->n_rows > 0) {
     kge::ScanParams p;
     p.packed = a->packed;
     p.qpacked = w.qpacked;
@@ -284,7 +380,7 @@ int kge_filter_side(const kge_rank_args_t* a) {
   if (kge::elem_cw(el) == 2 && !a->ent1) return fail(KGE_ERR_ARG, "kge_filter_side: ent1 required");
   const HostSchedule* hs = get_schedule(a->model, a->dim);
   if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_filter_side: unsupported dim");
-  Workspace w = carve(a->workspace, kge::elem_qw(el), a->dim, a->n);
+  Workspace w = carve(a->workspace, kge::elem_qw(el), a->dim, a->n);  // leading part only
   if (w.bytes > a->workspace_bytes) return fail(KGE_ERR_ARG, "kge_filter_side: workspace too small");
   KGE_CUDA_TRY(kge::launch_filter(el, hs->s.has_cascade, a->dim, a->n, a->n_filt, w.qplain, a->ent0,
                                   a->ent1, a->ent_lo, a->n_rows, a->filt_offs, a->filt_ids, w.perm,

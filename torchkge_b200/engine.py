@@ -6,6 +6,7 @@ may substitute an object with the same four methods (``pack``, ``gather_rows``,
 ``rank_side``, ``score_all``) to exercise the sharding logic on CPU.
 """
 import ctypes
+import os
 
 import torch
 
@@ -108,9 +109,14 @@ def _need_cuda(*tensors):
 class CudaEngine:
     """Direct calls into libkge_b200.so on the current CUDA stream."""
 
-    def __init__(self):
+    def __init__(self, tensor_core=None):
         self.lib = _lib.load()
         self.launches = 0  # kernels launched through this engine (bench.py reports it)
+        if tensor_core is None:
+            tensor_core = os.environ.get("KGE_TENSOR_CORE", "1") != "0"
+        #: use the tcgen05 bound-and-refine scan for models that have one (ranks unchanged)
+        self.tensor_core = bool(tensor_core)
+        self.tc_stats = []  # (device tensor [found, capacity]) per tensor-core call, for checks
 
     # ---- table packing: once per evaluate() ----
     def pack(self, spec):
@@ -124,6 +130,19 @@ class CudaEngine:
             self.launches += 1
         return packed
 
+    def pack_tc(self, spec):
+        """Tensor-core operand image of the shard, or None when the model has no such path."""
+        if not self.tensor_core:
+            return None
+        nbytes = self.lib.kge_tc_packed_bytes(spec.code, spec.n_rows, spec.dim)
+        if nbytes == 0:
+            return None
+        out = torch.empty(nbytes, dtype=torch.uint8, device=spec.ent0.device)
+        _lib.check(self.lib.kge_tc_pack_table(spec.code, _ptr(spec.ent0), _ptr(spec.ent1), spec.n_rows,
+                                              spec.dim, _ptr(out), _stream(out.device)), "kge_tc_pack_table")
+        self.launches += 2
+        return out
+
     def gather_rows(self, spec, idx):
         _need_cuda(spec.ent0, idx)
         n = idx.shape[0]
@@ -136,14 +155,20 @@ class CudaEngine:
         return out
 
     def rank_side(self, spec, packed, side, hrows, trows, r_idx, true_idx, filt, raw_count,
-                  filt_sub, true_score=None):
+                  filt_sub, true_score=None, tc_packed=None, tc_dump=None):
         """Adds this shard's counts for one side into raw_count / filt_sub (int32, device)."""
-        n = r_idx.shape[0]
+        n = r_idx.shape[0] if r_idx is not None else hrows.shape[0]
         dev = raw_count.device
-        ws_bytes = self.lib.kge_rank_workspace_bytes(spec.code, side, spec.dim, n)
+        flags = _lib.FLAG_TENSOR_CORE if tc_packed is not None else 0
+        ws_bytes = self.lib.kge_rank_workspace_bytes(spec.code, side, spec.dim, n, spec.n_rows, flags)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         a = _lib.RankArgs()
-        a.model, a.side, a.dim = spec.code, side, spec.dim
+        a.model, a.side, a.dim, a.flags = spec.code, side, spec.dim, flags
+        stats = None
+        if tc_packed is not None:
+            stats = torch.zeros(2, dtype=torch.int64, device=dev)
+            a.tc_packed, a.tc_stats, a.tc_dump = _ptr(tc_packed), _ptr(stats), _ptr(tc_dump)
+            self.tc_stats.append(stats)
         a.n, a.n_ent, a.ent_lo, a.n_rows = n, spec.n_ent, spec.ent_lo, spec.n_rows
         a.packed, a.ent0, a.ent1 = _ptr(packed), _ptr(spec.ent0), _ptr(spec.ent1)
         a.rel0, a.rel1 = _ptr(spec.rel0), _ptr(spec.rel1)
@@ -156,7 +181,7 @@ class CudaEngine:
         _lib.check(self.lib.kge_rank_side(ctypes.byref(a)), "kge_rank_side")
         # prep, pack_queries, pad fill, true scores, scan (+ filter)
         self.launches += 5 + (1 if filt is not None and filt[1].shape[0] > 0 else 0)
-        return (a, ws, packed, hrows, trows)  # handle for filter_side; keeps the buffers alive
+        return (a, ws, packed, hrows, trows, tc_packed, stats)  # handle for filter_side; keeps buffers alive
 
     def filter_side(self, handle, filt, filt_sub):
         """Sparse filter pass for a side whose dense scan was enqueued earlier by rank_side
@@ -175,7 +200,7 @@ class CudaEngine:
         n = hrows.shape[0]
         dev = hrows.device
         scores = torch.empty((n, spec.n_rows), dtype=torch.float32, device=dev)
-        ws_bytes = self.lib.kge_rank_workspace_bytes(spec.code, side, spec.dim, n)
+        ws_bytes = self.lib.kge_rank_workspace_bytes(spec.code, side, spec.dim, n, 0, 0)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         a = _lib.ScoreAllArgs()
         a.model, a.side, a.dim = spec.code, side, spec.dim
@@ -265,6 +290,7 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
             packed = None
     if packed is None:
         packed = engine.pack(spec)
+    tc_packed = engine.pack_tc(spec) if hasattr(engine, "pack_tc") else None
     dev = spec.ent0.device
     counters = torch.zeros((4, n), dtype=torch.int32, device=dev)  # raw_t, sub_t, raw_h, sub_h
     pending = []
@@ -279,16 +305,32 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
             shard.all_reduce_sum(trows)
         for side, true_idx, which, raw, sub in ((_lib.SIDE_TAIL, t, 0, counters[0], counters[1]),
                                                 (_lib.SIDE_HEAD, h, 1, counters[2], counters[3])):
-            handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
-                                      raw[lo:hi], sub[lo:hi])
-            pending.append((handle, which, lo, hi, sub))
+            if tc_packed is not None:
+                handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
+                                          raw[lo:hi], sub[lo:hi], tc_packed=tc_packed)
+            else:
+                handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
+                                          raw[lo:hi], sub[lo:hi])
+            pending.append((handle, which, lo, hi, sub, side, (hrows, trows, r, true_idx)))
     filts = [filt_tail, filt_head]
     for k in (0, 1):
         if callable(filts[k]):
             filts[k] = filts[k]()
-    for handle, which, lo, hi, sub in pending:
+    for handle, which, lo, hi, sub, side, inputs in pending:
         if filts[which] is not None:
             engine.filter_side(handle, _csr_slice(filts[which], lo, hi, n), sub[lo:hi])
+    if tc_packed is not None:
+        # the near-tie list of a tensor-core call is bounded; on overflow (never seen on real
+        # or synthetic embeddings, possible on adversarial ones) redo that side exactly
+        for handle, which, lo, hi, sub, side, (hrows, trows, r, true_idx) in pending:
+            stats = handle[6]
+            if stats is not None:
+                found, cap = (int(x) for x in stats.tolist())
+                if found > cap:
+                    raw = counters[0] if side == _lib.SIDE_TAIL else counters[2]
+                    raw[lo:hi].zero_()
+                    engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
+                                     raw[lo:hi], sub[lo:hi])
     del pending
     if shard is not None and shard.world > 1:
         shard.all_reduce_sum(counters)  # the single collective on the rank counters
