@@ -14,29 +14,32 @@ def run(code, d, n_ent, n_q, n_rel=1000, reps=3):
     rel0 = torch.randn(n_rel, d, device=dev, generator=g) * 0.07
     rel1 = torch.randn(n_rel, d, device=dev, generator=g) * 0.07 if planes == 2 else None
     spec = ModelSpec(code, d, n_ent, n_rel, ent0, ent1, rel0, rel1)
-    eng = CudaEngine()
+    import os
+    eng = CudaEngine(tensor_core=os.environ.get('QP_TC', '1') == '1')
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    t0.record(); packed = eng.pack(spec); t1.record(); torch.cuda.synchronize()
+    t0.record(); packed = eng.pack(spec); tcp = eng.pack_tc(spec); t1.record(); torch.cuda.synchronize()
     pack_ms = t0.elapsed_time(t1)
     h = torch.randint(0, n_ent, (n_q,), device=dev, generator=g)
     t = torch.randint(0, n_ent, (n_q,), device=dev, generator=g)
     r = torch.randint(0, n_rel, (n_q,), device=dev, generator=g)
     hrows = eng.gather_rows(spec, h); trows = eng.gather_rows(spec, t)
     out = {}
+    pairs = n_q * n_ent
     for side in (0, 1):
         raw = torch.zeros(n_q, dtype=torch.int32, device=dev); sub = torch.zeros_like(raw)
         best = 1e9
         for _ in range(reps):
             raw.zero_()
             t0.record()
-            ws = eng.rank_side(spec, packed, side, hrows, trows, r, t if side == 0 else h, None, raw, sub)
+            ws = eng.rank_side(spec, packed, side, hrows, trows, r, t if side == 0 else h, None, raw, sub, tc_packed=tcp)
             t1.record(); torch.cuda.synchronize()
             best = min(best, t0.elapsed_time(t1))
         out[side] = best
         assert int(raw.min()) >= 1, 'true entity must count itself'
+        if eng.tc_stats: out['amb%d' % side] = int(eng.tc_stats[-1][0]) / pairs
     pairs = n_q * n_ent
-    print('%-10s d=%4d nE=%8d nq=%6d pack %.2f ms | tail %.2f ms (%.2f Tpair-dim/s) head %.2f ms (%.2f) | mean raw rank %.0f' % (
-        _lib.MODEL_NAMES[code], d, n_ent, n_q, pack_ms, out[0], pairs * d / out[0] / 1e9, out[1], pairs * d / out[1] / 1e9, raw.float().mean().item()), flush=True)
+    print('%-10s d=%4d nE=%8d nq=%6d pack %.2f ms | tail %.2f ms (%.2f Tpair-dim/s) head %.2f ms (%.2f) | mean raw rank %.0f | near-tie frac %s' % (
+        _lib.MODEL_NAMES[code], d, n_ent, n_q, pack_ms, out[0], pairs * d / out[0] / 1e9, out[1], pairs * d / out[1] / 1e9, raw.float().mean().item(), (out.get('amb0'), out.get('amb1'))), flush=True)
 
 if __name__ == '__main__':
     n_ent = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000

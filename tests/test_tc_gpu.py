@@ -111,7 +111,7 @@ def test_exact_ties_and_duplicates_with_tensor_cores(cuda_device):
     kg, dh, dt = helpers.make_kg(n_ent, n_rel, n_facts=3000, n_test=200, seed=9)
     model = helpers.make_model("distmult", d, n_ent, n_rel, seed=9)
     with torch.no_grad():
-        model.ent_emb.weight[100:300] = model.ent_emb.weight[0:200]   # exact ties
+        model.ent_emb.weight[100:300] = model.ent_emb.weight[0:200].clone()   # exact ties
         model.ent_emb.weight[500:] = 0.0
     P = helpers.oracle_params("distmult", model)
     ref = oracle.link_prediction("distmult", P, kg.head_idx, kg.tail_idx, kg.relations, dh, dt, 50)
