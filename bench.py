@@ -128,6 +128,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)["bf16_tflops_sustained"]), "measured sustained bf16 (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 1400.0, "fallback (B200_PROFILING.md sustained)"
+
+
 class HostKG:
     """What LinkPredictionEvaluator reads from a knowledge graph."""
 
@@ -283,7 +294,8 @@ def run_ours(args, rank, local, world):
         ranks_dev = device_step()
     barrier()
     _lib.scan_timing_enable(True)
-    _lib.scan_timing_read()
+    for kind in (0, 1, 2):
+        _lib.scan_timing_read(kind)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -296,7 +308,9 @@ def run_ours(args, rank, local, world):
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = eng.launches - launches0
-    scan_n, scan_ms = _lib.scan_timing_read()
+    scan_n, scan_ms = _lib.scan_timing_read(0)
+    tc_n, tc_ms = _lib.scan_timing_read(1)
+    rc_n, rc_ms = _lib.scan_timing_read(2)
     _lib.scan_timing_enable(False)
     clock_rec = clocks.stop() if rank == 0 else None
     t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
@@ -329,34 +343,60 @@ def run_ours(args, rank, local, world):
         ranks_dev, (evaluator.rank_true_heads, evaluator.rank_true_tails,
                     evaluator.filt_rank_true_heads, evaluator.filt_rank_true_tails)))
 
-    # ---- roofline of the dominant kernel (dense scan) -------------------------------------
+    # ---- roofline of the dominant kernel -----------------------------------------------------
     peak, peak_src = measured_peaks()
     rows_here = hi - lo
     rb = row_bytes(code, dim)
-    # algorithmic bytes per scan launch = queries x candidate rows x row_bytes (SURVEY.md 8d:
-    # 2*nE*row_bytes per triple = nE*row_bytes per (triple, side) launch unit)
-    alg_bytes_per_launch = float(n_test) * rows_here * rb
-    scan_ms_per_launch = scan_ms / max(1, scan_n)
-    achieved = alg_bytes_per_launch / (scan_ms_per_launch / 1000.0) / 1e9
-    ops_per_elem = {_lib.TRANSE_L1: 2.5, _lib.TRANSE_L2: 3.5, _lib.DISTMULT: 2.0, _lib.RESCAL: 2.0,
-                    _lib.COMPLEX: 4.0, _lib.ROTATE: 7.0}[code]  # mean of tail/head fp32 ops per (q,c,k)
-    lane_ops = float(n_test) * rows_here * dim * ops_per_elem
     sm_mhz = (clock_rec or {}).get("sm_mhz") or 1965.0
-    fp32_peak = 148 * 128 * sm_mhz * 1e6
-    roofline = {
-        "kernel": "scan_kernel (dense rank scan)", "bound": "hbm", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "traffic": None,
-        "launches_timed": scan_n, "ms_per_launch": scan_ms_per_launch,
-        "scan_share_of_step": scan_ms / dev_ms if dev_ms > 0 else None,
-        "note": "algorithmic bytes = queries x rows x row_bytes per launch; every streamed candidate "
-                "tile is shared by 64 queries per CTA, so DRAM traffic is ~1/64 of this and the "
-                "kernel is fp32-issue bound (see fp32_issue)",
-        "fp32_issue": {"achieved_tlaneops": lane_ops / (scan_ms_per_launch / 1000.0) / 1e12,
-                       "peak_tlaneops": fp32_peak / 1e12,
-                       "frac": lane_ops / (scan_ms_per_launch / 1000.0) / fp32_peak,
-                       "ops_per_element": ops_per_elem},
-    }
+    near_ties = None
+    if tc_n > 0:
+        # tensor-core bound-and-refine scan: bf16x3 split GEMM (3 bf16 MMAs per fp32 product)
+        k_total = dim * (2 if code == _lib.COMPLEX else 1)
+        ms_per_launch = tc_ms / tc_n
+        alg_flops = 2.0 * n_test * rows_here * k_total          # the fp32 contraction itself
+        tensor_peak = measured_tensor_peak()
+        near_ties = sum(int(s_[0]) for s_ in eng.tc_stats[-2 * args.steps:]) / max(1, args.steps)
+        roofline = {
+            "kernel": "tc_scan_kernel (tcgen05 bf16x3 split GEMM + threshold epilogue)", "bound": "tensor",
+            "achieved": alg_flops / (ms_per_launch / 1000.0) / 1e12, "peak": tensor_peak[0],
+            "unit": "TFLOP/s", "frac": alg_flops / (ms_per_launch / 1000.0) / 1e12 / tensor_peak[0],
+            "peak_source": tensor_peak[1], "traffic": None,
+            "launches_timed": tc_n, "ms_per_launch": ms_per_launch,
+            "scan_share_of_step": tc_ms / dev_ms if dev_ms > 0 else None,
+            "recheck_ms_per_launch": rc_ms / max(1, rc_n),
+            "recheck_share_of_step": rc_ms / dev_ms if dev_ms > 0 else None,
+            "near_tie_pairs_per_step": near_ties,
+            "near_tie_fraction": near_ties / (2.0 * n_test * rows_here),
+            "executed_bf16_tflops": 3 * alg_flops / (ms_per_launch / 1000.0) / 1e12,
+            "note": "algorithmic flops = 2 x queries x rows x K (fp32 contraction); the kernel executes "
+                    "3 bf16 MMAs per product (hi*hi + lo*hi + hi*lo) and is L2->SM bandwidth bound "
+                    "(operand images stream at 12 B per (query, candidate)); near-ties are re-scored "
+                    "exactly so ranks stay bit-identical",
+        }
+    else:
+        # scalar fp32 scan.  algorithmic bytes per launch = queries x candidate rows x row_bytes
+        # (2*nE*row_bytes per triple = nE*row_bytes per (triple, side) launch unit)
+        alg_bytes_per_launch = float(n_test) * rows_here * rb
+        scan_ms_per_launch = scan_ms / max(1, scan_n)
+        achieved = alg_bytes_per_launch / (scan_ms_per_launch / 1000.0) / 1e9
+        ops_per_elem = {_lib.TRANSE_L1: 2.5, _lib.TRANSE_L2: 3.5, _lib.DISTMULT: 2.0, _lib.RESCAL: 2.0,
+                        _lib.COMPLEX: 4.0, _lib.ROTATE: 7.0}[code]  # mean of tail/head fp32 ops per (q,c,k)
+        lane_ops = float(n_test) * rows_here * dim * ops_per_elem
+        fp32_peak = 148 * 128 * sm_mhz * 1e6
+        roofline = {
+            "kernel": "scan_kernel (dense rank scan, fp32 pipes)", "bound": "hbm", "achieved": achieved,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+            "traffic": None,
+            "launches_timed": scan_n, "ms_per_launch": scan_ms_per_launch,
+            "scan_share_of_step": scan_ms / dev_ms if dev_ms > 0 else None,
+            "note": "algorithmic bytes = queries x rows x row_bytes per launch; every streamed candidate "
+                    "tile is shared by 64 queries per CTA, so DRAM traffic is ~1/64 of this and the "
+                    "kernel is fp32-issue bound (see fp32_issue)",
+            "fp32_issue": {"achieved_tlaneops": lane_ops / (scan_ms_per_launch / 1000.0) / 1e12,
+                           "peak_tlaneops": fp32_peak / 1e12,
+                           "frac": lane_ops / (scan_ms_per_launch / 1000.0) / fp32_peak,
+                           "ops_per_element": ops_per_elem},
+        }
 
     # ---- CPU baseline (oracle port) on a bounded sample + parity on that sample -----------
     cpu = None

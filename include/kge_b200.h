@@ -269,13 +269,14 @@ int kge_margin_step_bwd(const kge_margin_step_args_t* a, const kge_grads_t* g,
                         const float* grad_loss);
 
 /* ---- measurement hook ------------------------------------------------------------------
- * When enabled, every dense-scan launch (the dominant kernel of kge_rank_side /
- * kge_score_all) is bracketed by CUDA events recorded on the launch stream.
- * kge_scan_timing_read() synchronises those events, returns the number of launches and
- * their summed device time since the last read, and clears the record.  Used by bench.py
- * for the roofline figure; off by default (no events are created). */
+ * When enabled, the dominant kernels of kge_rank_side / kge_score_all are bracketed by CUDA
+ * events recorded on the launch stream: kind 0 = scalar dense scan, 1 = tensor-core scan,
+ * 2 = exact re-scoring of the near-tie list.  kge_scan_timing_read() synchronises the events
+ * of one kind, returns the number of launches and their summed device time since the last
+ * read, and clears that record.  Used by bench.py for the roofline figure; off by default
+ * (no events are created). */
 int kge_scan_timing_enable(int on);
-int kge_scan_timing_read(int64_t* launches, double* total_ms);
+int kge_scan_timing_read(int kind, int64_t* launches, double* total_ms);
 
 #ifdef __cplusplus
 }

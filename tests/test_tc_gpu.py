@@ -56,8 +56,9 @@ def test_approximate_scores_within_half_the_bound(kind, d, cuda_device):
         # the bound the kernel uses: gamma * |a| |b|  (dot) or gamma * (|a| + |b|)^2  (L2)
         k_total = 2 * d if kind == "complex" else d
         l2 = kind == "transe_l2"
-        split, accum = 3.0 * 2.0 ** -16, (3.0 * ((k_total + 15) // 16) + 2.0) * 2.0 ** -22
-        gamma = 2.0 * (split + accum + (k_total + 4.0) * 2.0 ** -24 + 8.0 * 2.0 ** -24) * (1.5 if l2 else 1.0)
+        gamma = (3.0 * 2.0 ** -16 + 2.0 * (3.0 * ((k_total + 15) // 16) + 2.0) * 2.0 ** -22
+                 + (k_total + 4.0) * 2.0 ** -24)                       # csrc/tc.h: tc_gamma
+        gamma2 = (k_total + 24.0) * 2.0 ** -23                         # csrc/tc.h: tc_gamma2
         # operand norms
         if kind == "complex":
             cand = torch.cat([P["re_ent"], P["im_ent"]], 1).double()
@@ -77,7 +78,9 @@ def test_approximate_scores_within_half_the_bound(kind, d, cuda_device):
             cand = P["ent"].double()
             q = ((P["ent"][h] + P["rel"][r]) if side == 0 else (P["ent"][t] - P["rel"][r])).double()
         na, nb = q.norm(dim=1).view(-1, 1), cand.norm(dim=1).view(1, -1)
-        bound = gamma * ((na + nb) ** 2 if l2 else na * nb)
+        if l2 and side == 1:   # head side: the kernel bounds |t - r| by |t| + |r| (see tc.cu)
+            na = (P["ent"][t].double().norm(dim=1) + P["rel"][r].double().norm(dim=1)).view(-1, 1)
+        bound = (2 * gamma * na * nb + gamma2 * (na + nb) ** 2) if l2 else gamma * na * nb
         ratio = ((got.double() - want).abs() / bound).max().item()
         assert ratio < 0.5, "%s %s d=%d: error / bound = %.3f" % (kind, name, d, ratio)
 

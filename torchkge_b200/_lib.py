@@ -106,7 +106,7 @@ SIGNATURES = {
     "kge_margin_step_fwd": (_c.c_int, [_c.POINTER(MarginStepArgs)]),
     "kge_margin_step_bwd": (_c.c_int, [_c.POINTER(MarginStepArgs), _c.POINTER(Grads), _p]),
     "kge_scan_timing_enable": (_c.c_int, [_c.c_int]),
-    "kge_scan_timing_read": (_c.c_int, [_c.POINTER(_c.c_int64), _c.POINTER(_c.c_double)]),
+    "kge_scan_timing_read": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_double)]),
 }
 
 _lock = threading.Lock()
@@ -163,8 +163,9 @@ def scan_timing_enable(on=True):
     check(load().kge_scan_timing_enable(1 if on else 0), "kge_scan_timing_enable")
 
 
-def scan_timing_read():
-    """(launches, total_ms) of the dense-scan kernel since the last read."""
+def scan_timing_read(kind=0):
+    """(launches, total_ms) since the last read for kind 0 = scalar dense scan, 1 = tensor-core
+    scan, 2 = exact recheck of the near-tie list."""
     n, ms = ctypes.c_int64(0), ctypes.c_double(0.0)
-    check(load().kge_scan_timing_read(ctypes.byref(n), ctypes.byref(ms)), "kge_scan_timing_read")
+    check(load().kge_scan_timing_read(kind, ctypes.byref(n), ctypes.byref(ms)), "kge_scan_timing_read")
     return n.value, ms.value

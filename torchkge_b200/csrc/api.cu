@@ -102,7 +102,7 @@ Workspace carve(void* base, int qw, int dim, int64_t n, int el = -1, int64_t n_r
     w.apack = static_cast<unsigned char*>(take(kge::tc::a_image_bytes(n, n_kb)));
     w.qbound = static_cast<float*>(take((size_t)n * sizeof(float)));
     w.qnorm2 = static_cast<float*>(take((size_t)n * sizeof(float)));
-    w.amb_count = static_cast<unsigned long long*>(take(sizeof(unsigned long long)));
+    w.amb_count = static_cast<unsigned long long*>(take(256 * sizeof(unsigned long long)));  // per-CTA regions
     // near-tie list: room for 1/256 of all pairs (the band is ~0.1 %), 1 Mi..128 Mi entries
     unsigned long long cap = (unsigned long long)n * (unsigned long long)n_rows / 256ull;
     if (cap < (1ull << 20)) cap = 1ull << 20;
@@ -139,26 +139,32 @@ bool model_needs_rel1(int model) { return model == KGE_COMPLEX || model == KGE_R
 // Optional CUDA-event bracketing of the scan launches (kge_scan_timing_*).
 std::mutex g_timing_mu;
 bool g_timing_on = false;
-std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timing_events;
+constexpr int TIMING_KINDS = 3;  // 0 scalar scan, 1 tensor-core scan, 2 exact recheck of near-ties
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timing_events[TIMING_KINDS];
 
-cudaError_t timed_scan(int el, bool casc, const kge::ScanParams& p, cudaStream_t st) {
+template <class Launch>
+cudaError_t timed_launch(int kind, cudaStream_t st, Launch&& launch) {
   bool on;
   {
     std::lock_guard<std::mutex> lock(g_timing_mu);
     on = g_timing_on;
   }
-  if (!on) return kge::launch_scan(el, casc, p, st);
+  if (!on) return launch();
   cudaEvent_t a, b;
   cudaError_t e = cudaEventCreate(&a);
   if (e != cudaSuccess) return e;
   e = cudaEventCreate(&b);
   if (e != cudaSuccess) return e;
   cudaEventRecord(a, st);
-  e = kge::launch_scan(el, casc, p, st);
+  e = launch();
   cudaEventRecord(b, st);
   std::lock_guard<std::mutex> lock(g_timing_mu);
-  g_timing_events.emplace_back(a, b);
+  g_timing_events[kind].emplace_back(a, b);
   return e;
+}
+
+cudaError_t timed_scan(int el, bool casc, const kge::ScanParams& p, cudaStream_t st) {
+  return timed_launch(0, st, [&] { return kge::launch_scan(el, casc, p, st); });
 }
 
 }  // namespace
@@ -318,7 +324,10 @@ int kge_rank_side(const kge_rank_args_t* a) {
     KGE_CUDA_TRY(kge::tc::launch_pack_a(w.qplain, qw, a->n, a->dim, k_total, n_kb,
                                         el == kge::EL_L2_HEAD ? 1 : 0, w.apack, w.qbound, w.qnorm2, st),
                  "tc pack queries");
-    KGE_CUDA_TRY(cudaMemsetAsync(w.amb_count, 0, sizeof(unsigned long long), st), "tc reset list");
+    const int regions = kge::tc::scan_grid_size(a->n, a->n_rows);
+    if (regions <= 0 || regions > 256) return fail(KGE_ERR_CUDA, "kge_rank_side: cannot size the tensor-core grid");
+    const unsigned long long region_cap = w.amb_cap / (unsigned long long)regions;
+    KGE_CUDA_TRY(cudaMemsetAsync(w.amb_count, 0, 256 * sizeof(unsigned long long), st), "tc reset list");
     const unsigned char* bpack = static_cast<const unsigned char*>(a->tc_packed);
     const float* cbound = reinterpret_cast<const float*>(bpack + kge::tc::b_image_bytes(a->n_rows, n_kb));
     kge::tc::TcScanParams tp;
@@ -326,21 +335,18 @@ int kge_rank_side(const kge_rank_args_t* a) {
     tp.qbound = w.qbound; tp.qnorm2 = w.qnorm2;
     tp.cbound = cbound; tp.cnorm2 = cbound + (size_t)n_ct * kge::tc::TC_BN;
     tp.counts = a->raw_count; tp.amb_count = w.amb_count; tp.amb_pairs = w.amb_pairs;
-    tp.amb_cap = w.amb_cap; tp.dump = a->tc_dump;
-    tp.gamma = kge::tc::tc_gamma(k_total, l2); tp.l2 = l2 ? 1 : 0;
+    tp.amb_cap = region_cap; tp.dump = a->tc_dump;
+    tp.gamma = kge::tc::tc_gamma(k_total); tp.gamma2 = kge::tc::tc_gamma2(k_total); tp.l2 = l2 ? 1 : 0;
     tp.n_kb = n_kb; tp.k_total = k_total;
     tp.n_q = a->n; tp.n_rows = a->n_rows;
     tp.n_qt = (a->n + kge::tc::TC_BM - 1) / kge::tc::TC_BM; tp.n_ct = n_ct;
-    KGE_CUDA_TRY(kge::tc::launch_tc_scan(tp, st), "tc scan");
-    KGE_CUDA_TRY(kge::tc::launch_recheck(el, casc, a->dim, w.amb_count, w.amb_cap, w.amb_pairs, w.qplain,
-                                         a->ent0, a->ent1, w.perm, w.code, w.s_true, a->raw_count, st),
+    KGE_CUDA_TRY(timed_launch(1, st, [&] { return kge::tc::launch_tc_scan(tp, st); }), "tc scan");
+    KGE_CUDA_TRY(timed_launch(2, st, [&] {
+                   return kge::tc::launch_recheck(el, a->dim, w.amb_count, regions, region_cap, w.amb_pairs,
+                                                  w.qplain, a->ent0, a->ent1, w.s_true, a->raw_count,
+                                                  reinterpret_cast<unsigned long long*>(a->tc_stats), st);
+                 }),
                  "tc recheck");
-    if (a->tc_stats) {
-      KGE_CUDA_TRY(cudaMemcpyAsync(a->tc_stats, w.amb_count, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st),
-                   "tc stats");
-      KGE_CUDA_TRY(cudaMemcpyAsync(a->tc_stats + 1, &w.amb_cap, sizeof(uint64_t), cudaMemcpyHostToDevice, st),
-                   "tc stats cap");
-    }
     if (a->filt_offs && a->n_filt > 0)
       KGE_CUDA_TRY(kge::launch_filter(el, casc, a->dim, a->n, a->n_filt, w.qplain, a->ent0, a->ent1,
                                       a->ent_lo, a->n_rows, a->filt_offs, a->filt_ids, w.perm,
@@ -551,11 +557,12 @@ int kge_scan_timing_enable(int on) {
   return KGE_OK;
 }
 
-int kge_scan_timing_read(int64_t* launches, double* total_ms) {
+int kge_scan_timing_read(int kind, int64_t* launches, double* total_ms) {
+  if (kind < 0 || kind >= TIMING_KINDS) return fail(KGE_ERR_ARG, "kge_scan_timing_read: bad kind");
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
   {
     std::lock_guard<std::mutex> lock(g_timing_mu);
-    ev.swap(g_timing_events);
+    ev.swap(g_timing_events[kind]);
   }
   double total = 0.0;
   int rc = KGE_OK;

@@ -38,10 +38,12 @@ constexpr int A_PLANE = BM * 128;  // bytes of one 128-row x 64-bf16 swizzled pl
 constexpr int B_PLANE = BN * 128;
 constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // A hi, A lo, B hi, B lo = 96 KB
 constexpr int NORM_FLOATS = 2 * BN;                     // cb[256], cn[256] per buffer
+constexpr int AMB_BUF = 128;                            // near-tie entries buffered per epilogue warp
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
-                              2 * NORM_FLOATS * sizeof(float) + 16 * sizeof(uint64_t) + 16;
+                              2 * NORM_FLOATS * sizeof(float) + 16 * sizeof(uint64_t) + 16 +
+                              4 * AMB_BUF * sizeof(int2);
 
 // -------- PTX helpers specific to tcgen05 --------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -124,6 +126,7 @@ struct Units {
   }
 };
 
+template <bool L2, bool DUMP>
 __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_constant__ TcScanParams p) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-B alignment for the 128-byte swizzle atoms
@@ -137,6 +140,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
   uint64_t* tfull_bar = bars + 4;       // [2]
   uint64_t* tempty_bar = bars + 6;      // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
+  int2* s_amb = reinterpret_cast<int2*>(bars + 10);  // [4 warps][AMB_BUF]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Units units(p.n_qt, p.n_ct);
@@ -216,6 +220,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
     float st = 0.f, qb = 0.f, qn = 0.f;
     int cnt = 0;
     int nbuf = 0;
+    int2* wbuf = s_amb + (warp - 2) * AMB_BUF;  // this warp's near-tie buffer
+    int amb_n = 0;                              // entries in it (warp-uniform)
     for (long long u = blockIdx.x; u < units.n_units; u += gridDim.x) {
      long long qt, ct_lo, ct_hi; units.decode(u, &qt, &ct_lo, &ct_hi);
      for (long long ct = ct_lo; ct < ct_hi; ++ct) {
@@ -244,28 +250,85 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
       fence_after();
       const int ncols = (int)min((long long)BN, p.n_rows - ct * BN);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      // per-thread constants of the threshold test  u = s~ - s_true  vs  eps
+      const float g_qb = p.gamma * qb;        // dot: eps = g_qb * cb[c]
+      const float g2_qb = 2.f * g_qb;         // L2 : eps = 2 gamma qb cb + gamma2 (qb + cb)^2
+      const float l2_off = -(qn + st);        // L2 : u = 2 dot + l2_off - cn[c]
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         const int lim = min(32, ncols - c0);
+        // 32 independent threshold tests -> two bit masks per thread (no per-element branches)
+        unsigned amb_mask = 0, gt_mask = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (j < lim) {
-            const float dot = __uint_as_float(v[j]);
-            // approximate score: dot product, or -(|q|^2 + |c|^2 - 2 q.c)
-            float s;
-            if (p.l2) s = -((qn + cns[c0 + j]) - 2.f * dot); else s = dot;
-            const float e = p.l2 ? p.gamma * (qb + cbs[c0 + j]) * (qb + cbs[c0 + j])
-                                 : p.gamma * qb * cbs[c0 + j];
-            const float u = s - st;
-            if (p.dump) {
-              if (q < p.n_q) p.dump[(size_t)q * p.n_rows + ct * BN + c0 + j] = s;
-            } else if (fabsf(u) <= e) {
-              // near-tie band (also catches NaN-free exact ties): exact re-score later
-              const unsigned long long slot = atomicAdd(p.amb_count, 1ull);
-              if (slot < p.amb_cap) p.amb_pairs[slot] = make_int2((int)q, (int)(ct * BN + c0 + j));
-            } else if (u > e) {
-              ++cnt;
+          const float dot = __uint_as_float(v[j]);
+          float u, e;
+          if constexpr (L2) {
+            u = fmaf(2.f, dot, l2_off) - cns[c0 + j];
+            const float cbj = cbs[c0 + j];
+            const float w = qb + cbj;
+            e = fmaf(g2_qb, cbj, p.gamma2 * w * w);
+          } else {
+            u = dot - st;
+            e = g_qb * cbs[c0 + j];
+          }
+          if constexpr (DUMP) {
+            if (j < lim && q < p.n_q) p.dump[(size_t)q * p.n_rows + ct * BN + c0 + j] = L2 ? u + st : dot;
+          } else {
+            amb_mask |= (fabsf(u) <= e ? 1u : 0u) << j;
+            gt_mask |= (u > e ? 1u : 0u) << j;
+          }
+        }
+        if constexpr (!DUMP) {
+          if (lim < 32) {  // columns past the table (last tile only)
+            const unsigned keep = (1u << lim) - 1u;
+            amb_mask &= keep; gt_mask &= keep;
+          }
+          cnt += __popc(gt_mask);
+          if (__any_sync(0xffffffffu, amb_mask != 0)) {
+            // near-ties in this 32 x 32 block: warp prefix sum of the per-lane counts, entries
+            // into this warp's shared buffer, one global atomic per ~100 entries on flush
+            const int mine = __popc(amb_mask);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int up = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += up;
+            }
+            const int total_new = __shfl_sync(0xffffffffu, incl, 31);
+            if (amb_n + total_new > AMB_BUF) {  // flush first (uniform decision)
+              __syncwarp();
+              unsigned long long base = 0;
+              if (lane == 0) base = atomicAdd(p.amb_count + blockIdx.x, (unsigned long long)amb_n);
+              base = __shfl_sync(0xffffffffu, base, 0);
+              for (int i = lane; i < amb_n; i += 32)
+                if (base + i < p.amb_cap) p.amb_pairs[(size_t)blockIdx.x * p.amb_cap + base + i] = wbuf[i];
+              __syncwarp();
+              amb_n = 0;
+            }
+            if (total_new <= AMB_BUF) {
+              int slot = amb_n + incl - mine;
+              unsigned m = amb_mask;
+              while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                wbuf[slot++] = make_int2((int)q, (int)(ct * BN + c0 + j));
+              }
+              amb_n += total_new;
+            } else {
+              // pathological block (more near-ties than the buffer holds): straight to global
+              unsigned long long base = 0;
+              if (lane == 0) base = atomicAdd(p.amb_count + blockIdx.x, (unsigned long long)total_new);
+              base = __shfl_sync(0xffffffffu, base, 0) + (unsigned long long)(incl - mine);
+              unsigned m = amb_mask;
+              while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                if (base < p.amb_cap)
+                  p.amb_pairs[(size_t)blockIdx.x * p.amb_cap + base] = make_int2((int)q, (int)(ct * BN + c0 + j));
+                ++base;
+              }
             }
           }
         }
@@ -280,6 +343,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
     if (cur_qt >= 0 && cnt != 0) {
       const long long pq = cur_qt * BM + row;
       if (pq < p.n_q) atomicAdd(&p.counts[pq], cnt);
+    }
+    if (amb_n > 0) {  // final flush of this warp's near-tie buffer
+      __syncwarp();
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(p.amb_count + blockIdx.x, (unsigned long long)amb_n);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (int i = lane; i < amb_n; i += 32)
+        if (base + i < p.amb_cap) p.amb_pairs[(size_t)blockIdx.x * p.amb_cap + base + i] = wbuf[i];
     }
   }
   fence_before();
@@ -349,45 +420,257 @@ __global__ void row_norms_kernel(const float* __restrict__ src0, const float* __
   if (w >= n_rows) return;
   const float* a = src0 + (size_t)w * row_stride;
   const float* b = src1 ? src1 + (size_t)w * row_stride : a + plane1_offset;
-  double s = 0.0;
+  double s = 0.0, sa = 0.0, sb = 0.0;
   for (int k = lane; k < k_total; k += 32) {
     float x;
-    if (sub_mode) x = k < dim ? __fsub_rn(b[k], a[k]) : 0.f;
-    else x = operand_value(a, b, dim, k, k_total);
+    if (sub_mode) {
+      x = k < dim ? __fsub_rn(b[k], a[k]) : 0.f;
+      if (k < dim) { sa += (double)a[k] * (double)a[k]; sb += (double)b[k] * (double)b[k]; }
+    } else {
+      x = operand_value(a, b, dim, k, k_total);
+    }
     s += (double)x * (double)x;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
   if (lane == 0) {
     norm2[w] = (float)s;
-    bound[w] = (float)(sqrt(s) * (1.0 + 1e-6)) + 1e-30f;
+    // L2 head side: the reference rounds c + r before subtracting t, an error that scales with
+    // |r| and |t| separately, so the bound uses |t| + |r| (>= |t - r|) for this operand
+    const double nb = sub_mode ? sqrt(sa) + sqrt(sb) : sqrt(s);
+    bound[w] = (float)(nb * (1.0 + 1e-6)) + 1e-30f;
   }
 }
 
-// exact adjudication of the near-tie band
-template <int EL, bool CASC>
-__global__ void recheck_kernel(int dim, const unsigned long long* __restrict__ n_pairs_dev,
-                               unsigned long long cap, const int2* __restrict__ pairs,
+// Exact score of one pair in NATURAL index order.  Same arithmetic as replaying the schedule
+// (every chain of the ATen reduction receives the same terms in the same order, chains are
+// combined in the same order) but the embedding index runs 0, 1, 2, ... so each thread streams
+// its two rows sequentially instead of revisiting every 32-byte sector eight times; the chain
+// accumulators live in registers (8 for the L2 norm, 32 (+32 cascade) for the cascade sum).
+template <int EL>
+__device__ __forceinline__ float elem_at(const float* q0, const float* q1, const float* c0,
+                                         const float* c1, int k) {
+  return elem_value<EL>(q0[k], q1[k], c0[k], c1[k]);
+}
+
+template <int EL>
+__device__ float pair_score_natural(int dim, const float* __restrict__ q0, const float* __restrict__ q1,
+                                    const float* __restrict__ c0, const float* __restrict__ c1) {
+  if constexpr (ElemTraits<EL>::RED == RED_NORM2) {
+    const int main_len = dim - dim % 8;
+    float acc[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc[l] = 0.f;
+    for (int k = 0; k < main_len; k += 8) {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        const float x = elem_at<EL>(q0, q1, c0, c1, k + l);
+        acc[l] = __fadd_rn(acc[l], __fmul_rn(x, x));
+      }
+    }
+    float t = 0.f;
+    if (main_len > 0) {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) t = __fadd_rn(t, acc[l]);
+    }
+    int k = main_len;
+    for (; k + 4 <= dim; k += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = elem_at<EL>(q0, q1, c0, c1, k + j);
+        t = __fadd_rn(t, __fmul_rn(x, x));
+      }
+    }
+    for (; k < dim; ++k) {
+      const float x = elem_at<EL>(q0, q1, c0, c1, k);
+      t = __fmaf_rn(x, x, t);
+    }
+    Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
+    return acc_finish<EL>(r);
+  } else {  // RED_SUM
+    float t = 0.f;
+    if (dim >= 8) {
+      const int vec_size = dim / 8, rows = vec_size / 4;
+      const bool casc = rows >= 16;
+      for (int k = vec_size * 8; k < dim; ++k) t = __fadd_rn(t, elem_at<EL>(q0, q1, c0, c1, k));
+      float acc[4][8], acc1[4][8];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) { acc[m][l] = 0.f; acc1[m][l] = 0.f; }
+      for (int i = 0; i < rows; ++i) {
+        const int k0 = i * 32;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int l = 0; l < 8; ++l)
+            acc[m][l] = __fadd_rn(acc[m][l], elem_at<EL>(q0, q1, c0, c1, k0 + m * 8 + l));
+        if (((i + 1) & 15) == 0) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int l = 0; l < 8; ++l) { acc1[m][l] = __fadd_rn(acc1[m][l], acc[m][l]); acc[m][l] = 0.f; }
+        }
+      }
+      if (casc) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int l = 0; l < 8; ++l) acc[m][l] = __fadd_rn(acc[m][l], acc1[m][l]);
+      }
+      for (int j = rows * 4; j < vec_size; ++j) {
+#pragma unroll
+        for (int l = 0; l < 8; ++l) acc[0][l] = __fadd_rn(acc[0][l], elem_at<EL>(q0, q1, c0, c1, j * 8 + l));
+      }
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        float pl = acc[0][l];
+        if (rows > 0) {
+#pragma unroll
+          for (int m = 1; m < 4; ++m) pl = __fadd_rn(pl, acc[m][l]);
+        }
+        t = __fadd_rn(t, pl);
+      }
+    } else {  // one lane: 4 interleaved chains, leftovers to chain 0
+      const int rows = dim / 4;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < rows; ++i) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc[m] = __fadd_rn(acc[m], elem_at<EL>(q0, q1, c0, c1, i * 4 + m));
+      }
+      for (int k = rows * 4; k < dim; ++k) acc[0] = __fadd_rn(acc[0], elem_at<EL>(q0, q1, c0, c1, k));
+      float pl = acc[0];
+      if (rows > 0) {
+#pragma unroll
+        for (int m = 1; m < 4; ++m) pl = __fadd_rn(pl, acc[m]);
+      }
+      t = __fadd_rn(t, pl);
+    }
+    Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
+    return acc_finish<EL>(r);
+  }
+}
+
+// Exact adjudication of the near-tie band (the list is kept as one region per CTA of the scan).
+// Chain-parallel: the independent chains of the ATen reduction are spread over the lanes of a
+// warp -- 8 lanes per pair for the L2 norm (4 pairs per warp), 32 lanes per pair for the
+// cascade sum -- so each step reads 32 / 128 contiguous bytes of the two rows; chains are then
+// combined through shuffles in exactly the schedule's order.  Same bits as pair_score_natural.
+template <int EL>
+__device__ __forceinline__ float pair_score_chains(int dim, const float* __restrict__ q0,
+                                                   const float* __restrict__ q1,
+                                                   const float* __restrict__ c0,
+                                                   const float* __restrict__ c1, int lane) {
+  if constexpr (ElemTraits<EL>::RED == RED_NORM2) {
+    const int l8 = lane & 7, g8 = lane & 24;  // lane of the norm, first lane of this pair's group
+    const int main_len = dim - dim % 8;
+    float acc = 0.f;
+    for (int k = l8; k < main_len; k += 8) {
+      const float x = elem_at<EL>(q0, q1, c0, c1, k);
+      acc = __fadd_rn(acc, __fmul_rn(x, x));
+    }
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      const float v = __shfl_sync(0xffffffffu, acc, g8 + l);
+      if (main_len > 0) t = __fadd_rn(t, v);
+    }
+    int k = main_len;
+    for (; k + 4 <= dim; k += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = elem_at<EL>(q0, q1, c0, c1, k + j);
+        t = __fadd_rn(t, __fmul_rn(x, x));
+      }
+    }
+    for (; k < dim; ++k) {
+      const float x = elem_at<EL>(q0, q1, c0, c1, k);
+      t = __fmaf_rn(x, x, t);
+    }
+    Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
+    return acc_finish<EL>(r);
+  } else {  // RED_SUM, dim >= 8: lane = 8 m + l owns chain (row m, lane l)
+    const int vec_size = dim / 8, rows = vec_size / 4;
+    float acc = 0.f, acc1 = 0.f;
+    for (int i = 0; i < rows; ++i) {
+      acc = __fadd_rn(acc, elem_at<EL>(q0, q1, c0, c1, i * 32 + lane));
+      if (((i + 1) & 15) == 0) { acc1 = __fadd_rn(acc1, acc); acc = 0.f; }
+    }
+    if (rows >= 16) acc = __fadd_rn(acc, acc1);
+    if (lane < 8)
+      for (int j = rows * 4; j < vec_size; ++j) acc = __fadd_rn(acc, elem_at<EL>(q0, q1, c0, c1, j * 8 + lane));
+    const int l = lane & 7;
+    float pl = __shfl_sync(0xffffffffu, acc, l);
+#pragma unroll
+    for (int m = 1; m < 4; ++m) {
+      const float v = __shfl_sync(0xffffffffu, acc, 8 * m + l);
+      if (rows > 0) pl = __fadd_rn(pl, v);
+    }
+    float t = 0.f;
+    for (int k = vec_size * 8; k < dim; ++k) t = __fadd_rn(t, elem_at<EL>(q0, q1, c0, c1, k));
+#pragma unroll
+    for (int ll = 0; ll < 8; ++ll) t = __fadd_rn(t, __shfl_sync(0xffffffffu, pl, ll));
+    Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
+    return acc_finish<EL>(r);
+  }
+}
+
+template <int EL>
+__global__ void recheck_kernel(int dim, const unsigned long long* __restrict__ region_counts,
+                               unsigned long long region_cap, const int2* __restrict__ pairs,
                                const float* __restrict__ qplain, const float* __restrict__ ent0,
-                               const float* __restrict__ ent1, const int32_t* __restrict__ perm,
-                               const uint8_t* __restrict__ code, const float* __restrict__ s_true,
+                               const float* __restrict__ ent1, const float* __restrict__ s_true,
                                int32_t* __restrict__ counts) {
   constexpr int QW = ElemTraits<EL>::QW, CW = ElemTraits<EL>::CW;
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long n_pairs = min(*n_pairs_dev, cap);
-  if (i >= n_pairs) return;
-  const int2 pr = pairs[i];
-  const float* q0 = qplain + (size_t)pr.x * QW * dim;
-  const float* q1 = q0 + (size_t)(QW - 1) * dim;
-  const float* c0 = ent0 + (size_t)pr.y * dim;
-  const float* c1 = (CW == 2 ? ent1 : ent0) + (size_t)pr.y * dim;
-  Acc r;
-  acc_reset(r);
-  for (int pos = 0; pos < dim; ++pos) {
-    const int k = perm[pos];
-    acc_step<EL, CASC>(r, code[pos], q0[k], q1[k], c0[k], c1[k]);
+  constexpr bool NORM = ElemTraits<EL>::RED == RED_NORM2;
+  constexpr int PAIRS_PER_WARP = NORM ? 4 : 1;
+  const unsigned long long region = blockIdx.y;
+  const unsigned long long n_pairs = min(region_counts[region], region_cap);
+  const int lane = threadIdx.x & 31;
+  const unsigned long long warp_global = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  const int2* list = pairs + region * region_cap;
+  if (!NORM && dim < 8) {  // one-lane schedule: plain per-thread scorer
+    for (unsigned long long i = warp_global * 32 + lane; i < n_pairs; i += n_warps * 32) {
+      const int2 pr = list[i];
+      const float* q0 = qplain + (size_t)pr.x * QW * dim;
+      const float* c0 = ent0 + (size_t)pr.y * dim;
+      if (pair_score_natural<EL>(dim, q0, q0 + (size_t)(QW - 1) * dim, c0,
+                                 (CW == 2 ? ent1 : ent0) + (size_t)pr.y * dim) >= s_true[pr.x])
+        atomicAdd(&counts[pr.x], 1);
+    }
+    return;
   }
-  if (acc_finish<EL>(r) >= s_true[pr.x]) atomicAdd(&counts[pr.x], 1);
+  for (unsigned long long base = warp_global * PAIRS_PER_WARP; base < n_pairs; base += n_warps * PAIRS_PER_WARP) {
+    const unsigned long long i = base + (NORM ? (lane >> 3) : 0);
+    const bool valid = i < n_pairs;
+    const int2 pr = list[valid ? i : base];  // idle groups redo the first pair (shuffles stay uniform)
+    const float* q0 = qplain + (size_t)pr.x * QW * dim;
+    const float* q1 = q0 + (size_t)(QW - 1) * dim;
+    const float* c0 = ent0 + (size_t)pr.y * dim;
+    const float* c1 = (CW == 2 ? ent1 : ent0) + (size_t)pr.y * dim;
+    const float sc = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane);
+    const bool leader = NORM ? ((lane & 7) == 0) : (lane == 0);
+    if (valid && leader && sc >= s_true[pr.x]) atomicAdd(&counts[pr.x], 1);
+  }
+}
+
+// stats[0] = near-tie pairs found (or capacity + 1 if any region overflowed), stats[1] = capacity
+__global__ void tc_stats_kernel(const unsigned long long* __restrict__ region_counts, int regions,
+                                unsigned long long region_cap, unsigned long long* __restrict__ stats) {
+  unsigned long long total = 0;
+  bool over = false;
+  for (int r = 0; r < regions; ++r) {
+    total += region_counts[r];
+    over |= region_counts[r] > region_cap;
+  }
+  const unsigned long long cap = region_cap * (unsigned long long)regions;
+  stats[0] = over ? cap + 1 : total;
+  stats[1] = cap;
 }
 
 }  // namespace
@@ -431,42 +714,55 @@ cudaError_t launch_pack_a(const float* qplain, int qw, long long n_q, int dim, i
 cudaError_t launch_tc_scan(const TcScanParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)SMEM_BYTES);
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto kern) {
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    };
+    set(tc_scan_kernel<false, false>); set(tc_scan_kernel<true, false>);
+    set(tc_scan_kernel<false, true>); set(tc_scan_kernel<true, true>);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  int dev = 0, sms = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (e != cudaSuccess) return e;
-  const long long units = p.n_qt * ((p.n_ct + TC_CT_GROUP - 1) / TC_CT_GROUP);
-  if (units <= 0) return cudaSuccess;
-  const int grid = (int)(units < sms ? units : sms);
-  tc_scan_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(p);
+  const int grid = scan_grid_size(p.n_q, p.n_rows);
+  if (grid <= 0) return cudaSuccess;
+  if (p.dump) {
+    if (p.l2) tc_scan_kernel<true, true><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    else tc_scan_kernel<false, true><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+  } else {
+    if (p.l2) tc_scan_kernel<true, false><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    else tc_scan_kernel<false, false><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+  }
   return cudaGetLastError();
 }
 
-cudaError_t launch_recheck(int el, bool cascade, int dim, const unsigned long long* n_pairs_dev,
-                           unsigned long long cap, const int2* pairs,
-                           const float* qplain, const float* ent0, const float* ent1,
-                           const int32_t* perm, const uint8_t* code, const float* s_true,
-                           int32_t* counts, cudaStream_t st) {
-  if (cap == 0) return cudaSuccess;
-  const unsigned blocks = (unsigned)((cap + 127) / 128);
-#define CALL_RC(EL, C)                                                                        \
-  recheck_kernel<EL, C><<<blocks, 128, 0, st>>>(dim, n_pairs_dev, cap, pairs, qplain, ent0, ent1, \
-                                                perm, code, s_true, counts)
+cudaError_t launch_recheck(int el, int dim, const unsigned long long* region_counts, int regions,
+                           unsigned long long region_cap, const int2* pairs, const float* qplain,
+                           const float* ent0, const float* ent1, const float* s_true, int32_t* counts,
+                           unsigned long long* stats, cudaStream_t st) {
+  if (regions <= 0 || region_cap == 0) return cudaSuccess;
+  dim3 grid(96, (unsigned)regions);
+#define CALL_RC(EL) \
+  recheck_kernel<EL><<<grid, 128, 0, st>>>(dim, region_counts, region_cap, pairs, qplain, ent0, ent1, s_true, counts)
   switch (el) {
-    case EL_DOT1: if (cascade) { CALL_RC(EL_DOT1, true); } else { CALL_RC(EL_DOT1, false); } break;
-    case EL_DOT2: if (cascade) { CALL_RC(EL_DOT2, true); } else { CALL_RC(EL_DOT2, false); } break;
-    case EL_L2_TAIL: CALL_RC(EL_L2_TAIL, false); break;
-    case EL_L2_HEAD: CALL_RC(EL_L2_HEAD, false); break;
+    case EL_DOT1: CALL_RC(EL_DOT1); break;
+    case EL_DOT2: CALL_RC(EL_DOT2); break;
+    case EL_L2_TAIL: CALL_RC(EL_L2_TAIL); break;
+    case EL_L2_HEAD: CALL_RC(EL_L2_HEAD); break;
     default: return cudaErrorInvalidValue;
   }
 #undef CALL_RC
+  if (stats) tc_stats_kernel<<<1, 1, 0, st>>>(region_counts, regions, region_cap, stats);
   return cudaGetLastError();
+}
+
+int scan_grid_size(long long n_q, long long n_rows) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  const long long n_qt = (n_q + BM - 1) / BM, n_ct = (n_rows + BN - 1) / BN;
+  const long long units = n_qt * ((n_ct + TC_CT_GROUP - 1) / TC_CT_GROUP);
+  return (int)(units < sms ? units : sms);
 }
 
 }  // namespace tc

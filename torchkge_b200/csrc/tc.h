@@ -20,33 +20,39 @@ struct TcScanParams {
   const float* cbound;         // [n_rows] >= |b|_2
   const float* cnorm2;         // [n_rows]
   int32_t* counts;             // [n_q] +=
-  unsigned long long* amb_count;
-  int2* amb_pairs;
-  unsigned long long amb_cap;
+  unsigned long long* amb_count;  // [gridDim.x] per-CTA region fill counts
+  int2* amb_pairs;                // [gridDim.x][amb_cap]
+  unsigned long long amb_cap;     // capacity of ONE region
   float* dump;                 // debug: write approximate scores [n_q][n_rows] instead of counting
-  float gamma;                 // relative error bound factor (tc_gamma)
-  int l2;                      // 1: score = -(|a|^2 + |b|^2 - 2 a.b), eps = gamma (|a|+|b|)^2
+  float gamma;                 // tc_gamma(k)
+  float gamma2;                // tc_gamma2(k) (L2 only)
+  int l2;                      // 1: score = -(|a|^2 + |b|^2 - 2 a.b)
   int n_kb;
   int k_total;
   long long n_q, n_rows, n_qt, n_ct;
 };
 
-// Bound on |s_tc - s_ATen| relative to |a|_2 |b|_2 (dot models) or (|a|_2 + |b|_2)^2 (L2):
-//   splitting x = hi + lo + r, |r| <= 2^-16 |x| (two bf16 roundings)   -> 3 * 2^-16 incl. lo*lo
-//   fp32 accumulation on the tensor core, <= 2 ulp per MMA instruction  -> (3 k/16 + 2) * 2^-22
-//   the reference's own fp32 evaluation (products, <= k-term sums)      -> (k + 4) * 2^-24
-//   epilogue arithmetic (norm sums, scaling)                            -> 8 * 2^-24
-// times a safety factor of 2.  tests/test_tc_gpu.py measures the actual error (it is ~20x
-// smaller) and checks it stays below half of this.
-inline float tc_gamma(int k_total, bool l2) {
+// Rigorous bound eps >= |s_tc - s_ATen| used by the threshold test:
+//   dot models : eps = gamma  * |a| |b|
+//   L2         : eps = gamma  * 2 |a| |b|  +  gamma2 * (|a| + |b|)^2
+// gamma collects everything proportional to sum_k |a_k b_k| <= |a| |b|:
+//   bf16 splitting x = hi + lo + r, |r| <= 2^-16 |x| (two roundings to 8 significant bits):
+//     dropped lo*lo, a*r_b, r_a*b                                   -> 3 * 2^-16       (exact bound)
+//   fp32 accumulation inside the tensor core: assumed <= 2 ulp of the running magnitude per
+//     MMA instruction, 3 instructions per 16 terms, doubled for safety -> 2 (3 ceil(k/16) + 2) 2^-22
+//   the reference's own fp32 evaluation of the products and their <= k-term sums (any order)
+//                                                                    -> (k + 4) * 2^-24 (exact bound)
+// gamma2 (L2 only) collects what is proportional to the squared norms: the reference's fp32 sum
+// of squares / sqrt / square, forming t - r in fp32, and the epilogue's |a|^2 + |b|^2 - 2ab.
+// tests/test_tc_gpu.py measures the actual error on every model and requires it to stay below
+// half of the bound (it is ~10-20x smaller).
+inline float tc_gamma(int k_total) {
   const double split = 3.0 * 0x1p-16;
-  const double accum = (3.0 * ((k_total + 15) / 16) + 2.0) * 0x1p-22;
+  const double accum = 2.0 * (3.0 * ((k_total + 15) / 16) + 2.0) * 0x1p-22;
   const double ref = (k_total + 4.0) * 0x1p-24;
-  const double epi = 8.0 * 0x1p-24;
-  double g = 2.0 * (split + accum + ref + epi);
-  if (l2) g *= 1.5;  // the three-term expansion |a|^2 + |b|^2 - 2ab carries each error once more
-  return (float)g;
+  return (float)(split + accum + ref);
 }
+inline float tc_gamma2(int k_total) { return (float)((k_total + 24.0) * 0x1p-23); }
 
 size_t a_image_bytes(long long n_q, int n_kb);
 size_t b_image_bytes(long long n_rows, int n_kb);
@@ -56,11 +62,13 @@ cudaError_t launch_pack_a(const float* qplain, int qw, long long n_q, int dim, i
                           int sub_mode, unsigned char* apack, float* qbound, float* qnorm2,
                           cudaStream_t st);
 cudaError_t launch_tc_scan(const TcScanParams& p, cudaStream_t st);
-cudaError_t launch_recheck(int el, bool cascade, int dim, const unsigned long long* n_pairs_dev,
-                           unsigned long long cap, const int2* pairs,
-                           const float* qplain, const float* ent0, const float* ent1,
-                           const int32_t* perm, const uint8_t* code, const float* s_true,
-                           int32_t* counts, cudaStream_t st);
+// The near-tie list is split into one region per CTA of the scan (regions = scan_grid_size):
+// region_counts[regions] (zeroed by the caller), pairs[regions][region_cap].
+int scan_grid_size(long long n_q, long long n_rows);
+cudaError_t launch_recheck(int el, int dim, const unsigned long long* region_counts, int regions,
+                           unsigned long long region_cap, const int2* pairs, const float* qplain,
+                           const float* ent0, const float* ent1, const float* s_true, int32_t* counts,
+                           unsigned long long* stats, cudaStream_t st);
 
 }  // namespace tc
 }  // namespace kge
