@@ -109,3 +109,26 @@ def test_sampler_and_training_refuse_cpu_tensors():
     m = tk.DistMultModel(8, 50, 3)
     with pytest.raises(_lib.KgeLibraryError):
         m.scoring_function(h[:10], t[:10], r[:10])
+
+
+def test_filter_index_equals_dictionary_semantics():
+    """FilterIndex.csr == filter_csr on the reference's dictionaries, quirks included."""
+    from torchkge_b200.data import FilterIndex
+    h, t, r = helpers.random_graph(300, 6, 4000, seed=2)
+    dh, dt = oracle.build_filter_dicts(h, t, r)
+    idx = FilterIndex(h, t, r, 300, 6)
+    g = torch.Generator().manual_seed(0)
+    # facts, plus random triples (true entity usually NOT in the set, some keys unknown)
+    qh = torch.cat([h[:300], torch.randint(0, 300, (150,), generator=g)])
+    qt = torch.cat([t[:300], torch.randint(0, 300, (150,), generator=g)])
+    qr = torch.cat([r[:300], torch.randint(0, 6, (150,), generator=g)])
+    for which, d, k1, k2, tr in (("tail", dt, qh, qr, qt), ("head", dh, qt, qr, qh)):
+        o1, i1 = filter_csr(d, k1, k2, tr)
+        o2, i2 = idx.csr(which, k1, k2, tr)
+        assert torch.equal(o1, o2)
+        for q in range(450):
+            assert sorted(i1[o1[q]:o1[q + 1]].tolist()) == sorted(i2[o2[q]:o2[q + 1]].tolist())
+    kg = tk.KnowledgeGraph(h[:40], t[:40], r[:40], 300, 6, filter_facts=(h, t, r))
+    assert kg.filter_index is not None
+    assert all(kg.dict_of_tails[k] == v for k, v in dt.items())   # lazily materialised dicts
+    assert all(kg.dict_of_heads[k] == v for k, v in dh.items())

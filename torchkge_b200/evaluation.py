@@ -80,11 +80,24 @@ class LinkPredictionEvaluator(object):
                 return tuple(x.to(dev, non_blocking=True) for x in csr)
             return build
 
+        def lazy_index_csr(index, which, k1, k2, true_idx):
+            def build():
+                csr = index.csr(which, k1, k2, true_idx)
+                stats["h2d_bytes"] += 8 * sum(x.numel() for x in csr)
+                return tuple(x.to(dev, non_blocking=True) for x in csr)
+            return build
+
+        index = getattr(kg, "filter_index", None)
+        if index is not None:  # sorted-array filters (torchkge_b200.data.KnowledgeGraph)
+            csr_tail = lazy_index_csr(index, "tail", heads, rels, tails)
+            csr_head = lazy_index_csr(index, "head", tails, rels, heads)
+        else:                  # the reference's dictionaries
+            csr_tail = lazy_csr(kg.dict_of_tails, heads, rels, tails)
+            csr_head = lazy_csr(kg.dict_of_heads, tails, rels, heads)
         engine = default_engine()
-        rh, rt, frh, frt = rank_link_prediction(
-            spec, h_d, t_d, r_d, lazy_csr(kg.dict_of_tails, heads, rels, tails),
-            lazy_csr(kg.dict_of_heads, tails, rels, heads), shard=self.shard, engine=engine,
-            chunk=DEFAULT_CHUNK)
+        rh, rt, frh, frt = rank_link_prediction(spec, h_d, t_d, r_d, csr_tail, csr_head,
+                                                shard=self.shard, engine=engine,
+                                                chunk=DEFAULT_CHUNK)
         self.last_stats = stats
         self.rank_true_heads = rh.cpu()
         self.rank_true_tails = rt.cpu()
