@@ -1,13 +1,12 @@
 #!/bin/bash
-# Round-1 GPU pass: parity tests, smoke, bench (c2), ncu launch list + one full capture of the scan.
+# GPU pass: parity tests, smoke, bench (c2), ncu launch list + one full capture of the dominant kernel.
 set -x
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.txt
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -6 | tee gpurun_out/pytest_gpu.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.txt
-timeout 900 python bench.py --steps 3 --warmup 3 2>gpurun_out/bench_err.txt | tee gpurun_out/bench_c2.json
+timeout 900 python bench.py --steps 5 --warmup 3 2>gpurun_out/bench_err.txt | tee gpurun_out/bench_c2.json | cut -c1-400
 tail -5 gpurun_out/bench_err.txt
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.txt 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 2 -c 1 -o gpurun_out/scan_c2 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.txt 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"scan|recheck|pack|rows|prep|true_scores|filter|finalize|stats|fill" --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu.txt 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_scan_kernel -s 2 -c 1 -o gpurun_out/tc_scan_c2 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.txt 2>&1
 tail -3 gpurun_out/ncu_full.txt
 ls -la gpurun_out

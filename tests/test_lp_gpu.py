@@ -155,3 +155,23 @@ def test_large_dim_cascade(kind, d, cuda_device):
     ref = oracle.link_prediction(kind, P, kg.head_idx, kg.tail_idx, kg.relations, dh, dt, b_size=35)
     ev = _ranks_gpu(model, kg)
     _assert_ranks_equal(ev, ref, kind)
+
+
+@pytest.mark.parametrize("kind", ["transe_l2", "transe_l1", "complex"])
+def test_filter_index_graph_gives_reference_ranks(kind, cuda_device):
+    """KnowledgeGraph(filter_facts=...) keeps the filter sets as sorted arrays resident on the
+    device instead of Python dictionaries; ranks must not change."""
+    n_ent, n_rel, d = 700, 8, 40
+    h, t, r = helpers.random_graph(n_ent, n_rel, 5000, seed=31)
+    dh, dt = oracle.build_filter_dicts(h, t, r)
+    # test facts: 200 real ones plus 40 corrupted ones whose true entity is not in its filter set
+    g = torch.Generator().manual_seed(1)
+    th = torch.cat([h[:200], torch.randint(0, n_ent, (40,), generator=g)])
+    tt = torch.cat([t[:200], torch.randint(0, n_ent, (40,), generator=g)])
+    tr = torch.cat([r[:200], torch.randint(0, n_rel, (40,), generator=g)])
+    kg = tk.KnowledgeGraph(th, tt, tr, n_ent, n_rel, filter_facts=(h, t, r))
+    model = helpers.make_model(kind, d, n_ent, n_rel, seed=31).to(cuda_device)
+    P = helpers.oracle_params(kind, model)
+    ref = oracle.link_prediction(kind, P, th, tt, tr, dh, dt, b_size=60)
+    ev = _ranks_gpu(model, kg)
+    _assert_ranks_equal(ev, ref, kind)

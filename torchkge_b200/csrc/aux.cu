@@ -230,6 +230,12 @@ __global__ void true_scores_kernel(int dim, long long n, const float* __restrict
   s_true[i] = pair_score<EL, CASC>(dim, q0, q1, c0, c1, perm, code);
 }
 
+// Filter pass.  For every CSR entry c of query i held by this shard:
+//   filt_sub[i] += [s(i,c) >= s_true(i)] - [s_true(i) == -inf]
+// (filter_scores writes -inf over the entry, modeling.py:100; get_rank then counts
+// (-inf >= s_true) instead of (s >= s_true), operations.py:61).  Chain-parallel scoring: 8 lanes
+// per entry for the L2 norm, 32 for the cascade sum (pair_score_chains), one lane for the
+// sequential L1 norm (schedule replay).
 template <int EL, bool CASC>
 __global__ void filter_kernel(int dim, long long n, long long n_filt,
                               const float* __restrict__ qplain, const float* __restrict__ ent0,
@@ -239,27 +245,45 @@ __global__ void filter_kernel(int dim, long long n, long long n_filt,
                               const uint8_t* __restrict__ code, const float* __restrict__ s_true,
                               int32_t* __restrict__ filt_sub) {
   constexpr int QW = ElemTraits<EL>::QW, CW = ElemTraits<EL>::CW;
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_filt) return;
-  const long long row = ids[e] - ent_lo;
-  if (row < 0 || row >= n_rows) return;
-  // query owning CSR entry e: largest i with offs[i] <= e
-  long long lo = 0, hi = n;
-  while (hi - lo > 1) {
-    const long long mid = (lo + hi) >> 1;
-    if (offs[mid] <= e) lo = mid; else hi = mid;
+  constexpr int RED = ElemTraits<EL>::RED;
+  constexpr int LANES = RED == RED_SEQ ? 1 : (RED == RED_NORM2 ? 8 : 32);  // lanes per entry
+  constexpr int PER_WARP = 32 / LANES;
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool small_sum = RED == RED_SUM && dim < 8;  // one-lane cascade: lane 0 scores alone
+  for (long long base = warp_global * PER_WARP; base < n_filt; base += n_warps * PER_WARP) {
+    const long long e = base + lane / LANES;
+    const bool in_range = e < n_filt;
+    const long long ee = in_range ? e : base;
+    const long long row = ids[ee] - ent_lo;
+    const bool held = in_range && row >= 0 && row < n_rows;
+    const long long rr = held ? row : 0;
+    // query owning CSR entry ee: largest i with offs[i] <= ee
+    long long lo = 0, hi = n;
+    while (hi - lo > 1) {
+      const long long mid = (lo + hi) >> 1;
+      if (offs[mid] <= ee) lo = mid; else hi = mid;
+    }
+    const long long i = lo;
+    const float* q0 = qplain + (size_t)i * QW * dim;
+    const float* q1 = q0 + (size_t)(QW - 1) * dim;
+    const float* c0 = ent0 + (size_t)rr * dim;
+    const float* c1 = (CW == 2 ? ent1 : ent0) + (size_t)rr * dim;
+    float s;
+    if constexpr (RED == RED_SEQ) {
+      s = pair_score<EL, CASC>(dim, q0, q1, c0, c1, perm, code);
+    } else {
+      if (small_sum) s = pair_score_natural<EL>(dim, q0, q1, c0, c1);
+      else s = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane);
+    }
+    const bool leader = (lane % LANES) == 0;
+    if (held && leader) {
+      const float st = s_true[i];
+      const int v = (s >= st ? 1 : 0) - (st == -INFINITY ? 1 : 0);
+      if (v != 0) atomicAdd(&filt_sub[i], v);
+    }
   }
-  const long long i = lo;
-  const float* q0 = qplain + (size_t)i * QW * dim;
-  const float* q1 = q0 + (size_t)(QW - 1) * dim;
-  const float* c0 = ent0 + (size_t)row * dim;
-  const float* c1 = (CW == 2 ? ent1 : ent0) + (size_t)row * dim;
-  const float s = pair_score<EL, CASC>(dim, q0, q1, c0, c1, perm, code);
-  const float st = s_true[i];
-  // filter_scores writes -inf over the entry (modeling.py:100); get_rank then counts
-  // (-inf >= s_true) instead of (s >= s_true) (operations.py:61).
-  const int v = (s >= st ? 1 : 0) - (st == -INFINITY ? 1 : 0);
-  if (v != 0) atomicAdd(&filt_sub[i], v);
 }
 
 __global__ void finalize_kernel(const int32_t* __restrict__ raw, const int32_t* __restrict__ sub,
@@ -270,6 +294,11 @@ __global__ void finalize_kernel(const int32_t* __restrict__ raw, const int32_t* 
   const int64_t r = raw[i];
   ranks[i] = r;
   filt_ranks[i] = r - (int64_t)sub[i];
+}
+
+inline unsigned filter_blocks(long long n_filt) {
+  const long long want = (n_filt + 3) / 4;  // >= one warp per entry group; grid-stride beyond
+  return (unsigned)(want < 1 ? 1 : (want > 148LL * 64 ? 148LL * 64 : want));
 }
 
 inline unsigned blocks_for(long long n, int threads) {
@@ -358,7 +387,7 @@ cudaError_t launch_filter(int el, bool cascade, int dim, int64_t n, int64_t n_fi
                           const float* s_true, int32_t* filt_sub, cudaStream_t stream) {
   if (n <= 0 || n_filt <= 0) return cudaSuccess;
 #define CALL_FILT(EL, C)                                                                   \
-  filter_kernel<EL, C><<<blocks_for(n_filt, 128), 128, 0, stream>>>(                       \
+  filter_kernel<EL, C><<<filter_blocks(n_filt), 128, 0, stream>>>(                         \
       dim, n, n_filt, qplain, ent0, ent1, ent_lo, n_rows, offs, ids, perm, code, s_true,   \
       filt_sub)
   KGE_DISPATCH_EL(el, cascade, CALL_FILT)

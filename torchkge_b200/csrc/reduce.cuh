@@ -157,4 +157,178 @@ __device__ __forceinline__ float acc_finish(const Acc& r) {
   }
 }
 
+// Exact score of one pair in NATURAL index order.  Same arithmetic as replaying the schedule
+// (every chain of the ATen reduction receives the same terms in the same order, chains are
+// combined in the same order) but the embedding index runs 0, 1, 2, ... so each thread streams
+// its two rows sequentially instead of revisiting every 32-byte sector eight times; the chain
+// accumulators live in registers (8 for the L2 norm, 32 (+32 cascade) for the cascade sum).
+template <int EL>
+__device__ __forceinline__ float elem_at(const float* q0, const float* q1, const float* c0,
+                                         const float* c1, int k) {
+  return elem_value<EL>(q0[k], q1[k], c0[k], c1[k]);
+}
+
+template <int EL>
+__device__ float pair_score_natural(int dim, const float* __restrict__ q0, const float* __restrict__ q1,
+                                    const float* __restrict__ c0, const float* __restrict__ c1) {
+  if constexpr (ElemTraits<EL>::RED == RED_NORM2) {
+    const int main_len = dim - dim % 8;
+    float acc[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc[l] = 0.f;
+    for (int k = 0; k < main_len; k += 8) {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        const float x = elem_at<EL>(q0, q1, c0, c1, k + l);
+        acc[l] = __fadd_rn(acc[l], __fmul_rn(x, x));
+      }
+    }
+    float t = 0.f;
+    if (main_len > 0) {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) t = __fadd_rn(t, acc[l]);
+    }
+    int k = main_len;
+    for (; k + 4 <= dim; k += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = elem_at<EL>(q0, q1, c0, c1, k + j);
+        t = __fadd_rn(t, __fmul_rn(x, x));
+      }
+    }
+    for (; k < dim; ++k) {
+      const float x = elem_at<EL>(q0, q1, c0, c1, k);
+      t = __fmaf_rn(x, x, t);
+    }
+    Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
+    return acc_finish<EL>(r);
+  } else {  // RED_SUM
+    float t = 0.f;
+    if (dim >= 8) {
+      const int vec_size = dim / 8, rows = vec_size / 4;
+      const bool casc = rows >= 16;
+      for (int k = vec_size * 8; k < dim; ++k) t = __fadd_rn(t, elem_at<EL>(q0, q1, c0, c1, k));
+      float acc[4][8], acc1[4][8];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) { acc[m][l] = 0.f; acc1[m][l] = 0.f; }
+      for (int i = 0; i < rows; ++i) {
+        const int k0 = i * 32;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int l = 0; l < 8; ++l)
+            acc[m][l] = __fadd_rn(acc[m][l], elem_at<EL>(q0, q1, c0, c1, k0 + m * 8 + l));
+        if (((i + 1) & 15) == 0) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int l = 0; l < 8; ++l) { acc1[m][l] = __fadd_rn(acc1[m][l], acc[m][l]); acc[m][l] = 0.f; }
+        }
+      }
+      if (casc) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int l = 0; l < 8; ++l) acc[m][l] = __fadd_rn(acc[m][l], acc1[m][l]);
+      }
+      for (int j = rows * 4; j < vec_size; ++j) {
+#pragma unroll
+        for (int l = 0; l < 8; ++l) acc[0][l] = __fadd_rn(acc[0][l], elem_at<EL>(q0, q1, c0, c1, j * 8 + l));
+      }
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        float pl = acc[0][l];
+        if (rows > 0) {
+#pragma unroll
+          for (int m = 1; m < 4; ++m) pl = __fadd_rn(pl, acc[m][l]);
+        }
+        t = __fadd_rn(t, pl);
+      }
+    } else {  // one lane: 4 interleaved chains, leftovers to chain 0
+      const int rows = dim / 4;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < rows; ++i) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc[m] = __fadd_rn(acc[m], elem_at<EL>(q0, q1, c0, c1, i * 4 + m));
+      }
+      for (int k = rows * 4; k < dim; ++k) acc[0] = __fadd_rn(acc[0], elem_at<EL>(q0, q1, c0, c1, k));
+      float pl = acc[0];
+      if (rows > 0) {
+#pragma unroll
+        for (int m = 1; m < 4; ++m) pl = __fadd_rn(pl, acc[m]);
+      }
+      t = __fadd_rn(t, pl);
+    }
+    Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
+    return acc_finish<EL>(r);
+  }
+}
+
+// Exact adjudication of the near-tie band (the list is kept as one region per CTA of the scan).
+// Chain-parallel: the independent chains of the ATen reduction are spread over the lanes of a
+// warp -- 8 lanes per pair for the L2 norm (4 pairs per warp), 32 lanes per pair for the
+// cascade sum -- so each step reads 32 / 128 contiguous bytes of the two rows; chains are then
+// combined through shuffles in exactly the schedule's order.  Same bits as pair_score_natural.
+template <int EL>
+__device__ __forceinline__ float pair_score_chains(int dim, const float* __restrict__ q0,
+                                                   const float* __restrict__ q1,
+                                                   const float* __restrict__ c0,
+                                                   const float* __restrict__ c1, int lane) {
+  if constexpr (ElemTraits<EL>::RED == RED_NORM2) {
+    const int l8 = lane & 7, g8 = lane & 24;  // lane of the norm, first lane of this pair's group
+    const int main_len = dim - dim % 8;
+    float acc = 0.f;
+    for (int k = l8; k < main_len; k += 8) {
+      const float x = elem_at<EL>(q0, q1, c0, c1, k);
+      acc = __fadd_rn(acc, __fmul_rn(x, x));
+    }
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      const float v = __shfl_sync(0xffffffffu, acc, g8 + l);
+      if (main_len > 0) t = __fadd_rn(t, v);
+    }
+    int k = main_len;
+    for (; k + 4 <= dim; k += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = elem_at<EL>(q0, q1, c0, c1, k + j);
+        t = __fadd_rn(t, __fmul_rn(x, x));
+      }
+    }
+    for (; k < dim; ++k) {
+      const float x = elem_at<EL>(q0, q1, c0, c1, k);
+      t = __fmaf_rn(x, x, t);
+    }
+    Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
+    return acc_finish<EL>(r);
+  } else {  // RED_SUM, dim >= 8: lane = 8 m + l owns chain (row m, lane l)
+    const int vec_size = dim / 8, rows = vec_size / 4;
+    float acc = 0.f, acc1 = 0.f;
+    for (int i = 0; i < rows; ++i) {
+      acc = __fadd_rn(acc, elem_at<EL>(q0, q1, c0, c1, i * 32 + lane));
+      if (((i + 1) & 15) == 0) { acc1 = __fadd_rn(acc1, acc); acc = 0.f; }
+    }
+    if (rows >= 16) acc = __fadd_rn(acc, acc1);
+    if (lane < 8)
+      for (int j = rows * 4; j < vec_size; ++j) acc = __fadd_rn(acc, elem_at<EL>(q0, q1, c0, c1, j * 8 + lane));
+    const int l = lane & 7;
+    float pl = __shfl_sync(0xffffffffu, acc, l);
+#pragma unroll
+    for (int m = 1; m < 4; ++m) {
+      const float v = __shfl_sync(0xffffffffu, acc, 8 * m + l);
+      if (rows > 0) pl = __fadd_rn(pl, v);
+    }
+    float t = 0.f;
+    for (int k = vec_size * 8; k < dim; ++k) t = __fadd_rn(t, elem_at<EL>(q0, q1, c0, c1, k));
+#pragma unroll
+    for (int ll = 0; ll < 8; ++ll) t = __fadd_rn(t, __shfl_sync(0xffffffffu, pl, ll));
+    Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
+    return acc_finish<EL>(r);
+  }
+}
+
+
 }  // namespace kge

@@ -39,11 +39,12 @@ constexpr int B_PLANE = BN * 128;
 constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // A hi, A lo, B hi, B lo = 96 KB
 constexpr int NORM_FLOATS = 2 * BN;                     // cb[256], cn[256] per buffer
 constexpr int AMB_BUF = 128;                            // near-tie entries buffered per epilogue warp
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                            // two per TMEM lane quadrant, half the columns each
+constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr int TMEM_COLS = 512;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
                               2 * NORM_FLOATS * sizeof(float) + 16 * sizeof(uint64_t) + 16 +
-                              4 * AMB_BUF * sizeof(int2);
+                              EPI_WARPS * AMB_BUF * sizeof(int2);
 
 // -------- PTX helpers specific to tcgen05 --------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
   uint64_t* tfull_bar = bars + 4;       // [2]
   uint64_t* tempty_bar = bars + 6;      // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
-  int2* s_amb = reinterpret_cast<int2*>(bars + 10);  // [4 warps][AMB_BUF]
+  int2* s_amb = reinterpret_cast<int2*>(bars + 10);  // [EPI_WARPS][AMB_BUF]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Units units(p.n_qt, p.n_ct);
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], EPI_WARPS); }
     ptx::fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, TMEM_COLS);
@@ -211,10 +212,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    // ------------------------------ epilogue (warps 2..9) ------------------------------
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // query row within the tile
     const int epi_tid = (warp - 2) * 32 + lane;
+    const int col_half = (warp - 2) >> 2;     // which 128 columns of the tile this warp handles
     int acc = 0; uint32_t acc_phase = 0;
     long long cur_qt = -1;
     float st = 0.f, qb = 0.f, qn = 0.f;
@@ -240,12 +242,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
       // candidate-side vectors of this tile -> shared (double buffered)
       float* cbs = s_norm + nbuf * NORM_FLOATS;
       float* cns = cbs + BN;
-      for (int j = epi_tid; j < BN; j += 128) {
+      for (int j = epi_tid; j < BN; j += EPI_WARPS * 32) {
         const long long c = ct * BN + j;
         cbs[j] = c < p.n_rows ? p.cbound[c] : 0.f;
         cns[j] = c < p.n_rows ? p.cnorm2[c] : 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, EPI_WARPS * 32);
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       fence_after();
       const int ncols = (int)min((long long)BN, p.n_rows - ct * BN);
@@ -254,7 +256,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
       const float g_qb = p.gamma * qb;        // dot: eps = g_qb * cb[c]
       const float g2_qb = 2.f * g_qb;         // L2 : eps = 2 gamma qb cb + gamma2 (qb + cb)^2
       const float l2_off = -(qn + st);        // L2 : u = 2 dot + l2_off - cn[c]
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
+      const int c_begin = col_half * (BN / 2), c_end = min(ncols, c_begin + BN / 2);
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         const int lim = min(32, ncols - c0);
@@ -443,179 +446,6 @@ __global__ void row_norms_kernel(const float* __restrict__ src0, const float* __
     // |r| and |t| separately, so the bound uses |t| + |r| (>= |t - r|) for this operand
     const double nb = sub_mode ? sqrt(sa) + sqrt(sb) : sqrt(s);
     bound[w] = (float)(nb * (1.0 + 1e-6)) + 1e-30f;
-  }
-}
-
-// Exact score of one pair in NATURAL index order.  Same arithmetic as replaying the schedule
-// (every chain of the ATen reduction receives the same terms in the same order, chains are
-// combined in the same order) but the embedding index runs 0, 1, 2, ... so each thread streams
-// its two rows sequentially instead of revisiting every 32-byte sector eight times; the chain
-// accumulators live in registers (8 for the L2 norm, 32 (+32 cascade) for the cascade sum).
-template <int EL>
-__device__ __forceinline__ float elem_at(const float* q0, const float* q1, const float* c0,
-                                         const float* c1, int k) {
-  return elem_value<EL>(q0[k], q1[k], c0[k], c1[k]);
-}
-
-template <int EL>
-__device__ float pair_score_natural(int dim, const float* __restrict__ q0, const float* __restrict__ q1,
-                                    const float* __restrict__ c0, const float* __restrict__ c1) {
-  if constexpr (ElemTraits<EL>::RED == RED_NORM2) {
-    const int main_len = dim - dim % 8;
-    float acc[8];
-#pragma unroll
-    for (int l = 0; l < 8; ++l) acc[l] = 0.f;
-    for (int k = 0; k < main_len; k += 8) {
-#pragma unroll
-      for (int l = 0; l < 8; ++l) {
-        const float x = elem_at<EL>(q0, q1, c0, c1, k + l);
-        acc[l] = __fadd_rn(acc[l], __fmul_rn(x, x));
-      }
-    }
-    float t = 0.f;
-    if (main_len > 0) {
-#pragma unroll
-      for (int l = 0; l < 8; ++l) t = __fadd_rn(t, acc[l]);
-    }
-    int k = main_len;
-    for (; k + 4 <= dim; k += 4) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x = elem_at<EL>(q0, q1, c0, c1, k + j);
-        t = __fadd_rn(t, __fmul_rn(x, x));
-      }
-    }
-    for (; k < dim; ++k) {
-      const float x = elem_at<EL>(q0, q1, c0, c1, k);
-      t = __fmaf_rn(x, x, t);
-    }
-    Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
-    return acc_finish<EL>(r);
-  } else {  // RED_SUM
-    float t = 0.f;
-    if (dim >= 8) {
-      const int vec_size = dim / 8, rows = vec_size / 4;
-      const bool casc = rows >= 16;
-      for (int k = vec_size * 8; k < dim; ++k) t = __fadd_rn(t, elem_at<EL>(q0, q1, c0, c1, k));
-      float acc[4][8], acc1[4][8];
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int l = 0; l < 8; ++l) { acc[m][l] = 0.f; acc1[m][l] = 0.f; }
-      for (int i = 0; i < rows; ++i) {
-        const int k0 = i * 32;
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-          for (int l = 0; l < 8; ++l)
-            acc[m][l] = __fadd_rn(acc[m][l], elem_at<EL>(q0, q1, c0, c1, k0 + m * 8 + l));
-        if (((i + 1) & 15) == 0) {
-#pragma unroll
-          for (int m = 0; m < 4; ++m)
-#pragma unroll
-            for (int l = 0; l < 8; ++l) { acc1[m][l] = __fadd_rn(acc1[m][l], acc[m][l]); acc[m][l] = 0.f; }
-        }
-      }
-      if (casc) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-#pragma unroll
-          for (int l = 0; l < 8; ++l) acc[m][l] = __fadd_rn(acc[m][l], acc1[m][l]);
-      }
-      for (int j = rows * 4; j < vec_size; ++j) {
-#pragma unroll
-        for (int l = 0; l < 8; ++l) acc[0][l] = __fadd_rn(acc[0][l], elem_at<EL>(q0, q1, c0, c1, j * 8 + l));
-      }
-#pragma unroll
-      for (int l = 0; l < 8; ++l) {
-        float pl = acc[0][l];
-        if (rows > 0) {
-#pragma unroll
-          for (int m = 1; m < 4; ++m) pl = __fadd_rn(pl, acc[m][l]);
-        }
-        t = __fadd_rn(t, pl);
-      }
-    } else {  // one lane: 4 interleaved chains, leftovers to chain 0
-      const int rows = dim / 4;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int i = 0; i < rows; ++i) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m) acc[m] = __fadd_rn(acc[m], elem_at<EL>(q0, q1, c0, c1, i * 4 + m));
-      }
-      for (int k = rows * 4; k < dim; ++k) acc[0] = __fadd_rn(acc[0], elem_at<EL>(q0, q1, c0, c1, k));
-      float pl = acc[0];
-      if (rows > 0) {
-#pragma unroll
-        for (int m = 1; m < 4; ++m) pl = __fadd_rn(pl, acc[m]);
-      }
-      t = __fadd_rn(t, pl);
-    }
-    Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
-    return acc_finish<EL>(r);
-  }
-}
-
-// Exact adjudication of the near-tie band (the list is kept as one region per CTA of the scan).
-// Chain-parallel: the independent chains of the ATen reduction are spread over the lanes of a
-// warp -- 8 lanes per pair for the L2 norm (4 pairs per warp), 32 lanes per pair for the
-// cascade sum -- so each step reads 32 / 128 contiguous bytes of the two rows; chains are then
-// combined through shuffles in exactly the schedule's order.  Same bits as pair_score_natural.
-template <int EL>
-__device__ __forceinline__ float pair_score_chains(int dim, const float* __restrict__ q0,
-                                                   const float* __restrict__ q1,
-                                                   const float* __restrict__ c0,
-                                                   const float* __restrict__ c1, int lane) {
-  if constexpr (ElemTraits<EL>::RED == RED_NORM2) {
-    const int l8 = lane & 7, g8 = lane & 24;  // lane of the norm, first lane of this pair's group
-    const int main_len = dim - dim % 8;
-    float acc = 0.f;
-    for (int k = l8; k < main_len; k += 8) {
-      const float x = elem_at<EL>(q0, q1, c0, c1, k);
-      acc = __fadd_rn(acc, __fmul_rn(x, x));
-    }
-    float t = 0.f;
-#pragma unroll
-    for (int l = 0; l < 8; ++l) {
-      const float v = __shfl_sync(0xffffffffu, acc, g8 + l);
-      if (main_len > 0) t = __fadd_rn(t, v);
-    }
-    int k = main_len;
-    for (; k + 4 <= dim; k += 4) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x = elem_at<EL>(q0, q1, c0, c1, k + j);
-        t = __fadd_rn(t, __fmul_rn(x, x));
-      }
-    }
-    for (; k < dim; ++k) {
-      const float x = elem_at<EL>(q0, q1, c0, c1, k);
-      t = __fmaf_rn(x, x, t);
-    }
-    Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
-    return acc_finish<EL>(r);
-  } else {  // RED_SUM, dim >= 8: lane = 8 m + l owns chain (row m, lane l)
-    const int vec_size = dim / 8, rows = vec_size / 4;
-    float acc = 0.f, acc1 = 0.f;
-    for (int i = 0; i < rows; ++i) {
-      acc = __fadd_rn(acc, elem_at<EL>(q0, q1, c0, c1, i * 32 + lane));
-      if (((i + 1) & 15) == 0) { acc1 = __fadd_rn(acc1, acc); acc = 0.f; }
-    }
-    if (rows >= 16) acc = __fadd_rn(acc, acc1);
-    if (lane < 8)
-      for (int j = rows * 4; j < vec_size; ++j) acc = __fadd_rn(acc, elem_at<EL>(q0, q1, c0, c1, j * 8 + lane));
-    const int l = lane & 7;
-    float pl = __shfl_sync(0xffffffffu, acc, l);
-#pragma unroll
-    for (int m = 1; m < 4; ++m) {
-      const float v = __shfl_sync(0xffffffffu, acc, 8 * m + l);
-      if (rows > 0) pl = __fadd_rn(pl, v);
-    }
-    float t = 0.f;
-    for (int k = vec_size * 8; k < dim; ++k) t = __fadd_rn(t, elem_at<EL>(q0, q1, c0, c1, k));
-#pragma unroll
-    for (int ll = 0; ll < 8; ++ll) t = __fadd_rn(t, __shfl_sync(0xffffffffu, pl, ll));
-    Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
-    return acc_finish<EL>(r);
   }
 }
 

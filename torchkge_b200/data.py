@@ -26,34 +26,47 @@ class FilterIndex:
     def __init__(self, heads, tails, relations, n_ent, n_rel):
         heads, tails, relations = (x.long().cpu() for x in (heads, tails, relations))
         self.n_ent, self.n_rel = int(n_ent), int(n_rel)
-        self.kv, self.keys, self.vals = {}, {}, {}
-        for which, k1, val in (("tail", heads, tails), ("head", tails, heads)):
-            kv = torch.unique((k1 * self.n_rel + relations) * self.n_ent + val)  # sorted, deduplicated
-            self.kv[which] = kv
-            self.keys[which] = torch.div(kv, self.n_ent, rounding_mode="floor")
-            self.vals[which] = kv - self.keys[which] * self.n_ent
+        # one sorted, deduplicated int64 array per side: (key1 * n_rel + rel) * n_ent + value
+        self.kv = {
+            "tail": torch.unique((heads * self.n_rel + relations) * self.n_ent + tails),
+            "head": torch.unique((tails * self.n_rel + relations) * self.n_ent + heads),
+        }
+        self._on_device = {}
+
+    def on(self, device):
+        """The two key arrays on ``device`` (uploaded once and kept, like model weights)."""
+        device = torch.device(device)
+        if device.type == "cpu":
+            return self.kv
+        if device not in self._on_device:
+            self._on_device[device] = {k: v.to(device) for k, v in self.kv.items()}
+        return self._on_device[device]
 
     def csr(self, which, key1, key2, true_idx):
         """CSR (offs, ids) with exactly the semantics of ``filter_csr`` on the dictionaries:
         row i = {v : (key1[i], key2[i], v) is a fact} minus true_idx[i], empty when the true
-        entity is not in that set (get_true_targets' KeyError quirk)."""
-        keys, vals, kv = self.keys[which], self.vals[which], self.kv[which]
-        kq = key1.long() * self.n_rel + key2.long()
-        lo = torch.searchsorted(keys, kq)
-        hi = torch.searchsorted(keys, kq, right=True)
-        kvq = kq * self.n_ent + true_idx.long()
+        entity is not in that set (get_true_targets' KeyError quirk).  Runs on the device of
+        ``key1`` (CPU or CUDA); everything is searchsorted / gather, no Python loop."""
+        dev = key1.device
+        kv = self.on(dev)[which]
+        kq = (key1.long() * self.n_rel + key2.long()) * self.n_ent
+        true_idx = true_idx.long()
+        lo = torch.searchsorted(kv, kq)
+        hi = torch.searchsorted(kv, kq + self.n_ent)
+        kvq = kq + true_idx
         pos_true = torch.searchsorted(kv, kvq)
         has_true = (pos_true < kv.numel()) & (kv[pos_true.clamp(max=max(kv.numel() - 1, 0))] == kvq)
-        cnt = torch.where(has_true, hi - lo - 1, torch.zeros_like(lo))
-        offs = torch.zeros(kq.numel() + 1, dtype=torch.int64)
-        torch.cumsum(cnt, 0, out=offs[1:])
+        zero = torch.zeros_like(lo)
+        cnt = torch.where(has_true, hi - lo - 1, zero)
         n = kq.numel()
-        full = torch.where(has_true, hi - lo, torch.zeros_like(lo))
-        row = torch.repeat_interleave(torch.arange(n), full)
+        offs = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(cnt, 0, out=offs[1:])
+        full = torch.where(has_true, hi - lo, zero)
+        row = torch.repeat_interleave(torch.arange(n, device=dev), full)
         start = torch.cumsum(full, 0) - full
-        pos = torch.arange(row.numel()) - start[row] + lo[row]
-        ids = vals[pos]
-        ids = ids[ids != true_idx.long()[row]]
+        pos = torch.arange(row.numel(), device=dev) - start[row] + lo[row]
+        ids = kv[pos] - kq[row]
+        ids = ids[ids != true_idx[row]]
         return offs, ids.contiguous()
 
     def as_dicts(self):
@@ -61,8 +74,10 @@ class FilterIndex:
         out = {}
         for which in ("head", "tail"):
             d = defaultdict(set)
-            keys, vals = self.keys[which].tolist(), self.vals[which].tolist()
-            for k, v in zip(keys, vals):
+            kv = self.kv[which]
+            keys = torch.div(kv, self.n_ent, rounding_mode="floor")
+            vals = (kv - keys * self.n_ent).tolist()
+            for k, v in zip(keys.tolist(), vals):
                 d[(k // self.n_rel, k % self.n_rel)].add(v)
             out[which] = d
         return out["head"], out["tail"]

@@ -80,17 +80,13 @@ class LinkPredictionEvaluator(object):
                 return tuple(x.to(dev, non_blocking=True) for x in csr)
             return build
 
-        def lazy_index_csr(index, which, k1, k2, true_idx):
-            def build():
-                csr = index.csr(which, k1, k2, true_idx)
-                stats["h2d_bytes"] += 8 * sum(x.numel() for x in csr)
-                return tuple(x.to(dev, non_blocking=True) for x in csr)
-            return build
-
         index = getattr(kg, "filter_index", None)
-        if index is not None:  # sorted-array filters (torchkge_b200.data.KnowledgeGraph)
-            csr_tail = lazy_index_csr(index, "tail", heads, rels, tails)
-            csr_head = lazy_index_csr(index, "head", tails, rels, heads)
+        if index is not None:
+            # sorted-array filters (torchkge_b200.data.KnowledgeGraph): the index is resident on
+            # the device (uploaded at first use, like weights); the per-row lists of this test set
+            # come from searchsorted + gather on the device, after the scans are enqueued
+            csr_tail = lambda: index.csr("tail", h_d, r_d, t_d)   # noqa: E731
+            csr_head = lambda: index.csr("head", t_d, r_d, h_d)   # noqa: E731
         else:                  # the reference's dictionaries
             csr_tail = lazy_csr(kg.dict_of_tails, heads, rels, tails)
             csr_head = lazy_csr(kg.dict_of_heads, tails, rels, heads)
