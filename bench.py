@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=24, help="test triples in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--split", default="auto", choices=["auto", "queries", "entities"],
+                    help="multi-GPU decomposition: shard the test triples (replicated table) or the entity table")
     return ap.parse_args()
 
 
@@ -221,7 +223,7 @@ def run_reference(args, rank, world):
         "value": value, "unit": "triples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * el / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, wl, world),
+        "config": workload_config(args.workload, wl, world, split_mode(args, wl, world)),
         "cpu_baseline": {"value": value, "unit": "triples/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -238,12 +240,25 @@ def oracle_params_from_tables(kind, tabs):
     return {"re_ent": tabs["ent0"], "im_ent": tabs["ent1"], "re_rel": tabs["rel0"], "im_rel": tabs["rel1"]}
 
 
-def workload_config(name, wl, world):
+def split_mode(args, wl, world):
+    """single | queries (replicated table, test triples sharded) | entities (table range-partitioned)"""
+    if world == 1:
+        return "single"
+    if args.split != "auto":
+        return args.split
+    table_bytes = wl["n_ent"] * wl["dim"] * (8 if wl["model"] in ("ComplEx", "RotatE") else 4)
+    return "entities" if table_bytes > 24e9 else "queries"
+
+
+def workload_config(name, wl, world, mode="single"):
     return {"workload": "%s: %s%s dim=%d |E|=%d |R|=%d, %d test triples, full filtered LP (head+tail)" % (
                 name, wl["model"], ("-" + wl["diss"]) if wl["diss"] else "", wl["dim"], wl["n_ent"],
                 wl["n_rel"], wl["n_test"]),
             "n_facts_requested": wl["n_facts"],
-            "parallelism": "entity-range shards x%d, 1 all-reduce of rank counters" % world if world > 1 else "single GPU",
+            "parallelism": {"single": "single GPU",
+                            "queries": "test triples sharded x%d, table replicated, no data-path collective "
+                                       "(rank vectors all-gathered)" % world,
+                            "entities": "entity-range shards x%d, 1 all-reduce of rank counters" % world}[mode],
             "l2_policy": "inputs larger than L2 (table %.0f MB >> 126 MB)" % (
                 wl["n_ent"] * wl["dim"] * (8 if wl["model"] in ("ComplEx", "RotatE") else 4) / 1e6)}
 
@@ -261,11 +276,17 @@ def run_ours(args, rank, local, world):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     wl = S.WORKLOADS[args.workload]
     code = S.MODEL_CODE[(wl["model"], wl["diss"])]
     n_ent, n_rel, dim = wl["n_ent"], wl["n_rel"], wl["dim"]
-    shard = EntityShard(n_ent, rank, world, None, local_storage=True) if world > 1 else None
+    # How the job is split over ranks: a table that fits one GPU is
+    # replicated and the TEST TRIPLES are sharded (independent units, no collective on the data
+    # path, ranks all-gathered at the end); a table that does not (c4) is range-partitioned over
+    # the ranks and the rank counters are summed by one all-reduce.
+    mode = split_mode(args, wl, world)
+    shard = EntityShard(n_ent, rank, world, None, local_storage=True) if mode == "entities" else None
     lo, hi = (shard.lo, shard.hi) if shard else (0, n_ent)
 
     tabs = S.make_tables(code, dim, n_ent, n_rel, lo, hi, args.seed, dev)
@@ -275,6 +296,15 @@ def run_ours(args, rank, local, world):
     torch.cuda.synchronize()
     csr_build_s = time.perf_counter() - t0
     n_test = graph["test_h"].numel()
+    if mode == "queries":
+        # this rank's contiguous slice of the test set (and of the filter CSRs)
+        per = (n_test + world - 1) // world
+        q_lo, q_hi = min(n_test, rank * per), min(n_test, (rank + 1) * per)
+    else:
+        q_lo, q_hi = 0, n_test
+    from torchkge_b200.engine import _csr_slice
+    my_h, my_t, my_r = (graph[k][q_lo:q_hi].contiguous() for k in ("test_h", "test_t", "test_r"))
+    my_csr_t, my_csr_h = _csr_slice(csr_t, q_lo, q_hi, n_test), _csr_slice(csr_h, q_lo, q_hi, n_test)
     spec = ModelSpec(code, dim, n_ent, n_rel, tabs["ent0"], tabs["ent1"], tabs["rel0"], tabs["rel1"],
                      ent_lo=lo)
     eng = CudaEngine()
@@ -286,8 +316,20 @@ def run_ours(args, rank, local, world):
         torch.cuda.synchronize()
 
     def device_step():
-        return rank_link_prediction(spec, graph["test_h"], graph["test_t"], graph["test_r"],
-                                    csr_t, csr_h, shard=shard, engine=eng)
+        return rank_link_prediction(spec, my_h, my_t, my_r, my_csr_t, my_csr_h, shard=shard, engine=eng)
+
+    def gather_ranks(parts):
+        """all ranks' slices -> full-length vectors (query-sharded mode only)"""
+        if mode != "queries":
+            return parts
+        out = []
+        for x in parts:
+            pad = torch.zeros(per, dtype=x.dtype, device=dev)
+            pad[:x.numel()] = x
+            bufs = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(bufs, pad)
+            out.append(torch.cat(bufs)[:n_test])
+        return out
 
     # ---- device-resident timing -------------------------------------------------------
     for _ in range(args.warmup):
@@ -325,7 +367,7 @@ def run_ours(args, rank, local, world):
     # host-side knowledge graph: test facts + the filter sets of the FULL graph as sorted arrays
     from torchkge_b200.data import KnowledgeGraph
     t0 = time.perf_counter()
-    kg = KnowledgeGraph(graph["test_h"].cpu(), graph["test_t"].cpu(), graph["test_r"].cpu(), n_ent, n_rel,
+    kg = KnowledgeGraph(my_h.cpu(), my_t.cpu(), my_r.cpu(), n_ent, n_rel,
                         filter_facts=(graph["heads"].cpu(), graph["tails"].cpu(), graph["rels"].cpu()))
     kg.head_idx, kg.tail_idx, kg.relations = (x.pin_memory() for x in (kg.head_idx, kg.tail_idx, kg.relations))
     filter_index_build_s = time.perf_counter() - t0
@@ -346,6 +388,7 @@ def run_ours(args, rank, local, world):
     same = all(torch.equal(a.cpu(), b) for a, b in zip(
         ranks_dev, (evaluator.rank_true_heads, evaluator.rank_true_tails,
                     evaluator.filt_rank_true_heads, evaluator.filt_rank_true_tails)))
+    ranks_dev = gather_ranks(ranks_dev)
 
     # ---- roofline of the dominant kernel -----------------------------------------------------
     peak, peak_src = measured_peaks()
@@ -357,7 +400,8 @@ def run_ours(args, rank, local, world):
         # tensor-core bound-and-refine scan: bf16x3 split GEMM (3 bf16 MMAs per fp32 product)
         k_total = dim * (2 if code == _lib.COMPLEX else 1)
         ms_per_launch = tc_ms / tc_n
-        alg_flops = 2.0 * n_test * rows_here * k_total          # the fp32 contraction itself
+        n_my = q_hi - q_lo
+        alg_flops = 2.0 * n_my * rows_here * k_total            # the fp32 contraction itself (this rank)
         tensor_peak = measured_tensor_peak()
         near_ties = sum(int(s_[0]) for s_ in eng.tc_stats[-2 * args.steps:]) / max(1, args.steps)
         roofline = {
@@ -370,7 +414,7 @@ def run_ours(args, rank, local, world):
             "recheck_ms_per_launch": rc_ms / max(1, rc_n),
             "recheck_share_of_step": rc_ms / dev_ms if dev_ms > 0 else None,
             "near_tie_pairs_per_step": near_ties,
-            "near_tie_fraction": near_ties / (2.0 * n_test * rows_here),
+            "near_tie_fraction": near_ties / (2.0 * max(1, n_my) * rows_here),
             "executed_bf16_tflops": 3 * alg_flops / (ms_per_launch / 1000.0) / 1e12,
             "note": "algorithmic flops = 2 x queries x rows x K (fp32 contraction); the kernel executes "
                     "3 bf16 MMAs per product (hi*hi + lo*hi + hi*lo) and is L2->SM bandwidth bound "
@@ -380,12 +424,12 @@ def run_ours(args, rank, local, world):
     else:
         # scalar fp32 scan.  algorithmic bytes per launch = queries x candidate rows x row_bytes
         # (2*nE*row_bytes per triple = nE*row_bytes per (triple, side) launch unit)
-        alg_bytes_per_launch = float(n_test) * rows_here * rb
+        alg_bytes_per_launch = float(q_hi - q_lo) * rows_here * rb
         scan_ms_per_launch = scan_ms / max(1, scan_n)
         achieved = alg_bytes_per_launch / (scan_ms_per_launch / 1000.0) / 1e9
         ops_per_elem = {_lib.TRANSE_L1: 2.5, _lib.TRANSE_L2: 3.5, _lib.DISTMULT: 2.0, _lib.RESCAL: 2.0,
                         _lib.COMPLEX: 4.0, _lib.ROTATE: 7.0}[code]  # mean of tail/head fp32 ops per (q,c,k)
-        lane_ops = float(n_test) * rows_here * dim * ops_per_elem
+        lane_ops = float(q_hi - q_lo) * rows_here * dim * ops_per_elem
         fp32_peak = 148 * 128 * sm_mhz * 1e6
         roofline = {
             "kernel": "scan_kernel (dense rank scan, fp32 pipes)", "bound": "hbm", "achieved": achieved,
@@ -411,12 +455,12 @@ def run_ours(args, rank, local, world):
         torch.set_num_threads(cores)
         big = n_ent >= 100000
         ns = min(n_test, args.cpu_sample if big else 2048)
-        if world > 1:
+        if mode == "entities":
             full = S.make_tables(code, dim, n_ent, n_rel, 0, n_ent, args.seed, dev)
         else:
             full = tabs
         P = oracle_params_from_tables(kind, {k: (v.cpu() if v is not None else None) for k, v in full.items()})
-        th, tt, tr = kg.head_idx[:ns], kg.tail_idx[:ns], kg.relations[:ns]
+        th, tt, tr = (graph[k][:ns].cpu() for k in ("test_h", "test_t", "test_r"))
         dh, dt = S.filters_as_dicts(graph, n_ent, n_rel, limit=ns)  # reference-style dicts, sample keys
         b_size = 4 if big else 256
         t0 = time.perf_counter()
@@ -439,7 +483,7 @@ def run_ours(args, rank, local, world):
         "value": value, "unit": "triples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, wl, world),
+        "config": workload_config(args.workload, wl, world, mode),
         "e2e": {"value": e2e_value, "unit": "triples/s",
                 "h2d_bytes_per_step": evaluator.last_stats.get("h2d_bytes"),
                 "d2h_bytes_per_step": evaluator.last_stats.get("d2h_bytes"),
