@@ -349,6 +349,9 @@ def run_ours(args, rank, local, world):
     ev1.record()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
+    if eng.trace is not None and rank == 0:   # KGE_TRACE=1: where the steps spent their time
+        for lab, host_ms, dev_ms_ in eng.trace_report():
+            print("trace %-28s host %9.3f ms  device %9.3f ms" % (lab, host_ms, dev_ms_), file=sys.stderr)
     launches = eng.launches - launches0
     scan_n, scan_ms = _lib.scan_timing_read(0)
     tc_n, tc_ms = _lib.scan_timing_read(1)

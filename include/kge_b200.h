@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 2
+#define KGE_ABI_VERSION 4
 
 /* error codes */
 #define KGE_OK 0
@@ -60,7 +60,11 @@ typedef enum {
 /* Which element of the triple is being completed. */
 typedef enum {
   KGE_SIDE_TAIL = 0, /* (h, r, ?)  evaluation.py:292 */
-  KGE_SIDE_HEAD = 1  /* (?, r, t)  evaluation.py:297 */
+  KGE_SIDE_HEAD = 1, /* (?, r, t)  evaluation.py:297 */
+  KGE_SIDE_REL = 2   /* (h, ?, t)  RelationPredictionEvaluator, evaluation.py:94-97: the candidate
+                        table (packed / ent0 / ent1) is the RELATION table (rel_emb; re_/im_rel_emb),
+                        rel0 / rel1 / r_idx are unused, true_rows is required.  TransE L1/L2, DistMult,
+                        ComplEx (RESCAL's batched matmul and RotatE are not on this path). */
 } kge_side_t;
 
 /* Geometry of the packed layouts, fixed at build time; exported so that callers can
@@ -103,6 +107,13 @@ int kge_build_schedule(int model, int dim, int32_t* perm_host, uint8_t* code_hos
  * [hi/lo bf16 planes in 128-byte-swizzled shared-memory order | per-row norm bounds].
  * kge_tc_packed_bytes returns 0 for models without such a path (TransE-L1, RotatE). */
 size_t kge_tc_packed_bytes(int model, int64_t n_rows, int dim);
+/* Tuning / test hook of the tensor-core scan (process-wide; defaults also settable through the
+ * environment: KGE_TC_BK, KGE_TC_RESIDENT, KGE_TC_GROUP, KGE_TC_MAX_CTAS).  bk = bf16 per k-block
+ * (32: 64-byte swizzle, query-tile image resident in shared memory when k <= 224; 64: 128-byte
+ * swizzle, both operands streamed); ct_group = candidate tiles per work unit (0 = automatic);
+ * max_ctas = grid limit (0 = one CTA per SM).  Negative arguments keep the current value.
+ * Images packed under one bk must be scanned under the same bk.  Results never depend on it. */
+int kge_tc_configure(int bk, int resident, int ct_group, int max_ctas);
 int kge_tc_pack_table(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
                       void* tc_packed, void* stream);
 
@@ -168,6 +179,11 @@ typedef struct {
                                this call are INVALID: redo the call without the flag */
   float* tc_dump;           /* debug / tests: if set, the tensor-core pass writes its approximate
                                scores [n][n_rows] here and counts nothing */
+  const float* true_rows;   /* [n][cand_planes][dim] rows of the true candidates; NULL: trows (tail
+                               side) / hrows (head side).  Required for KGE_SIDE_REL. */
+  const float* true_score_in; /* [n] or NULL: use these true scores instead of scoring true_rows
+                               (undirected relation prediction ranks the swapped (t, ?, h) scores
+                               against the directed true score, evaluation.py:99-107) */
 } kge_rank_args_t;
 
 #define KGE_FLAG_TENSOR_CORE 1 /* use the tensor-core bound-and-refine scan when the model has one */
@@ -242,6 +258,17 @@ int kge_margin_loss_fwd(const float* pos, const float* neg, int64_t n, float mar
                         void* stream);
 int kge_margin_loss_bwd(const float* pos, const float* neg, int64_t n, float margin,
                         const float* grad_loss, float* grad_pos, float* grad_neg, void* stream);
+
+/* LogisticLoss (utils/losses.py:47-78: SoftMarginLoss(reduction='sum') on (pos, +1) and (neg, -1))
+ * and BinaryCrossEntropyLoss (utils/losses.py:81-112: BCELoss(sum) of sigmoid(pos) vs 1 and
+ * sigmoid(neg) vs 0, log clamped at -100 as torch does):
+ *   kind 1: loss += sum_i log(1 + exp(-pos[i])) + log(1 + exp(neg[i]))
+ *   kind 2: loss += sum_i -max(log(sig(pos[i])), -100) - max(log(1 - sig(neg[i])), -100) */
+#define KGE_LOSS_LOGISTIC 1
+#define KGE_LOSS_BCE 2
+int kge_pair_loss_fwd(int kind, const float* pos, const float* neg, int64_t n, float* loss, void* stream);
+int kge_pair_loss_bwd(int kind, const float* pos, const float* neg, int64_t n, const float* grad_loss,
+                      float* grad_pos, float* grad_neg, void* stream);
 
 /* Fused training step = corrupt_batch + Model.forward (models/interfaces.py:39-82) +
  * MarginLoss in one kernel: one warp per positive triple scores it and its n_neg negatives;

@@ -11,6 +11,9 @@ v0.17.7 (commit 3adb934) runs for
   * filtering               utils/modeling.py:53-102
   * ranking                 utils/operations.py:37-61
   * the evaluator loop      evaluation.py:263-308
+  * relation prediction     evaluation.py:64-112 with the relation case of
+                            inference_scoring_function (interfaces.py:261-272,
+                            bilinear.py:115-121, 241-245, 524-528)
   * per-triple scoring      models/translation.py:69-81, models/bilinear.py:60-71,
                             188-199, 460-473, models/interfaces.py:39-82
   * Bernoulli corruption    sampling.py:259-327, utils/operations.py:116-179
@@ -192,6 +195,70 @@ def link_prediction(kind, P, heads, tails, rels, dict_of_heads, dict_of_tails, b
         out[0][lo:hi] = rank_of_true(s, h)
         out[2][lo:hi] = rank_of_true(fs, h)
     return tuple(out)
+
+
+# --------------------------------------------------------------------------- relation prediction
+def relation_scores_all(kind, P, h_idx, t_idx):
+    """(b, n_rel) scores of every relation for the pairs (h, t): inference_prepare_candidates(...,
+    entities=False) + the relation case of inference_scoring_function -- interfaces.py:261-272
+    (TransE), bilinear.py:115-121 (RESCAL), 241-245 (DistMult), 524-528 (ComplEx)."""
+    b = h_idx.shape[0]
+    if kind in ("transe_l1", "transe_l2"):
+        diss = l1_diss if kind == "transe_l1" else l2_diss
+        d = P["ent"].shape[1]
+        h, t = P["ent"][h_idx], P["ent"][t_idx]
+        cands = P["rel"].view(1, -1, d).expand(b, -1, -1)
+        return -diss(h.view(b, -1, d) + cands, t.view(b, -1, d))
+    if kind == "distmult":
+        d = P["ent"].shape[1]
+        h, t = P["ent"][h_idx], P["ent"][t_idx]
+        cands = P["rel"].view(1, -1, d).expand(b, -1, -1)
+        hr = h.view(b, 1, d) * cands
+        return (hr * t.view(b, 1, d)).sum(dim=2)
+    if kind == "rescal":
+        d = P["ent"].shape[1]
+        n_rel = P["rel_mat"].shape[0]
+        h, t = P["ent"][h_idx], P["ent"][t_idx]
+        cands = P["rel_mat"].view(1, n_rel, d, d).expand(b, n_rel, d, d)
+        hr = torch.matmul(h.view(b, 1, 1, d), cands).view(b, n_rel, d)
+        return (hr * t.view(b, 1, d)).sum(dim=2)
+    if kind == "complex":
+        d = P["re_ent"].shape[1]
+        re_h, im_h = _rows(P, ("re_ent", "im_ent"), h_idx)
+        re_t, im_t = _rows(P, ("re_ent", "im_ent"), t_idx)
+        re_r = P["re_rel"].view(1, -1, d).expand(b, -1, -1)
+        im_r = P["im_rel"].view(1, -1, d).expand(b, -1, -1)
+        return ((re_h * re_t + im_h * im_t).view(b, 1, d) * re_r
+                + (re_h * im_t - im_h * re_t).view(b, 1, d) * im_r).sum(dim=2)
+    raise ValueError(kind)
+
+
+def relation_prediction(kind, P, heads, tails, rels, dict_of_rels, b_size, directed=True):
+    """RelationPredictionEvaluator.evaluate, evaluation.py:64-112: (rank_true_rels,
+    filt_rank_true_rels).  Undirected: the (t, ?, h) scores are concatenated after the (h, ?, t)
+    ones and the true relation keeps its index in the first half."""
+    n = heads.shape[0]
+    out = [torch.empty(n, dtype=torch.long) for _ in range(2)]
+    for lo in range(0, n, b_size):
+        hi = min(n, lo + b_size)
+        h, t, r = heads[lo:hi], tails[lo:hi], rels[lo:hi]
+        s = relation_scores_all(kind, P, h, t)
+        fs = filtered_scores(s, dict_of_rels, h, t, r)
+        if not directed:
+            s2 = relation_scores_all(kind, P, t, h)
+            fs2 = filtered_scores(s2, dict_of_rels, h, t, r)
+            s, fs = torch.cat((s, s2), dim=1), torch.cat((fs, fs2), dim=1)
+        out[0][lo:hi] = rank_of_true(s, r)
+        out[1][lo:hi] = rank_of_true(fs, r)
+    return tuple(out)
+
+
+def build_rel_dict(heads, tails, rels):
+    """data_structures.py:386-397: dict_of_rels keyed (h, t)."""
+    dr = defaultdict(set)
+    for h, t, r in zip(heads.tolist(), tails.tolist(), rels.tolist()):
+        dr[(h, t)].add(r)
+    return dr
 
 
 def lp_metrics(rh, rt, frh, frt, k=10):

@@ -109,6 +109,15 @@ def load_golden(name):
     return out
 
 
+def load_golden_rel(name):
+    """Relation-prediction outputs of the reference for fixture `name` (rel_<name>.npz) plus the
+    dict_of_rels it used (key "dr")."""
+    z = np.load(os.path.join(GOLDEN_DIR, "rel_" + name + ".npz"), allow_pickle=False)
+    out = {k: z[k] for k in z.files}
+    out["dr"] = _arrays_to_dict(z["dr_keys"], z["dr_offs"], z["dr_vals"])
+    return out
+
+
 def model_from_golden(g):
     model = KIND_TO_CLASS[g["kind"]](g["dim"], g["n_ent"], g["n_rel"])
     model.load_state_dict(g["state"])

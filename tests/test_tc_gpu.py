@@ -54,11 +54,11 @@ def test_approximate_scores_within_half_the_bound(kind, d, cuda_device):
         want = oracle.scores_all(kind, P, h, t, r, name).double()
         assert not torch.isnan(got).any()
         # the bound the kernel uses: gamma * |a| |b|  (dot) or gamma * (|a| + |b|)^2  (L2)
-        k_total = 2 * d if kind == "complex" else d
         l2 = kind == "transe_l2"
+        k_total = 2 * d if kind == "complex" else (d + 3 if l2 else d)  # csrc/api.cu: tc_k_total
         gamma = (3.0 * 2.0 ** -16 + 2.0 * (3.0 * ((k_total + 15) // 16) + 2.0) * 2.0 ** -22
                  + (k_total + 4.0) * 2.0 ** -24)                       # csrc/tc.h: tc_gamma
-        gamma2 = (k_total + 24.0) * 2.0 ** -23                         # csrc/tc.h: tc_gamma2
+        gamma2 = (k_total + 42.0) * 2.0 ** -23                         # csrc/tc.h: tc_gamma2
         # operand norms
         if kind == "complex":
             cand = torch.cat([P["re_ent"], P["im_ent"]], 1).double()
@@ -123,3 +123,34 @@ def test_exact_ties_and_duplicates_with_tensor_cores(cuda_device):
     for a, b in zip((ev.rank_true_heads, ev.rank_true_tails, ev.filt_rank_true_heads,
                      ev.filt_rank_true_tails), ref):
         assert torch.equal(a, b)
+
+
+# (bk, resident, ct_group, max_ctas): every geometry of the scan, with grids small enough that
+# each CTA walks many work units (ring phases wrap, the resident query image is replaced, both
+# TMEM accumulators are reused)
+TC_CONFIGS = [(32, 1, 1, 3), (32, 1, 2, 5), (32, 1, 0, 0), (32, 0, 2, 4), (64, 0, 1, 3), (64, 0, 0, 0)]
+
+
+@pytest.mark.parametrize("cfg", TC_CONFIGS, ids=lambda c: "bk%d_res%d_grp%d_ctas%d" % c)
+@pytest.mark.parametrize("kind,d", [("transe_l2", 200), ("distmult", 72), ("complex", 120)])
+def test_every_scan_geometry_gives_oracle_ranks(cfg, kind, d, cuda_device):
+    n_ent, n_rel = 2700, 6
+    kg, dh, dt = helpers.make_kg(n_ent, n_rel, n_facts=9000, n_test=520, seed=41 + d)
+    model = helpers.make_model(kind, d, n_ent, n_rel, seed=d).to(cuda_device)
+    P = helpers.oracle_params(kind, model)
+    ref = oracle.link_prediction(kind, P, kg.head_idx, kg.tail_idx, kg.relations, dh, dt, 128)
+    dev = cuda_device
+    csr_t = tuple(x.to(dev) for x in filter_csr(dt, kg.head_idx, kg.relations, kg.tail_idx))
+    csr_h = tuple(x.to(dev) for x in filter_csr(dh, kg.tail_idx, kg.relations, kg.head_idx))
+    try:
+        _lib.tc_configure(*cfg)
+        eng = CudaEngine(tensor_core=True)
+        spec = ModelSpec.from_model(model)
+        got = rank_link_prediction(spec, kg.head_idx.to(dev), kg.tail_idx.to(dev), kg.relations.to(dev),
+                                   csr_t, csr_h, engine=eng)
+        torch.cuda.synchronize()
+    finally:
+        _lib.tc_configure(32, 1, 0, 0)
+    assert len(eng.tc_stats) == 2
+    for a, b in zip(got, ref):
+        assert torch.equal(a.cpu(), b)

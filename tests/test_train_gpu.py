@@ -116,6 +116,45 @@ def test_gradients_match_torch_autograd_of_the_oracle(kind, cuda_device):
         _close_grad(p.grad, leaves[name].grad, rtol=2e-4)
 
 
+@pytest.mark.parametrize("kind", ["transe_l1", "transe_l2", "distmult"])
+@pytest.mark.parametrize("d", [200, 256, 36])
+def test_fast_fused_step_matches_oracle_autograd(kind, d, cuda_device):
+    """The register-resident fused step (csrc/train.cu: margin_step_fast_kernel; dim % 4 == 0,
+    dim <= 256): head- and tail-corrupted negatives mixed, a negative equal to the positive, a few
+    pairs with BOTH ends replaced (generic path inside the fast kernel), un-normalised weights."""
+    n_ent, n_rel, b, n_neg = 900, 7, 96, 40
+    model = helpers.make_model(kind, d, n_ent, n_rel, seed=11)
+    with torch.no_grad():
+        model.ent_emb.weight.mul_(1.0 + torch.rand(n_ent, 1))
+    model = model.to(cuda_device)
+    gen = torch.Generator().manual_seed(5)
+    h = torch.randint(0, n_ent, (b,), generator=gen)
+    t = torch.randint(0, n_ent, (b,), generator=gen)
+    r = torch.randint(0, n_rel, (b,), generator=gen)
+    nh, nt = h.repeat(n_neg), t.repeat(n_neg)
+    which = torch.rand(b * n_neg, generator=gen) < 0.45
+    rnd = torch.randint(1, n_ent, (b * n_neg,), generator=gen)
+    nh = torch.where(which, rnd, nh)
+    nt = torch.where(~which, rnd, nt)
+    nt[5], nh[5] = t[5], h[5]                       # a "negative" identical to the positive
+    both = torch.arange(17, b * n_neg, 301)
+    nh[both] = (h.repeat(n_neg)[both] + 3) % n_ent  # both ends differ
+    nt[both] = (t.repeat(n_neg)[both] + 5) % n_ent
+    P = {k: v.requires_grad_(True) for k, v in helpers.oracle_params(kind, model).items()}
+    pos, neg = oracle.forward_pos_neg(kind, P, h, t, r, nh, nt)
+    margin = 1.0 if kind == "distmult" else 0.3
+    ref_loss = oracle.margin_loss(pos, neg, margin)
+    ref_loss.backward()
+    frac_active = ((margin - pos + neg) > 0).float().mean().item()
+    assert 0.05 < frac_active <= 1.0
+    dev = cuda_device
+    loss = fused_margin_step(model, h.to(dev), t.to(dev), r.to(dev), margin, negatives=(nh.to(dev), nt.to(dev)))
+    assert loss.item() == pytest.approx(ref_loss.item(), rel=2e-5)
+    loss.backward()
+    _close_grad(model.ent_emb.weight.grad, P["ent"].grad, rtol=2e-4)
+    _close_grad(model.rel_emb.weight.grad, P["rel"].grad, rtol=2e-4)
+
+
 def test_sampler_probabilities_match_reference():
     pass  # CPU-side; see tests/test_host_logic.py::test_bernoulli_probs_match_golden
 
@@ -201,3 +240,50 @@ def test_training_loop_reduces_loss(cuda_device):
         model.normalize_parameters()
         losses.append(loss.item())
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+@pytest.mark.parametrize("name", ["LogisticLoss", "BinaryCrossEntropyLoss"])
+def test_logistic_and_bce_losses_match_torch(name, cuda_device):
+    """utils/losses.py:47-112 restated with the same torch modules on the CPU."""
+    gen = torch.Generator().manual_seed(3)
+    pos = (torch.randn(5000, generator=gen) * 4).requires_grad_(True)
+    neg = (torch.randn(5000, generator=gen) * 4).requires_grad_(True)
+    with torch.no_grad():
+        pos[:3] = torch.tensor([40.0, -40.0, 0.0])      # saturated sigmoids
+        neg[:3] = torch.tensor([-40.0, 40.0, 0.0])
+    if name == "LogisticLoss":
+        crit = torch.nn.SoftMarginLoss(reduction="sum")
+        ref = crit(pos, torch.ones_like(pos)) + crit(neg, -torch.ones_like(neg))
+    else:
+        crit = torch.nn.BCELoss(reduction="sum")
+        ref = crit(torch.sigmoid(pos), torch.ones_like(pos)) + crit(torch.sigmoid(neg), torch.zeros_like(neg))
+    ref.backward()
+    p = pos.detach().to(cuda_device).requires_grad_(True)
+    n = neg.detach().to(cuda_device).requires_grad_(True)
+    loss = getattr(tk, name)()(p, n)
+    assert loss.item() == pytest.approx(ref.item(), rel=1e-5)
+    (2.0 * loss).backward()
+    _close(p.grad, 2.0 * pos.grad, 1e-4, 1e-6)
+    _close(n.grad, 2.0 * neg.grad, 1e-4, 1e-6)
+
+
+def test_uniform_sampler_support_and_frequencies(cuda_device):
+    n_ent, n_rel = 3000, 4
+    h, t, r = helpers.random_graph(n_ent, n_rel, 20000, seed=8)
+    kg = tk.KnowledgeGraph(h, t, r, n_ent, n_rel, dict_of_heads={}, dict_of_tails={})
+    sampler = tk.UniformNegativeSampler(kg, n_neg=8, seed=5)
+    b = 4096
+    hb, tb_ = h[:b].to(cuda_device), t[:b].to(cuda_device)
+    nh, nt = sampler.corrupt_batch(hb, tb_)          # relations are optional, as in the reference
+    assert nh.shape == (b * 8,) and nh.dtype == torch.int64 and nh.device == hb.device
+    H, T = hb.repeat(8), tb_.repeat(8)
+    head_changed, tail_changed = nh != H, nt != T
+    assert not (head_changed & tail_changed).any()
+    f = head_changed.float().mean().item()
+    assert abs(f - 0.5) < 5 * (0.25 / (b * 8)) ** 0.5 + 2.0 / n_ent
+    corrupted = torch.where(head_changed, nh, nt)[head_changed | tail_changed]
+    assert corrupted.min().item() >= 1 and corrupted.max().item() < n_ent
+    nh2, nt2 = tk.UniformNegativeSampler(kg, n_neg=8, seed=5).corrupt_batch(hb, tb_)
+    assert torch.equal(nh, nh2) and torch.equal(nt, nt2)
+    ch, ct = sampler.corrupt_kg(1000, True)          # whole graph, n_neg = 1, CPU tensors out
+    assert ch.shape == (kg.n_facts,) and not ch.is_cuda and ct.dtype == torch.int64

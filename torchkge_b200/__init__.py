@@ -9,8 +9,8 @@ from .exceptions import (NotYetEvaluatedError, NotYetImplementedError, SanityErr
 from .data import KnowledgeGraph  # noqa: F401
 from .models import (ComplExModel, DistMultModel, RESCALModel, RotatEModel,  # noqa: F401
                      TransEModel)
-from .evaluation import LinkPredictionEvaluator  # noqa: F401
-from .losses import MarginLoss  # noqa: F401
-from .sampling import BernoulliNegativeSampler  # noqa: F401
+from .evaluation import LinkPredictionEvaluator, RelationPredictionEvaluator  # noqa: F401
+from .losses import BinaryCrossEntropyLoss, LogisticLoss, MarginLoss  # noqa: F401
+from .sampling import BernoulliNegativeSampler, UniformNegativeSampler  # noqa: F401
 
 __version__ = "0.1.0"

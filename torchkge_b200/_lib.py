@@ -13,10 +13,11 @@ LIB_PATH = os.path.join(HERE, "lib", "libkge_b200.so")
 
 # kge_model_t / kge_side_t (include/kge_b200.h)
 TRANSE_L1, TRANSE_L2, DISTMULT, RESCAL, COMPLEX, ROTATE = range(6)
-SIDE_TAIL, SIDE_HEAD = 0, 1
+SIDE_TAIL, SIDE_HEAD, SIDE_REL = 0, 1, 2
 TILE_C, TILE_Q = 128, 64
-ABI_VERSION = 2
+ABI_VERSION = 4
 FLAG_TENSOR_CORE = 1
+LOSS_LOGISTIC, LOSS_BCE = 1, 2
 
 MODEL_NAMES = {TRANSE_L1: "TransE-L1", TRANSE_L2: "TransE-L2", DISTMULT: "DistMult",
                RESCAL: "RESCAL", COMPLEX: "ComplEx", ROTATE: "RotatE"}
@@ -41,6 +42,7 @@ class RankArgs(ctypes.Structure):
         ("raw_count", _p), ("filt_sub", _p), ("true_score", _p),
         ("workspace", _p), ("workspace_bytes", _c.c_size_t), ("stream", _p),
         ("tc_packed", _p), ("tc_stats", _p), ("tc_dump", _p),
+        ("true_rows", _p), ("true_score_in", _p),
     ]
 
 
@@ -91,6 +93,7 @@ SIGNATURES = {
     "kge_rank_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64,
                                                _c.c_int]),
     "kge_tc_packed_bytes": (_c.c_size_t, [_c.c_int, _c.c_int64, _c.c_int]),
+    "kge_tc_configure": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     "kge_tc_pack_table": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _c.c_int, _p, _p]),
     "kge_rank_side": (_c.c_int, [_c.POINTER(RankArgs)]),
     "kge_filter_side": (_c.c_int, [_c.POINTER(RankArgs)]),
@@ -103,6 +106,8 @@ SIGNATURES = {
                                      _c.c_uint64, _c.c_uint64, _p, _p, _p]),
     "kge_margin_loss_fwd": (_c.c_int, [_p, _p, _c.c_int64, _c.c_float, _p, _p]),
     "kge_margin_loss_bwd": (_c.c_int, [_p, _p, _c.c_int64, _c.c_float, _p, _p, _p, _p]),
+    "kge_pair_loss_fwd": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _p, _p]),
+    "kge_pair_loss_bwd": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _p, _p, _p, _p]),
     "kge_margin_step_fwd": (_c.c_int, [_c.POINTER(MarginStepArgs)]),
     "kge_margin_step_bwd": (_c.c_int, [_c.POINTER(MarginStepArgs), _c.POINTER(Grads), _p]),
     "kge_scan_timing_enable": (_c.c_int, [_c.c_int]),
@@ -157,6 +162,11 @@ def build_schedule(model, dim):
     code = np.zeros(dim, dtype=np.uint8)
     check(lib.kge_build_schedule(model, dim, perm.ctypes.data, code.ctypes.data), "kge_build_schedule")
     return perm, code
+
+
+def tc_configure(bk=-1, resident=-1, ct_group=-1, max_ctas=-1):
+    """Tuning / test hook of the tensor-core scan (include/kge_b200.h: kge_tc_configure)."""
+    check(load().kge_tc_configure(bk, resident, ct_group, max_ctas), "kge_tc_configure")
 
 
 def scan_timing_enable(on=True):

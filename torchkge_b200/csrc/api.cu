@@ -78,7 +78,10 @@ struct Workspace {
 bool tc_supported(int el) {
   return el == kge::EL_DOT1 || el == kge::EL_DOT2 || el == kge::EL_L2_TAIL || el == kge::EL_L2_HEAD;
 }
-int tc_k_total(int el, int dim) { return el == kge::EL_DOT2 ? 2 * dim : dim; }
+bool tc_is_l2(int el) { return el == kge::EL_L2_TAIL || el == kge::EL_L2_HEAD; }
+// contraction length of the operand images: both planes for ComplEx; L2 carries the candidate's
+// squared norm in three extra k slots (tc.h: launch_pack_b)
+int tc_k_total(int el, int dim) { return el == kge::EL_DOT2 ? 2 * dim : (tc_is_l2(el) ? dim + 3 : dim); }
 
 Workspace carve(void* base, int qw, int dim, int64_t n, int el = -1, int64_t n_rows = 0,
                 int flags = 0) {
@@ -98,7 +101,7 @@ Workspace carve(void* base, int qw, int dim, int64_t n, int el = -1, int64_t n_r
   w.apack = nullptr; w.qbound = w.qnorm2 = nullptr; w.amb_count = nullptr; w.amb_pairs = nullptr;
   w.amb_cap = 0;
   if ((flags & KGE_FLAG_TENSOR_CORE) && el >= 0 && tc_supported(el) && n_rows > 0) {
-    const int n_kb = (tc_k_total(el, dim) + kge::tc::TC_BK - 1) / kge::tc::TC_BK;
+    const int n_kb = kge::tc::n_kblocks(tc_k_total(el, dim));
     w.apack = static_cast<unsigned char*>(take(kge::tc::a_image_bytes(n, n_kb)));
     w.qbound = static_cast<float*>(take((size_t)n * sizeof(float)));
     w.qnorm2 = static_cast<float*>(take((size_t)n * sizeof(float)));
@@ -248,9 +251,14 @@ size_t kge_rank_workspace_bytes(int model, int side, int dim, int64_t n, int64_t
 size_t kge_tc_packed_bytes(int model, int64_t n_rows, int dim) {
   const int el = kge::elem_kind_for(model, KGE_SIDE_TAIL);
   if (el < 0 || !tc_supported(el) || n_rows <= 0 || dim < 1) return 0;
-  const int n_kb = (tc_k_total(el, dim) + kge::tc::TC_BK - 1) / kge::tc::TC_BK;
+  const int n_kb = kge::tc::n_kblocks(tc_k_total(el, dim));
   const int64_t n_ct = (n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
   return kge::tc::b_image_bytes(n_rows, n_kb) + 2 * (size_t)n_ct * kge::tc::TC_BN * sizeof(float);
+}
+
+int kge_tc_configure(int bk, int resident, int ct_group, int max_ctas) {
+  kge::tc::configure(bk, resident, ct_group, max_ctas);
+  return KGE_OK;
 }
 
 int kge_tc_pack_table(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
@@ -261,12 +269,12 @@ int kge_tc_pack_table(int model, const float* ent0, const float* ent1, int64_t n
   if (!ent0 || !tc_packed || (kge::elem_cw(el) == 2 && !ent1))
     return fail(KGE_ERR_ARG, "kge_tc_pack_table: null pointer");
   const int k_total = tc_k_total(el, dim);
-  const int n_kb = (k_total + kge::tc::TC_BK - 1) / kge::tc::TC_BK;
+  const int n_kb = kge::tc::n_kblocks(k_total);
   const int64_t n_ct = (n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
   unsigned char* bpack = static_cast<unsigned char*>(tc_packed);
   float* cbound = reinterpret_cast<float*>(bpack + kge::tc::b_image_bytes(n_rows, n_kb));
   float* cnorm2 = cbound + (size_t)n_ct * kge::tc::TC_BN;
-  KGE_CUDA_TRY(kge::tc::launch_pack_b(ent0, ent1, n_rows, dim, k_total, n_kb, bpack, cbound, cnorm2,
+  KGE_CUDA_TRY(kge::tc::launch_pack_b(ent0, ent1, n_rows, dim, k_total, n_kb, tc_is_l2(el), bpack, cbound, cnorm2,
                                       static_cast<cudaStream_t>(stream)),
                "tc pack table");
   return KGE_OK;
@@ -278,12 +286,15 @@ int kge_rank_side(const kge_rank_args_t* a) {
   if (el < 0) return fail(KGE_ERR_ARG, "kge_rank_side: unknown model/side");
   if (a->n == 0) return KGE_OK;
   if (a->n < 0 || a->n_rows < 0 || a->dim < 1) return fail(KGE_ERR_ARG, "kge_rank_side: bad sizes");
-  if (!a->packed || !a->ent0 || !a->rel0 || !a->hrows || !a->trows || !a->raw_count ||
+  const bool rel_side = a->side == KGE_SIDE_REL;
+  if (!a->packed || !a->ent0 || (!a->rel0 && !rel_side) || !a->hrows || !a->trows || !a->raw_count ||
       !a->workspace)
     return fail(KGE_ERR_ARG, "kge_rank_side: null pointer");
   if (kge::elem_cw(el) == 2 && !a->ent1) return fail(KGE_ERR_ARG, "kge_rank_side: ent1 required");
-  if (model_needs_rel1(a->model) && !a->rel1)
+  if (!rel_side && model_needs_rel1(a->model) && !a->rel1)
     return fail(KGE_ERR_ARG, "kge_rank_side: rel1 required");
+  if (rel_side && !a->true_rows && !a->true_score_in)
+    return fail(KGE_ERR_ARG, "kge_rank_side: true_rows required for KGE_SIDE_REL");
   if (a->filt_offs && (!a->filt_ids || !a->filt_sub) && a->n_filt > 0)
     return fail(KGE_ERR_ARG, "kge_rank_side: filter arrays incomplete");
   const HostSchedule* hs = get_schedule(a->model, a->dim);
@@ -305,10 +316,15 @@ int kge_rank_side(const kge_rank_args_t* a) {
   const float nan_v = __builtin_nanf("");
   KGE_CUDA_TRY(kge::launch_fill_f32(w.s_true + a->n, nan_v, n_qt * kge::TILE_Q - a->n, st),
                "fill s_true pad");
-  const float* true_rows = a->side == KGE_SIDE_TAIL ? a->trows : a->hrows;
-  KGE_CUDA_TRY(kge::launch_true_scores(el, casc, a->dim, a->n, w.qplain, true_rows, w.perm, w.code,
-                                       w.s_true, st),
-               "true_scores");
+  const float* true_rows = a->true_rows ? a->true_rows : (a->side == KGE_SIDE_TAIL ? a->trows : a->hrows);
+  if (a->true_score_in)
+    KGE_CUDA_TRY(cudaMemcpyAsync(w.s_true, a->true_score_in, (size_t)a->n * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st),
+                 "copy true_score_in");
+  else
+    KGE_CUDA_TRY(kge::launch_true_scores(el, casc, a->dim, a->n, w.qplain, true_rows, w.perm, w.code,
+                                         w.s_true, st),
+                 "true_scores");
   if (a->true_score)
     KGE_CUDA_TRY(cudaMemcpyAsync(a->true_score, w.s_true, (size_t)a->n * sizeof(float),
                                  cudaMemcpyDeviceToDevice, st),
@@ -318,13 +334,13 @@ int kge_rank_side(const kge_rank_args_t* a) {
     // tensor-core bound-and-refine: approximate scores decide all but the near-tie band,
     // which is re-scored exactly (same device functions as the scalar scan)
     const int k_total = tc_k_total(el, a->dim);
-    const int n_kb = (k_total + kge::tc::TC_BK - 1) / kge::tc::TC_BK;
+    const int n_kb = kge::tc::n_kblocks(k_total);
     const int64_t n_ct = (a->n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
     const bool l2 = el == kge::EL_L2_TAIL || el == kge::EL_L2_HEAD;
     KGE_CUDA_TRY(kge::tc::launch_pack_a(w.qplain, qw, a->n, a->dim, k_total, n_kb,
-                                        el == kge::EL_L2_HEAD ? 1 : 0, w.apack, w.qbound, w.qnorm2, st),
+                                        el == kge::EL_L2_HEAD ? 1 : 0, l2, w.apack, w.qbound, w.qnorm2, st),
                  "tc pack queries");
-    const int regions = kge::tc::scan_grid_size(a->n, a->n_rows);
+    const int regions = kge::tc::scan_grid_size(a->n, a->n_rows, n_kb);
     if (regions <= 0 || regions > 256) return fail(KGE_ERR_CUDA, "kge_rank_side: cannot size the tensor-core grid");
     const unsigned long long region_cap = w.amb_cap / (unsigned long long)regions;
     KGE_CUDA_TRY(cudaMemsetAsync(w.amb_count, 0, 256 * sizeof(unsigned long long), st), "tc reset list");
@@ -337,7 +353,7 @@ int kge_rank_side(const kge_rank_args_t* a) {
     tp.counts = a->raw_count; tp.amb_count = w.amb_count; tp.amb_pairs = w.amb_pairs;
     tp.amb_cap = region_cap; tp.dump = a->tc_dump;
     tp.gamma = kge::tc::tc_gamma(k_total); tp.gamma2 = kge::tc::tc_gamma2(k_total); tp.l2 = l2 ? 1 : 0;
-    tp.n_kb = n_kb; tp.k_total = k_total;
+    tp.n_kb = n_kb; tp.k_total = k_total; tp.ct_group = 0;
     tp.n_q = a->n; tp.n_rows = a->n_rows;
     tp.n_qt = (a->n + kge::tc::TC_BM - 1) / kge::tc::TC_BM; tp.n_ct = n_ct;
     KGE_CUDA_TRY(timed_launch(1, st, [&] { return kge::tc::launch_tc_scan(tp, st); }), "tc scan");
@@ -531,6 +547,27 @@ int kge_margin_loss_bwd(const float* pos, const float* neg, int64_t n, float mar
   KGE_CUDA_TRY(kge::launch_margin_loss_bwd(pos, neg, n, margin, grad_loss, grad_pos, grad_neg,
                                            static_cast<cudaStream_t>(stream)),
                "margin_loss_bwd");
+  return KGE_OK;
+}
+
+int kge_pair_loss_fwd(int kind, const float* pos, const float* neg, int64_t n, float* loss, void* stream) {
+  if (kind != KGE_LOSS_LOGISTIC && kind != KGE_LOSS_BCE) return fail(KGE_ERR_ARG, "kge_pair_loss_fwd: unknown loss kind");
+  if (n == 0) return KGE_OK;
+  if (n < 0 || !pos || !neg || !loss) return fail(KGE_ERR_ARG, "kge_pair_loss_fwd: bad argument");
+  KGE_CUDA_TRY(kge::launch_pair_loss_fwd(kind, pos, neg, n, loss, static_cast<cudaStream_t>(stream)),
+               "pair_loss_fwd");
+  return KGE_OK;
+}
+
+int kge_pair_loss_bwd(int kind, const float* pos, const float* neg, int64_t n, const float* grad_loss,
+                      float* grad_pos, float* grad_neg, void* stream) {
+  if (kind != KGE_LOSS_LOGISTIC && kind != KGE_LOSS_BCE) return fail(KGE_ERR_ARG, "kge_pair_loss_bwd: unknown loss kind");
+  if (n == 0) return KGE_OK;
+  if (n < 0 || !pos || !neg || !grad_loss || !grad_pos || !grad_neg)
+    return fail(KGE_ERR_ARG, "kge_pair_loss_bwd: bad argument");
+  KGE_CUDA_TRY(kge::launch_pair_loss_bwd(kind, pos, neg, n, grad_loss, grad_pos, grad_neg,
+                                         static_cast<cudaStream_t>(stream)),
+               "pair_loss_bwd");
   return KGE_OK;
 }
 

@@ -8,6 +8,20 @@ namespace kge {
 
 int elem_kind_for(int model, int side) {
   const bool tail = side == KGE_SIDE_TAIL;
+  if (side == KGE_SIDE_REL) {
+    // candidates are relation rows, the query is the (h, t) pair:
+    //   TransE   -diss(h + c, t)                       interfaces.py:261-272  ((c + h) - t: fp add commutes)
+    //   DistMult ((h * c) * t).sum                     bilinear.py:241-245
+    //   ComplEx  ((re_h re_t + im_h im_t) re_c + (re_h im_t - im_h re_t) im_c).sum   bilinear.py:524-528
+    switch (model) {
+      case KGE_TRANSE_L1: return EL_L1_HEAD;
+      case KGE_TRANSE_L2: return EL_L2_HEAD;
+      case KGE_DISTMULT: return EL_DOT_MID;
+      case KGE_COMPLEX: return EL_DOT2;
+      default: return -1;  // RESCAL (batched matmul in the reference) and RotatE: not on this path
+    }
+  }
+  if (side != KGE_SIDE_TAIL && side != KGE_SIDE_HEAD) return -1;
   switch (model) {
     case KGE_TRANSE_L1: return tail ? EL_L1_TAIL : EL_L1_HEAD;
     case KGE_TRANSE_L2: return tail ? EL_L2_TAIL : EL_L2_HEAD;
@@ -92,6 +106,9 @@ __global__ void gather_rows_kernel(const float* __restrict__ ent0, const float* 
 //   ComplEx head q0 = re_r*re_t + im_r*im_t ; q1 = re_r*im_t - im_r*re_t   bilinear.py:521-522
 //   RotatE       same algebra as ComplEx with (rel0, rel1) = (cos, sin) of the phases:
 //                tail q = h o r ; head q = t o conj(r)
+// Relation prediction (side = KGE_SIDE_REL, candidates = relation rows; rel0/rel1 unused):
+//   TransE / DistMult  q0 = h, q1 = t
+//   ComplEx  q0 = re_h*re_t + im_h*im_t ; q1 = re_h*im_t - im_h*re_t       bilinear.py:527-528
 __global__ void prep_queries_kernel(int model, int side, int dim, long long n,
                                     const float* __restrict__ hrows,
                                     const float* __restrict__ trows,
@@ -103,8 +120,20 @@ __global__ void prep_queries_kernel(int model, int side, int dim, long long n,
   if (gid >= n * dim) return;
   const long long i = gid / dim;
   const int k = (int)(gid - i * dim);
-  const long long r = r_idx ? r_idx[i] : i;  // null r_idx: rel tables hold one row per query
   const bool tail = side == KGE_SIDE_TAIL;
+  if (side == KGE_SIDE_REL) {
+    if (model == KGE_COMPLEX) {
+      const float re_h = hrows[((size_t)i * 2 + 0) * dim + k], im_h = hrows[((size_t)i * 2 + 1) * dim + k];
+      const float re_t = trows[((size_t)i * 2 + 0) * dim + k], im_t = trows[((size_t)i * 2 + 1) * dim + k];
+      qplain[((size_t)i * 2 + 0) * dim + k] = __fadd_rn(__fmul_rn(re_h, re_t), __fmul_rn(im_h, im_t));
+      qplain[((size_t)i * 2 + 1) * dim + k] = __fsub_rn(__fmul_rn(re_h, im_t), __fmul_rn(im_h, re_t));
+    } else {
+      qplain[((size_t)i * 2 + 0) * dim + k] = hrows[(size_t)i * dim + k];
+      qplain[((size_t)i * 2 + 1) * dim + k] = trows[(size_t)i * dim + k];
+    }
+    return;
+  }
+  const long long r = r_idx ? r_idx[i] : i;  // null r_idx: rel tables hold one row per query
   switch (model) {
     case KGE_TRANSE_L1:
     case KGE_TRANSE_L2: {
@@ -362,6 +391,7 @@ cudaError_t launch_fill_f32(float* dst, float value, int64_t n, cudaStream_t str
     case EL_DOT1: if (cascade) { CALL(EL_DOT1, true); } else { CALL(EL_DOT1, false); } break; \
     case EL_DOT2: if (cascade) { CALL(EL_DOT2, true); } else { CALL(EL_DOT2, false); } break; \
     case EL_ROT: if (cascade) { CALL(EL_ROT, true); } else { CALL(EL_ROT, false); } break;    \
+    case EL_DOT_MID: if (cascade) { CALL(EL_DOT_MID, true); } else { CALL(EL_DOT_MID, false); } break; \
     case EL_L1_TAIL: CALL(EL_L1_TAIL, false); break;                        \
     case EL_L1_HEAD: CALL(EL_L1_HEAD, false); break;                        \
     case EL_L2_TAIL: CALL(EL_L2_TAIL, false); break;                        \

@@ -21,7 +21,8 @@ enum ElemKind : int {
   EL_L2_TAIL = 4,  // (q0 - c0)^2                interfaces.py:253-254 + dissimilarities.py:25
   EL_L2_HEAD = 5,  // ((c0 + q0) - q1)^2         interfaces.py:258-260 + dissimilarities.py:25
   EL_ROT = 6,      // sqrt((q0-c0)^2+(q1-c1)^2)  oracle RotatE restatement
-  EL_COUNT = 7
+  EL_DOT_MID = 7,  // (q0*c0)*q1                 DistMult relation prediction, bilinear.py:243-245
+  EL_COUNT = 8
 };
 
 template <int EL> struct ElemTraits;
@@ -32,6 +33,7 @@ template <> struct ElemTraits<EL_L1_HEAD> { static constexpr int QW = 2, CW = 1,
 template <> struct ElemTraits<EL_L2_TAIL> { static constexpr int QW = 1, CW = 1, RED = RED_NORM2; };
 template <> struct ElemTraits<EL_L2_HEAD> { static constexpr int QW = 2, CW = 1, RED = RED_NORM2; };
 template <> struct ElemTraits<EL_ROT> { static constexpr int QW = 2, CW = 2, RED = RED_SUM; };
+template <> struct ElemTraits<EL_DOT_MID> { static constexpr int QW = 2, CW = 1, RED = RED_SUM; };
 
 // For the L2 kinds returns the difference x (the caller squares it, fused or not); for all
 // other kinds returns the finished term.
@@ -49,6 +51,8 @@ __device__ __forceinline__ float elem_value(float q0, float q1, float c0, float 
     return __fsub_rn(q0, c0);
   } else if constexpr (EL == EL_L2_HEAD) {
     return __fsub_rn(__fadd_rn(c0, q0), q1);
+  } else if constexpr (EL == EL_DOT_MID) {
+    return __fmul_rn(__fmul_rn(q0, c0), q1);
   } else {  // EL_ROT
     const float dr = __fsub_rn(q0, c0);
     const float di = __fsub_rn(q1, c1);
@@ -147,7 +151,7 @@ __device__ __forceinline__ void acc_t_add_a(Acc& r) { r.t = __fadd_rn(r.t, r.a);
 // (dissimilarities.py:25 computes norm(p=2)**2; interfaces.py:254,260 negate).
 template <int EL>
 __device__ __forceinline__ float acc_finish(const Acc& r) {
-  if constexpr (EL == EL_DOT1 || EL == EL_DOT2) {
+  if constexpr (EL == EL_DOT1 || EL == EL_DOT2 || EL == EL_DOT_MID) {
     return r.t;
   } else if constexpr (elem_is_l2<EL>()) {
     const float n = __fsqrt_rn(r.t);

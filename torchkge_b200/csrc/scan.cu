@@ -299,6 +299,8 @@ cudaError_t launch_scan_g(int el, bool cascade, ScanParams& p, cudaStream_t stre
       return cascade ? launch_one<EL_DOT2, true, G>(p, stream) : launch_one<EL_DOT2, false, G>(p, stream);
     case EL_ROT:
       return cascade ? launch_one<EL_ROT, true, G>(p, stream) : launch_one<EL_ROT, false, G>(p, stream);
+    case EL_DOT_MID:
+      return cascade ? launch_one<EL_DOT_MID, true, G>(p, stream) : launch_one<EL_DOT_MID, false, G>(p, stream);
     case EL_L1_TAIL: return launch_one<EL_L1_TAIL, false, G>(p, stream);
     case EL_L1_HEAD: return launch_one<EL_L1_HEAD, false, G>(p, stream);
     case EL_L2_TAIL: return launch_one<EL_L2_TAIL, false, G>(p, stream);

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -32,19 +33,39 @@ namespace tc {
 
 namespace {
 
-constexpr int BM = TC_BM, BN = TC_BN, BK = TC_BK;
-constexpr int STAGES = 2;
-constexpr int A_PLANE = BM * 128;  // bytes of one 128-row x 64-bf16 swizzled plane
-constexpr int B_PLANE = BN * 128;
-constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // A hi, A lo, B hi, B lo = 96 KB
-constexpr int NORM_FLOATS = 2 * BN;                     // cb[256], cn[256] per buffer
-constexpr int AMB_BUF = 128;                            // near-tie entries buffered per epilogue warp
-constexpr int EPI_WARPS = 8;                            // two per TMEM lane quadrant, half the columns each
+constexpr int BM = TC_BM, BN = TC_BN;
+constexpr int AMB_BUF = 64;          // near-tie entries buffered per epilogue warp
+constexpr int EPI_WARPS = 8;         // two per TMEM lane quadrant, half the columns each
 constexpr int THREADS = (2 + EPI_WARPS) * 32;
 constexpr int TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
-                              2 * NORM_FLOATS * sizeof(float) + 16 * sizeof(uint64_t) + 16 +
-                              EPI_WARPS * AMB_BUF * sizeof(int2);
+constexpr int MAX_STAGES = 4;
+constexpr int BAR_SLOTS = 32;        // full[4] empty[4] tfull[2] tempty[2] a_full[8] a_empty[1] ...
+constexpr size_t SMEM_TAIL = BAR_SLOTS * sizeof(uint64_t) + EPI_WARPS * AMB_BUF * sizeof(int2);
+constexpr size_t SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA on sm_100
+
+// Geometry of one kernel variant: BKT bf16 per k-block (= one swizzle span of 2*BKT bytes);
+// RES = the query tile's whole A image stays resident in shared memory for a unit and only B
+// is streamed (possible when the image is <= 7 k-blocks of 32, i.e. k_total <= 224).
+template <int BKT, bool RES>
+struct Geo {
+  static constexpr int ROWB = 2 * BKT;                 // bytes per operand row in a k-block
+  static constexpr int A_PLANE = BM * ROWB;            // one 128-row (hi or lo) plane
+  static constexpr int B_PLANE = BN * ROWB;
+  static constexpr int A_BLOCK = 2 * A_PLANE;          // hi + lo
+  static constexpr int B_BLOCK = 2 * B_PLANE;
+  static constexpr int STAGE_BYTES = RES ? B_BLOCK : A_BLOCK + B_BLOCK;
+  static constexpr int STAGES = RES ? 3 : (BKT == 64 ? 2 : 4);
+  static constexpr int K16 = BKT / 16;                 // MMA k-steps per block
+  static constexpr uint64_t LAYOUT = BKT == 64 ? 2 : 4;  // SWIZZLE_128B : SWIZZLE_64B
+  static constexpr uint32_t SBO = 8 * ROWB;            // byte stride between 8-row groups
+};
+
+template <int BKT, bool RES>
+size_t smem_bytes(int n_kb) {
+  using G = Geo<BKT, RES>;
+  return 1024 /*align slack*/ + (RES ? (size_t)n_kb * G::A_BLOCK : 0) + (size_t)G::STAGES * G::STAGE_BYTES +
+         SMEM_TAIL;
+}
 
 // -------- PTX helpers specific to tcgen05 --------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -75,16 +96,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start address >> 4 | LBO = 1 (ignored for swizzled K-major) | SBO = 1024 B (8 rows x 128 B)
-// | version 1 (sm_100) | layout type 2 (SWIZZLE_128B).
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address
+// >> 4 | LBO = 1 (ignored for swizzled K-major) | SBO = 8 rows x row bytes | version 1 (sm_100)
+// | layout type (2 = SWIZZLE_128B for 128-byte rows, 4 = SWIZZLE_64B for 64-byte rows).
+template <class G>
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(G::SBO >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= G::LAYOUT << 61;
   return d;
 }
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, K-major both, N = 256, M = 128
@@ -105,51 +127,53 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
-// Work order: a unit = (group of TC_CT_GROUP consecutive candidate tiles, query tile); a CTA
+// Work order: a unit = (group of p.ct_group consecutive candidate tiles, query tile); a CTA
 // takes units round-robin and walks the group's candidate tiles for that query tile.  CTAs
 // running together work on the same group with different query tiles, so the group's B images
 // are served from L2 (B streams from HBM once per launch) and the whole A image (tens of MB)
 // stays L2-resident; per-query counters are flushed once per unit.
 struct Units {
-  long long n_qt, n_ct, n_groups, n_units;
-  __device__ Units(long long nq, long long nc)
-      : n_qt(nq), n_ct(nc), n_groups((nc + TC_CT_GROUP - 1) / TC_CT_GROUP),
-        n_units(nq * ((nc + TC_CT_GROUP - 1) / TC_CT_GROUP)) {}
+  long long n_qt, n_ct, grp, n_units;
+  __device__ Units(long long nq, long long nc, long long g)
+      : n_qt(nq), n_ct(nc), grp(g), n_units(nq * ((nc + g - 1) / g)) {}
   __device__ void decode(long long u, long long* qt, long long* ct_lo, long long* ct_hi) const {
     const long long g = u / n_qt;
     *qt = u - g * n_qt;
-    *ct_lo = g * TC_CT_GROUP;
-    *ct_hi = min(n_ct, *ct_lo + TC_CT_GROUP);
+    *ct_lo = g * grp;
+    *ct_hi = min(n_ct, *ct_lo + grp);
   }
 };
 
-template <bool L2, bool DUMP>
+template <bool L2, bool DUMP, int BKT, bool RES>
 __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_constant__ TcScanParams p) {
+  using G = Geo<BKT, RES>;
+  constexpr int STAGES = G::STAGES;
   extern __shared__ unsigned char smem_raw[];
-  // 1024-B alignment for the 128-byte swizzle atoms
+  // 1024-B alignment for the swizzle atoms
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   unsigned char* smem = smem_raw + ((1024 - (raw_addr & 1023)) & 1023);
-  unsigned char* stage_base = smem;
-  float* s_norm = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_norm + 2 * NORM_FLOATS);
-  uint64_t* full_bar = bars;            // [STAGES]
-  uint64_t* empty_bar = bars + 2;       // [STAGES]
-  uint64_t* tfull_bar = bars + 4;       // [2]
-  uint64_t* tempty_bar = bars + 6;      // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
-  int2* s_amb = reinterpret_cast<int2*>(bars + 10);  // [EPI_WARPS][AMB_BUF]
+  const int n_kb = p.n_kb;
+  unsigned char* a_res = smem;  // [n_kb][hi, lo][128 rows]   (RES only)
+  unsigned char* stage_base = smem + (RES ? (size_t)n_kb * G::A_BLOCK : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + (size_t)STAGES * G::STAGE_BYTES);
+  uint64_t* full_bar = bars;             // [MAX_STAGES]
+  uint64_t* empty_bar = bars + 4;        // [MAX_STAGES]
+  uint64_t* tfull_bar = bars + 8;        // [2]
+  uint64_t* tempty_bar = bars + 10;      // [2]
+  uint64_t* afull_bar = bars + 12;       // [8]  one per resident A k-block
+  uint64_t* aempty_bar = bars + 20;      // [1]  resident A region free again
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 30);
+  int2* s_amb = reinterpret_cast<int2*>(bars + BAR_SLOTS);  // [EPI_WARPS][AMB_BUF]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const Units units(p.n_qt, p.n_ct);
-  const int n_kb = p.n_kb;
+  const Units units(p.n_qt, p.n_ct, p.ct_group);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull_bar[a], 1); ptx::mbar_init(&tempty_bar[a], EPI_WARPS); }
+    for (int k = 0; k < 8; ++k) ptx::mbar_init(&afull_bar[k], 1);
+    ptx::mbar_init(aempty_bar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(s_tmem, TMEM_COLS);
@@ -162,18 +186,30 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
     // ------------------------------ producer ------------------------------
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (long long u = blockIdx.x; u < units.n_units; u += gridDim.x) {
+      uint32_t unit_no = 0;
+      for (long long u = blockIdx.x; u < units.n_units; u += gridDim.x, ++unit_no) {
         long long qt, ct_lo, ct_hi; units.decode(u, &qt, &ct_lo, &ct_hi);
-        const unsigned char* asrc = p.apack + (size_t)qt * n_kb * (2 * A_PLANE);
+        const unsigned char* asrc = p.apack + (size_t)qt * n_kb * G::A_BLOCK;
+        if constexpr (RES) {
+          // the previous unit's MMAs must have finished reading the resident A image
+          if (unit_no > 0) ptx::mbar_wait(aempty_bar, (unit_no - 1) & 1u);
+          for (int kb = 0; kb < n_kb; ++kb) {
+            ptx::mbar_arrive_expect_tx(&afull_bar[kb], G::A_BLOCK);
+            ptx::bulk_g2s(a_res + (size_t)kb * G::A_BLOCK, asrc + (size_t)kb * G::A_BLOCK, G::A_BLOCK,
+                          &afull_bar[kb]);
+          }
+        }
         for (long long ct = ct_lo; ct < ct_hi; ++ct) {
-          const unsigned char* bsrc = p.bpack + (size_t)ct * n_kb * (2 * B_PLANE);
+          const unsigned char* bsrc = p.bpack + (size_t)ct * n_kb * G::B_BLOCK;
           for (int kb = 0; kb < n_kb; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-            unsigned char* sa = stage_base + (size_t)stage * STAGE_BYTES;
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-            ptx::bulk_g2s(sa, asrc + (size_t)kb * (2 * A_PLANE), 2 * A_PLANE, &full_bar[stage]);
-            ptx::bulk_g2s(sa + 2 * A_PLANE, bsrc + (size_t)kb * (2 * B_PLANE), 2 * B_PLANE,
-                          &full_bar[stage]);
+            unsigned char* sa = stage_base + (size_t)stage * G::STAGE_BYTES;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], G::STAGE_BYTES);
+            if constexpr (!RES) {
+              ptx::bulk_g2s(sa, asrc + (size_t)kb * G::A_BLOCK, G::A_BLOCK, &full_bar[stage]);
+              sa += G::A_BLOCK;
+            }
+            ptx::bulk_g2s(sa, bsrc + (size_t)kb * G::B_BLOCK, G::B_BLOCK, &full_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -184,19 +220,25 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (long long u = blockIdx.x; u < units.n_units; u += gridDim.x) {
+      uint32_t unit_no = 0;
+      for (long long u = blockIdx.x; u < units.n_units; u += gridDim.x, ++unit_no) {
        long long qt_, ct_lo, ct_hi; units.decode(u, &qt_, &ct_lo, &ct_hi);
        for (long long ct = ct_lo; ct < ct_hi; ++ct) {
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < n_kb; ++kb) {
+          if constexpr (RES) {
+            if (ct == ct_lo) ptx::mbar_wait(&afull_bar[kb], unit_no & 1u);
+          }
           ptx::mbar_wait(&full_bar[stage], phase);
           fence_after();
-          const uint32_t sa = ptx::smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
-          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_PLANE);
-          const uint64_t b_hi = make_desc(sa + 2 * A_PLANE), b_lo = make_desc(sa + 2 * A_PLANE + B_PLANE);
-          const int k16s = min(BK / 16, (p.k_total - kb * BK + 15) / 16);
+          const uint32_t sb = ptx::smem_u32(stage_base + (size_t)stage * G::STAGE_BYTES);
+          const uint32_t sa = RES ? ptx::smem_u32(a_res + (size_t)kb * G::A_BLOCK) : sb;
+          const uint32_t sbb = RES ? sb : sb + G::A_BLOCK;
+          const uint64_t a_hi = make_desc<G>(sa), a_lo = make_desc<G>(sa + G::A_PLANE);
+          const uint64_t b_hi = make_desc<G>(sbb), b_lo = make_desc<G>(sbb + G::B_PLANE);
+          const int k16s = min(G::K16, (p.k_total - kb * BKT + 15) / 16);
           for (int k = 0; k < k16s; ++k) {
             const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16-B units
             umma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kb | k) ? 1u : 0u);
@@ -209,21 +251,33 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
         umma_commit(&tfull_bar[acc]);  // accumulator complete
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
        }
+       if constexpr (RES) umma_commit(aempty_bar);  // every MMA of the unit has read A
       }
     }
   } else {
     // ------------------------------ epilogue (warps 2..9) ------------------------------
+    // The accumulator holds  f = a.b  (dot models) or  f = a.b - |b|^2/2  (L2: the candidate's
+    // squared norm rides in three spare k slots of the operand images, see pack_operand_kernel),
+    // so a pair is decided by comparing f with two per-thread thresholds -- no per-candidate
+    // loads, no arithmetic per element:
+    //   dot: s~ = f,            u = s~ - s_true = f - st
+    //   L2 : s~ = 2 f - |a|^2,  u = 2 f - (qn + st)
+    //   eps(q, c) <= E(q, cbmax) with cbmax = max bound of the 32 candidates of the block
+    //   (eps is increasing in the candidate's norm bound), hence
+    //   f >  T_hi = (st + E)            [L2: (qn + st + E) / 2]  =>  s(q,c) >  s_true : count
+    //   f <  T_lo = (st - E)            [L2: (qn + st - E) / 2]  =>  s(q,c) <  s_true : skip
+    //   otherwise near-tie: exact recheck.  T_hi is rounded up, T_lo down.
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // query row within the tile
-    const int epi_tid = (warp - 2) * 32 + lane;
     const int col_half = (warp - 2) >> 2;     // which 128 columns of the tile this warp handles
     int acc = 0; uint32_t acc_phase = 0;
     long long cur_qt = -1;
     float st = 0.f, qb = 0.f, qn = 0.f;
     int cnt = 0;
-    int nbuf = 0;
     int2* wbuf = s_amb + (warp - 2) * AMB_BUF;  // this warp's near-tie buffer
     int amb_n = 0;                              // entries in it (warp-uniform)
+    float k1 = 0.f, k0 = 0.f, tbase = 0.f;
+    constexpr float INFL = 1.f + 0x1p-19f;      // covers the fp32 rounding of E's evaluation
     for (long long u = blockIdx.x; u < units.n_units; u += gridDim.x) {
      long long qt, ct_lo, ct_hi; units.decode(u, &qt, &ct_lo, &ct_hi);
      for (long long ct = ct_lo; ct < ct_hi; ++ct) {
@@ -238,51 +292,62 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
         st = vq ? p.s_true[q] : INFINITY;
         qb = vq ? p.qbound[q] : 0.f;
         qn = vq ? p.qnorm2[q] : 0.f;
+        if constexpr (L2) {
+          // E = 2 gamma qb cb + gamma2 (qb + cb)^2 = cb (k1 + gamma2 cb) + k0
+          k1 = 2.f * (p.gamma + p.gamma2) * qb * INFL;
+          k0 = p.gamma2 * qb * qb * INFL;
+          tbase = qn + st;
+        } else {
+          k1 = p.gamma * qb * INFL;   // E = gamma qb cb
+          tbase = st;
+        }
       }
-      // candidate-side vectors of this tile -> shared (double buffered)
-      float* cbs = s_norm + nbuf * NORM_FLOATS;
-      float* cns = cbs + BN;
-      for (int j = epi_tid; j < BN; j += EPI_WARPS * 32) {
-        const long long c = ct * BN + j;
-        cbs[j] = c < p.n_rows ? p.cbound[c] : 0.f;
-        cns[j] = c < p.n_rows ? p.cnorm2[c] : 0.f;
+      // largest candidate norm bound of each of this warp's four 32-column blocks (one coalesced
+      // load + one redux each, issued before waiting for the accumulator)
+      const int c_begin = col_half * (BN / 2);
+      float cbm[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const long long c = ct * BN + c_begin + 32 * b + lane;
+        const float x = c < p.n_rows ? p.cbound[c] : 0.f;
+        cbm[b] = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(x)));  // x >= 0
       }
-      named_bar_sync(1, EPI_WARPS * 32);
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       fence_after();
       const int ncols = (int)min((long long)BN, p.n_rows - ct * BN);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      // per-thread constants of the threshold test  u = s~ - s_true  vs  eps
-      const float g_qb = p.gamma * qb;        // dot: eps = g_qb * cb[c]
-      const float g2_qb = 2.f * g_qb;         // L2 : eps = 2 gamma qb cb + gamma2 (qb + cb)^2
-      const float l2_off = -(qn + st);        // L2 : u = 2 dot + l2_off - cn[c]
-      const int c_begin = col_half * (BN / 2), c_end = min(ncols, c_begin + BN / 2);
-      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      const int c_end = min(ncols, c_begin + BN / 2);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int c0 = c_begin + 32 * b;
+        if (c0 >= c_end) break;
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         const int lim = min(32, ncols - c0);
+        float t_hi, t_lo;
+        {
+          const float cb = cbm[b];
+          float e;
+          if constexpr (L2) e = fmaf(cb, fmaf(p.gamma2 * INFL, cb, k1), k0) * INFL;
+          else e = k1 * cb;
+          t_hi = __fadd_ru(tbase, e);
+          t_lo = __fadd_rd(tbase, -e);
+          if constexpr (L2) { t_hi = __fmul_ru(t_hi, 0.5f); t_lo = __fmul_rd(t_lo, 0.5f); }
+        }
         // 32 independent threshold tests -> two bit masks per thread (no per-element branches)
-        unsigned amb_mask = 0, gt_mask = 0;
+        unsigned ge_mask = 0, gt_mask = 0, amb_mask = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float dot = __uint_as_float(v[j]);
-          float u, e;
-          if constexpr (L2) {
-            u = fmaf(2.f, dot, l2_off) - cns[c0 + j];
-            const float cbj = cbs[c0 + j];
-            const float w = qb + cbj;
-            e = fmaf(g2_qb, cbj, p.gamma2 * w * w);
-          } else {
-            u = dot - st;
-            e = g_qb * cbs[c0 + j];
-          }
+          const float f = __uint_as_float(v[j]);
           if constexpr (DUMP) {
-            if (j < lim && q < p.n_q) p.dump[(size_t)q * p.n_rows + ct * BN + c0 + j] = L2 ? u + st : dot;
+            if (j < lim && q < p.n_q)
+              p.dump[(size_t)q * p.n_rows + ct * BN + c0 + j] = L2 ? fmaf(2.f, f, -qn) : f;
           } else {
-            amb_mask |= (fabsf(u) <= e ? 1u : 0u) << j;
-            gt_mask |= (u > e ? 1u : 0u) << j;
+            gt_mask |= (f > t_hi ? 1u : 0u) << j;
+            ge_mask |= (f >= t_lo ? 1u : 0u) << j;
           }
         }
+        amb_mask = ge_mask & ~gt_mask;
         if constexpr (!DUMP) {
           if (lim < 32) {  // columns past the table (last tile only)
             const unsigned keep = (1u << lim) - 1u;
@@ -291,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
           cnt += __popc(gt_mask);
           if (__any_sync(0xffffffffu, amb_mask != 0)) {
             // near-ties in this 32 x 32 block: warp prefix sum of the per-lane counts, entries
-            // into this warp's shared buffer, one global atomic per ~100 entries on flush
+            // into this warp's shared buffer, one global atomic per ~50 entries on flush
             const int mine = __popc(amb_mask);
             int incl = mine;
 #pragma unroll
@@ -340,7 +405,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
       acc ^= 1; if (acc == 0) acc_phase ^= 1u;
-      nbuf ^= 1;
      }
     }
     if (cur_qt >= 0 && cnt != 0) {
@@ -362,9 +426,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
-// Operand packing: fp32 rows -> (hi, lo) bf16 planes in the shared-memory image of K-major,
-// 128-byte-swizzled tiles.  One thread per (row, 16-byte chunk): 8 consecutive k of one plane.
-//   image offset of (row r, chunk j) inside a plane = (r/8)*1024 + (r%8)*128 + ((j ^ (r%8))*16)
+// Operand packing: fp32 rows -> (hi, lo) bf16 planes in the shared-memory image of K-major
+// swizzled tiles.  One thread per (row, 16-byte chunk): 8 consecutive k of one plane.
+//   128-byte rows (BKT = 64, SWIZZLE_128B): offset of (row r, chunk j) inside a plane =
+//       (r/8)*1024 + (r%8)*128 + ((j ^ (r%8)) * 16)              j = 0..7
+//   64-byte rows  (BKT = 32, SWIZZLE_64B) :
+//       (r/8)*512  + (r%8)*64  + ((j ^ ((r>>1)&3)) * 16)         j = 0..3
+// (the swizzle XORs address bits [4,7) with bits [7,10), resp. bits [4,6) with bits [7,9)).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float operand_value(const float* __restrict__ p0,
                                                const float* __restrict__ p1, int dim, int k,
@@ -373,19 +441,26 @@ __device__ __forceinline__ float operand_value(const float* __restrict__ p0,
   return k < dim ? p0[k] : p1[k - dim];
 }
 
-template <int ROWS>
+template <int ROWS, int BKT>
 __global__ void pack_operand_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
                                     long long row_stride, long long plane1_offset, long long n_rows,
-                                    int dim, int k_total, int n_kb, int sub_mode,
+                                    int dim, int k_total, int n_kb, int sub_mode, int fold,
+                                    const float* __restrict__ norm2,
                                     unsigned char* __restrict__ out) {
   // src0 + row*row_stride = first plane of the row; second plane at +plane1_offset (same row)
   // or in src1 (separate table).  sub_mode = 1: value = plane1[k] - plane0[k]  (t - r, L2 head)
+  // fold (L2 only; k_total = dim + 3): the three k slots after the data carry, on the candidate
+  // side (fold = 2), -|b|^2/2 split exactly into three bf16 pieces (hi plane; lo plane 0) and, on
+  // the query side (fold = 1), 1.0 -- so the hi*hi product adds -|b|^2/2 to every accumulator
+  // and the epilogue compares the accumulator with thresholds directly.
+  constexpr int CH = BKT / 8;        // 16-byte chunks per row
+  constexpr int ROWB = 2 * BKT;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n_tiles = (n_rows + ROWS - 1) / ROWS;
-  const long long total = n_tiles * n_kb * ROWS * 8;
+  const long long total = n_tiles * n_kb * ROWS * CH;
   if (gid >= total) return;
-  const int j = (int)(gid & 7);
-  long long rest = gid >> 3;
+  const int j = (int)(gid % CH);
+  long long rest = gid / CH;
   const int r = (int)(rest % ROWS);
   rest /= ROWS;
   const int kb = (int)(rest % n_kb);
@@ -394,21 +469,40 @@ __global__ void pack_operand_kernel(const float* __restrict__ src0, const float*
   __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int k = kb * BK + j * 8 + e;
+    const int k = kb * BKT + j * 8 + e;
     float x = 0.f;
     if (row < n_rows) {
-      const float* a = src0 + (size_t)row * row_stride;
-      const float* b = src1 ? src1 + (size_t)row * row_stride : a + plane1_offset;
-      if (sub_mode) x = k < dim ? __fsub_rn(b[k], a[k]) : 0.f;
-      else x = operand_value(a, b, dim, k, k_total);
+      if (fold && k >= dim) {
+        if (k < dim + 3) {
+          if (fold == 1) {
+            hi[e] = __float2bfloat16_rn(1.0f);
+          } else {
+            float rest = -0.5f * norm2[row];
+            __nv_bfloat16 piece = __float2bfloat16_rn(rest);
+            for (int i = 0; i < k - dim; ++i) {
+              rest -= __bfloat162float(piece);  // exact: piece holds the leading bits of rest
+              piece = __float2bfloat16_rn(rest);
+            }
+            hi[e] = piece;
+          }
+          lo[e] = __float2bfloat16_rn(0.f);
+          continue;
+        }
+      } else {
+        const float* a = src0 + (size_t)row * row_stride;
+        const float* b = src1 ? src1 + (size_t)row * row_stride : a + plane1_offset;
+        if (sub_mode) x = k < dim ? __fsub_rn(b[k], a[k]) : 0.f;
+        else x = operand_value(a, b, dim, k, k_total);
+      }
     }
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
     hi[e] = h;
     lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
   }
-  const size_t plane = (size_t)ROWS * 128;
+  const size_t plane = (size_t)ROWS * ROWB;
   const size_t base = ((size_t)tile * n_kb + kb) * (2 * plane);
-  const size_t off = (size_t)(r / 8) * 1024 + (size_t)(r % 8) * 128 + (size_t)((j ^ (r % 8)) * 16);
+  const int sw = BKT == 64 ? (r & 7) : ((r >> 1) & 3);
+  const size_t off = (size_t)(r / 8) * (8 * ROWB) + (size_t)(r % 8) * ROWB + (size_t)((j ^ sw) * 16);
   *reinterpret_cast<uint4*>(out + base + off) = *reinterpret_cast<const uint4*>(hi);
   *reinterpret_cast<uint4*>(out + base + plane + off) = *reinterpret_cast<const uint4*>(lo);
 }
@@ -505,65 +599,129 @@ __global__ void tc_stats_kernel(const unsigned long long* __restrict__ region_co
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------
+// Geometry choice.  k-block = 32 bf16 (64-byte swizzle) by default: finer stages, 7 % instead of
+// 23 % padding at k = 200, and the query tile's A image (<= 7 blocks, k_total <= 224) can stay
+// resident in shared memory so that only B streams (1/3 less L2 -> SM traffic, the limiter of
+// the streamed form).  KGE_TC_BK=64 selects the 128-byte-swizzle layout (2 stages of 96 KB),
+// KGE_TC_RESIDENT=0 disables residency, KGE_TC_GROUP sets candidate tiles per unit.
+// ------------------------------------------------------------------------------------------
+namespace {
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+struct Config {
+  int bk, resident, group, max_ctas;
+  Config()
+      : bk(env_int("KGE_TC_BK", 32) == 64 ? 64 : 32), resident(env_int("KGE_TC_RESIDENT", 1) != 0),
+        group(env_int("KGE_TC_GROUP", 0)), max_ctas(env_int("KGE_TC_MAX_CTAS", 0)) {}
+};
+Config& config() {
+  static Config c;
+  return c;
+}
+}  // namespace
+
+void configure(int bk_, int resident_, int group_, int max_ctas_) {
+  Config& c = config();
+  if (bk_ == 32 || bk_ == 64) c.bk = bk_;
+  if (resident_ >= 0) c.resident = resident_ != 0;
+  if (group_ >= 0) c.group = group_;
+  if (max_ctas_ >= 0) c.max_ctas = max_ctas_;
+}
+int bk() { return config().bk; }
+int n_kblocks(int k_total) { return (k_total + bk() - 1) / bk(); }
+bool resident(int n_kb) {
+  return config().resident && bk() == 32 && n_kb <= 7 && smem_bytes<32, true>(n_kb) <= SMEM_LIMIT;
+}
+int ct_group(int n_kb) {
+  if (config().group > 0) return config().group;
+  return resident(n_kb) ? 32 : 16;
+}
+
 size_t a_image_bytes(long long n_q, int n_kb) {
   const long long n_qt = (n_q + BM - 1) / BM;
-  return (size_t)n_qt * n_kb * 2 * A_PLANE;
+  return (size_t)n_qt * n_kb * 2 * BM * 2 * bk();
 }
 size_t b_image_bytes(long long n_rows, int n_kb) {
   const long long n_ct = (n_rows + BN - 1) / BN;
-  return (size_t)n_ct * n_kb * 2 * B_PLANE;
+  return (size_t)n_ct * n_kb * 2 * BN * 2 * bk();
 }
 
 cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows, int dim, int k_total,
-                          int n_kb, unsigned char* bpack, float* cbound, float* cnorm2,
+                          int n_kb, bool fold, unsigned char* bpack, float* cbound, float* cnorm2,
                           cudaStream_t st) {
   if (n_rows <= 0) return cudaSuccess;
   const long long n_ct = (n_rows + BN - 1) / BN;
-  const long long total = n_ct * n_kb * BN * 8;
-  pack_operand_kernel<BN><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      ent0, ent1, dim, 0, n_rows, dim, k_total, n_kb, 0, bpack);
+  const long long total = n_ct * n_kb * BN * (bk() / 8);
+  // norms first: with fold the image carries -|b|^2/2 (the SAME fp32 value the bound uses)
   row_norms_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, st>>>(
-      ent0, ent1, dim, 0, n_rows, dim, k_total, 0, cbound, cnorm2);
+      ent0, ent1, dim, 0, n_rows, dim, fold ? dim : k_total, 0, cbound, cnorm2);
+  const int f = fold ? 2 : 0;
+  if (bk() == 64)
+    pack_operand_kernel<BN, 64><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        ent0, ent1, dim, 0, n_rows, dim, k_total, n_kb, 0, f, cnorm2, bpack);
+  else
+    pack_operand_kernel<BN, 32><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        ent0, ent1, dim, 0, n_rows, dim, k_total, n_kb, 0, f, cnorm2, bpack);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pack_a(const float* qplain, int qw, long long n_q, int dim, int k_total, int n_kb,
-                          int sub_mode, unsigned char* apack, float* qbound, float* qnorm2,
+                          int sub_mode, bool fold, unsigned char* apack, float* qbound, float* qnorm2,
                           cudaStream_t st) {
   if (n_q <= 0) return cudaSuccess;
   const long long n_qt = (n_q + BM - 1) / BM;
-  const long long total = n_qt * n_kb * BM * 8;
+  const long long total = n_qt * n_kb * BM * (bk() / 8);
   // qplain rows are [qw][dim]: plane 1 (if any) follows plane 0 inside the row
-  pack_operand_kernel<BM><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      qplain, nullptr, (long long)qw * dim, dim, n_q, dim, k_total, n_kb, sub_mode, apack);
+  if (bk() == 64)
+    pack_operand_kernel<BM, 64><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        qplain, nullptr, (long long)qw * dim, dim, n_q, dim, k_total, n_kb, sub_mode, fold ? 1 : 0, nullptr, apack);
+  else
+    pack_operand_kernel<BM, 32><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        qplain, nullptr, (long long)qw * dim, dim, n_q, dim, k_total, n_kb, sub_mode, fold ? 1 : 0, nullptr, apack);
   row_norms_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, st>>>(
-      qplain, nullptr, (long long)qw * dim, dim, n_q, dim, k_total, sub_mode, qbound, qnorm2);
+      qplain, nullptr, (long long)qw * dim, dim, n_q, dim, fold ? dim : k_total, sub_mode, qbound, qnorm2);
   return cudaGetLastError();
 }
 
-cudaError_t launch_tc_scan(const TcScanParams& p, cudaStream_t st) {
-  static bool configured = false;
+namespace {
+template <int BKT, bool RES>
+cudaError_t launch_variant(const TcScanParams& p, int grid, cudaStream_t st) {
+  const size_t smem = smem_bytes<BKT, RES>(p.n_kb);
+  if (smem > SMEM_LIMIT) return cudaErrorInvalidValue;
+  static bool configured = false;  // one flag per template instantiation
   if (!configured) {
     cudaError_t e = cudaSuccess;
     auto set = [&](auto kern) {
       if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     };
-    set(tc_scan_kernel<false, false>); set(tc_scan_kernel<true, false>);
-    set(tc_scan_kernel<false, true>); set(tc_scan_kernel<true, true>);
+    set(tc_scan_kernel<false, false, BKT, RES>); set(tc_scan_kernel<true, false, BKT, RES>);
+    set(tc_scan_kernel<false, true, BKT, RES>); set(tc_scan_kernel<true, true, BKT, RES>);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int grid = scan_grid_size(p.n_q, p.n_rows);
-  if (grid <= 0) return cudaSuccess;
   if (p.dump) {
-    if (p.l2) tc_scan_kernel<true, true><<<grid, THREADS, SMEM_BYTES, st>>>(p);
-    else tc_scan_kernel<false, true><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    if (p.l2) tc_scan_kernel<true, true, BKT, RES><<<grid, THREADS, smem, st>>>(p);
+    else tc_scan_kernel<false, true, BKT, RES><<<grid, THREADS, smem, st>>>(p);
   } else {
-    if (p.l2) tc_scan_kernel<true, false><<<grid, THREADS, SMEM_BYTES, st>>>(p);
-    else tc_scan_kernel<false, false><<<grid, THREADS, SMEM_BYTES, st>>>(p);
+    if (p.l2) tc_scan_kernel<true, false, BKT, RES><<<grid, THREADS, smem, st>>>(p);
+    else tc_scan_kernel<false, false, BKT, RES><<<grid, THREADS, smem, st>>>(p);
   }
   return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t launch_tc_scan(const TcScanParams& p_in, cudaStream_t st) {
+  TcScanParams p = p_in;
+  p.ct_group = ct_group(p.n_kb);
+  const int grid = scan_grid_size(p.n_q, p.n_rows, p.n_kb);
+  if (grid <= 0) return cudaSuccess;
+  if (bk() == 64) return launch_variant<64, false>(p, grid, st);
+  if (resident(p.n_kb)) return launch_variant<32, true>(p, grid, st);
+  return launch_variant<32, false>(p, grid, st);
 }
 
 cudaError_t launch_recheck(int el, int dim, const unsigned long long* region_counts, int regions,
@@ -586,12 +744,14 @@ cudaError_t launch_recheck(int el, int dim, const unsigned long long* region_cou
   return cudaGetLastError();
 }
 
-int scan_grid_size(long long n_q, long long n_rows) {
+int scan_grid_size(long long n_q, long long n_rows, int n_kb) {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   const long long n_qt = (n_q + BM - 1) / BM, n_ct = (n_rows + BN - 1) / BN;
-  const long long units = n_qt * ((n_ct + TC_CT_GROUP - 1) / TC_CT_GROUP);
+  const long long g = ct_group(n_kb);
+  const long long units = n_qt * ((n_ct + g - 1) / g);
+  if (config().max_ctas > 0 && config().max_ctas < sms) sms = config().max_ctas;
   return (int)(units < sms ? units : sms);
 }
 

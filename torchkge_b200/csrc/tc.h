@@ -8,12 +8,18 @@ namespace tc {
 
 constexpr int TC_BM = 128;       // queries per MMA tile (TMEM lanes)
 constexpr int TC_BN = 256;       // candidates per MMA tile (TMEM columns, fp32)
-constexpr int TC_BK = 64;        // bf16 per k-block = one 128-byte swizzle span
-constexpr int TC_CT_GROUP = 16;  // candidate tiles a CTA walks per query tile before moving on
+// k-block width (bf16 per swizzle span) is a run-time choice: bk() = 32 (64-byte swizzle,
+// default) or 64 (128-byte swizzle, KGE_TC_BK=64); n_kblocks(k_total) = ceil(k_total / bk()).
+int bk();
+int n_kblocks(int k_total);
+// Tuning / test hook (kge_tc_configure): bk 32|64, resident 0|1, ct_group (0 = automatic),
+// max_ctas (0 = one per SM); negative values keep the current setting.  Operand images packed
+// under one bk must be scanned under the same bk.
+void configure(int bk, int resident, int ct_group, int max_ctas);
 
 struct TcScanParams {
-  const unsigned char* apack;  // [n_qt][n_kb][hi,lo][128 x 128 B swizzled]
-  const unsigned char* bpack;  // [n_ct][n_kb][hi,lo][256 x 128 B swizzled]
+  const unsigned char* apack;  // [n_qt][n_kb][hi,lo][128 rows x 2*bk() B, swizzled]
+  const unsigned char* bpack;  // [n_ct][n_kb][hi,lo][256 rows x 2*bk() B, swizzled]
   const float* s_true;         // [n_q] exact (ATen-order) true scores
   const float* qbound;         // [n_q] >= |a|_2
   const float* qnorm2;         // [n_q] |a|_2^2 (L2 only)
@@ -29,6 +35,7 @@ struct TcScanParams {
   int l2;                      // 1: score = -(|a|^2 + |b|^2 - 2 a.b)
   int n_kb;
   int k_total;
+  int ct_group;                // candidate tiles a CTA walks per query tile (set by launch_tc_scan)
   long long n_q, n_rows, n_qt, n_ct;
 };
 
@@ -52,19 +59,24 @@ inline float tc_gamma(int k_total) {
   const double ref = (k_total + 4.0) * 0x1p-24;
   return (float)(split + accum + ref);
 }
-inline float tc_gamma2(int k_total) { return (float)((k_total + 24.0) * 0x1p-23); }
+// + the three-piece bf16 representation of |b|^2/2 carried in the operand image (2^-24 |b|^2) and
+// the tensor-core accumulation of the (at most 6) MMAs that see it (<= 6 * 2^-21 * |b|^2 / 2).
+inline float tc_gamma2(int k_total) { return (float)((k_total + 42.0) * 0x1p-23); }
 
 size_t a_image_bytes(long long n_q, int n_kb);
 size_t b_image_bytes(long long n_rows, int n_kb);
+// fold = true (L2 models, k_total = dim + 3): the images carry -|b|^2/2 resp. 1.0 in the three k
+// slots after the data, so the accumulator already holds  a.b - |b|^2/2.
 cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows, int dim, int k_total,
-                          int n_kb, unsigned char* bpack, float* cbound, float* cnorm2, cudaStream_t st);
+                          int n_kb, bool fold, unsigned char* bpack, float* cbound, float* cnorm2,
+                          cudaStream_t st);
 cudaError_t launch_pack_a(const float* qplain, int qw, long long n_q, int dim, int k_total, int n_kb,
-                          int sub_mode, unsigned char* apack, float* qbound, float* qnorm2,
+                          int sub_mode, bool fold, unsigned char* apack, float* qbound, float* qnorm2,
                           cudaStream_t st);
 cudaError_t launch_tc_scan(const TcScanParams& p, cudaStream_t st);
 // The near-tie list is split into one region per CTA of the scan (regions = scan_grid_size):
 // region_counts[regions] (zeroed by the caller), pairs[regions][region_cap].
-int scan_grid_size(long long n_q, long long n_rows);
+int scan_grid_size(long long n_q, long long n_rows, int n_kb);
 cudaError_t launch_recheck(int el, int dim, const unsigned long long* region_counts, int regions,
                            unsigned long long region_cap, const int2* pairs, const float* qplain,
                            const float* ent0, const float* ent1, const float* s_true, int32_t* counts,

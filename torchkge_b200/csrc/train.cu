@@ -326,6 +326,265 @@ __global__ void margin_step_bwd_kernel(MarginStepParams a, TrainGrads gr, const 
   if (active) triple_backward(a.model, a.dim, pp, gr, hi, ti, ri, -g * (float)active, lane);
 }
 
+// ------------------------------------------------------------------------------------------
+// Fast fused step for the single-plane normalising models with a closed form per negative
+// (TransE-L1 / TransE-L2 / DistMult), dim % 4 == 0, dim <= 256.
+//
+// One warp per positive triple.  Lane l owns the 16-byte chunks l and l + 32 of every row, so a
+// row is two coalesced LDG.128 per lane (and two float4 atomics on the way back).  The positive's
+// h, t, r rows are read ONCE and kept in registers as
+//     A  = what a tail-corrupted negative is scored against  (DistMult: hn*r,  TransE: hn + r)
+//     Bv = what a head-corrupted negative is scored against  (DistMult: r*tn,  TransE: tn - r)
+// so each negative costs exactly one random row: its squared norm and its product with A / Bv
+// come out of ONE two-value shuffle tree (TransE-L2 expands |P - en|^2 = |P|^2 - 2 P.en + |en|^2).
+// Backward: the corrupted row's gradient is scattered immediately (the only unavoidable
+// read-modify-write, 4*dim bytes per negative); the gradients of the intact entity and of the
+// relation are linear in  V = sum over active negatives of en  (TransE-L1: of sign(P - en)),
+// which stays in registers, so the positive's three rows are written once per positive instead of
+// once per negative (the relation rows are shared by thousands of triples: 256x fewer atomics on
+// the hottest addresses).  Philox draws are made 32 negatives at a time, one per lane.
+// Algorithmic traffic per positive: forward (n_neg + 3) * 4 dim bytes, backward the same rows
+// again (recomputed, not stored) plus one RMW of each.
+// ------------------------------------------------------------------------------------------
+constexpr int FAST_NCH = 2;         // float4 chunks per lane
+constexpr int FAST_MAX_DIM = 4 * 32 * FAST_NCH;
+
+struct Vec { float4 c[FAST_NCH]; };
+
+__device__ __forceinline__ Vec vec_load(const float* __restrict__ row, int dim, int lane) {
+  Vec v;
+#pragma unroll
+  for (int i = 0; i < FAST_NCH; ++i) {
+    const int k = 4 * (lane + 32 * i);
+    v.c[i] = k < dim ? __ldg(reinterpret_cast<const float4*>(row + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  return v;
+}
+__device__ __forceinline__ void vec_atomic_add(float* __restrict__ row, int dim, int lane, const Vec& v) {
+#pragma unroll
+  for (int i = 0; i < FAST_NCH; ++i) {
+    const int k = 4 * (lane + 32 * i);
+    if (k < dim) atomicAdd(reinterpret_cast<float4*>(row + k), v.c[i]);
+  }
+}
+template <class F>
+__device__ __forceinline__ Vec vec_map(const Vec& a, const Vec& b, F f) {
+  Vec o;
+#pragma unroll
+  for (int i = 0; i < FAST_NCH; ++i)
+    o.c[i] = make_float4(f(a.c[i].x, b.c[i].x), f(a.c[i].y, b.c[i].y), f(a.c[i].z, b.c[i].z),
+                         f(a.c[i].w, b.c[i].w));
+  return o;
+}
+template <class F>
+__device__ __forceinline__ Vec vec_map3(const Vec& a, const Vec& b, const Vec& c, F f) {
+  Vec o;
+#pragma unroll
+  for (int i = 0; i < FAST_NCH; ++i)
+    o.c[i] = make_float4(f(a.c[i].x, b.c[i].x, c.c[i].x), f(a.c[i].y, b.c[i].y, c.c[i].y),
+                         f(a.c[i].z, b.c[i].z, c.c[i].z), f(a.c[i].w, b.c[i].w, c.c[i].w));
+  return o;
+}
+__device__ __forceinline__ Vec vec_scale(const Vec& a, float s) {
+  return vec_map(a, a, [s](float x, float) { return x * s; });
+}
+__device__ __forceinline__ float vec_dot(const Vec& a, const Vec& b) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < FAST_NCH; ++i) {
+    s = fmaf(a.c[i].x, b.c[i].x, s); s = fmaf(a.c[i].y, b.c[i].y, s);
+    s = fmaf(a.c[i].z, b.c[i].z, s); s = fmaf(a.c[i].w, b.c[i].w, s);
+  }
+  return s;
+}
+__device__ __forceinline__ float vec_l1_diff(const Vec& a, const Vec& b) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < FAST_NCH; ++i)
+    s += fabsf(a.c[i].x - b.c[i].x) + fabsf(a.c[i].y - b.c[i].y) + fabsf(a.c[i].z - b.c[i].z) +
+         fabsf(a.c[i].w - b.c[i].w);
+  return s;
+}
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+__device__ __forceinline__ float sgn(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+
+template <int MODEL, bool BWD>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+margin_step_fast_kernel(MarginStepParams a, TrainGrads gr, const float* __restrict__ gloss) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= a.b) return;
+  const int dim = a.dim;
+  const float* __restrict__ ent = a.tb.ent0;
+  const long long hi = a.h[w], ti = a.t[w], ri = a.r[w];
+  const Vec h = vec_load(ent + (size_t)hi * dim, dim, lane);
+  const Vec t = vec_load(ent + (size_t)ti * dim, dim, lane);
+  const Vec r = vec_load(a.tb.rel0 + (size_t)ri * dim, dim, lane);
+  float sh = vec_dot(h, h), stt = vec_dot(t, t);
+  warp_sum2(sh, stt);
+  const float inv_h = 1.0f / fmaxf(sqrtf(sh), NORM_EPS), inv_t = 1.0f / fmaxf(sqrtf(stt), NORM_EPS);
+  const Vec hn = vec_scale(h, inv_h), tn = vec_scale(t, inv_t);
+  Vec A, Bv;
+  if constexpr (MODEL == KGE_DISTMULT) {
+    A = vec_map(hn, r, [](float x, float y) { return x * y; });
+    Bv = vec_map(r, tn, [](float x, float y) { return x * y; });
+  } else {
+    A = vec_map(hn, r, [](float x, float y) { return x + y; });
+    Bv = vec_map(tn, r, [](float x, float y) { return x - y; });
+  }
+  float sA = 0.f, sB = 0.f, pos;
+  if constexpr (MODEL == KGE_DISTMULT) {
+    pos = warp_sum(vec_dot(A, tn));
+  } else if constexpr (MODEL == KGE_TRANSE_L2) {
+    sA = vec_dot(A, A); sB = vec_dot(Bv, Bv);
+    warp_sum2(sA, sB);
+    const Vec x = vec_map(A, tn, [](float p, float q) { return p - q; });
+    pos = -warp_sum(vec_dot(x, x));
+  } else {
+    pos = -warp_sum(vec_l1_diff(A, tn));
+  }
+  if (lane == 0 && a.pos_out && !BWD) a.pos_out[w] = pos;
+  const float p_head = a.nh ? 0.f : a.probs[ri];
+  const float g = BWD ? *gloss : 0.f;
+  float loss = 0.f;
+  Vec Vt, Vh;  // sums over the active tail- / head-corrupted negatives (BWD only)
+#pragma unroll
+  for (int i = 0; i < FAST_NCH; ++i) Vt.c[i] = Vh.c[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int n_t = 0, n_h = 0;  // active negatives per kind
+  for (int j0 = 0; j0 < a.n_neg; j0 += 32) {
+    // this lane's draw for negative j0 + lane
+    long long my_nh = hi, my_nt = ti;
+    if (j0 + lane < a.n_neg) {
+      const long long idx = (long long)(j0 + lane) * a.b + w;
+      if (a.nh) { my_nh = a.nh[idx]; my_nt = a.nt[idx]; }
+      else corrupt_one(a.seed, a.offset, (uint64_t)idx, p_head, a.n_ent, hi, ti, &my_nh, &my_nt);
+      if (!BWD && a.nh_out) { a.nh_out[idx] = my_nh; a.nt_out[idx] = my_nt; }
+    }
+    const int jn = min(32, a.n_neg - j0);
+#pragma unroll 2
+    for (int jj = 0; jj < jn; ++jj) {
+      const long long nh = __shfl_sync(0xffffffffu, my_nh, jj), nt = __shfl_sync(0xffffffffu, my_nt, jj);
+      const long long idx = (long long)(j0 + jj) * a.b + w;
+      if (nh != hi && nt != ti) {
+        // both ends replaced (possible with caller-supplied negatives only): generic path
+        const RowPtrs pn = make_rows(MODEL, dim, a.tb, nh, nt, ri);
+        const float neg = triple_score(MODEL, dim, pn, lane, nullptr, nullptr);
+        const float v = a.margin - pos + neg;
+        if (lane == 0) {
+          if (!BWD && a.neg_out) a.neg_out[idx] = neg;
+          loss += fmaxf(0.f, v);
+        }
+        if (BWD && v > 0.f) {
+          triple_backward(MODEL, dim, pn, gr, nh, nt, ri, g, lane);
+          const RowPtrs pp = make_rows(MODEL, dim, a.tb, hi, ti, ri);
+          triple_backward(MODEL, dim, pp, gr, hi, ti, ri, -g, lane);
+        }
+        continue;
+      }
+      const bool head = nh != hi;            // warp-uniform
+      const long long e = head ? nh : nt;
+      const Vec ev = vec_load(ent + (size_t)e * dim, dim, lane);
+      const Vec& P = head ? Bv : A;
+      float se = vec_dot(ev, ev), sp = vec_dot(ev, P);
+      warp_sum2(se, sp);
+      const float inv_e = 1.0f / fmaxf(sqrtf(se), NORM_EPS);
+      float neg, en_dot_G = 0.f;  // en . (d neg / d en), needed by the normalisation Jacobian
+      Vec en;
+      if constexpr (MODEL == KGE_DISTMULT) {
+        neg = sp * inv_e;
+        en_dot_G = neg;
+      } else if constexpr (MODEL == KGE_TRANSE_L2) {
+        const float sP = head ? sB : sA;
+        const float ee = inv_e * inv_e * se, pe = inv_e * sp;
+        neg = -(sP - 2.f * pe + ee);
+        en_dot_G = 2.f * (pe - ee);
+      } else {
+        en = vec_scale(ev, inv_e);
+        float l1 = vec_l1_diff(P, en), eg = 0.f;
+        if (BWD) {
+          const Vec sg = vec_map(P, en, [](float p, float q) { return sgn(p - q); });
+          eg = vec_dot(en, sg);
+        }
+        warp_sum2(l1, eg);
+        neg = -l1;
+        en_dot_G = eg;
+      }
+      const float v = a.margin - pos + neg;
+      if (lane == 0) {
+        if (!BWD && a.neg_out) a.neg_out[idx] = neg;
+        loss += fmaxf(0.f, v);
+      }
+      if (BWD && v > 0.f) {  // same sub-gradient as torch: zero at the kink
+        if constexpr (MODEL != KGE_TRANSE_L1) en = vec_scale(ev, inv_e);
+        // G = d neg / d en ; d neg / d e = (G - en (en . G)) * inv_e
+        Vec ge, V;
+        const float c = g * inv_e;
+        if constexpr (MODEL == KGE_DISTMULT) {
+          ge = vec_map(P, en, [=](float p, float q) { return c * (p - q * en_dot_G); });
+          V = en;
+        } else if constexpr (MODEL == KGE_TRANSE_L2) {
+          ge = vec_map(P, en, [=](float p, float q) { return c * (2.f * (p - q) - q * en_dot_G); });
+          V = en;
+        } else {
+          V = vec_map(P, en, [](float p, float q) { return sgn(p - q); });
+          ge = vec_map(V, en, [=](float s_, float q) { return c * (s_ - q * en_dot_G); });
+        }
+        vec_atomic_add(gr.ent0 + (size_t)e * dim, dim, lane, ge);
+        if (head) { Vh = vec_map(Vh, V, [](float x, float y) { return x + y; }); ++n_h; }
+        else { Vt = vec_map(Vt, V, [](float x, float y) { return x + y; }); ++n_t; }
+      }
+    }
+  }
+  if (!BWD) {
+    if (lane == 0) atomicAdd(a.loss, loss);
+    return;
+  }
+  if (n_t + n_h == 0) return;
+  // Gradients with respect to hn, tn, r: +g per active negative, -g * (n_t + n_h) for the positive.
+  const float fn_t = (float)n_t, fn_h = (float)n_h, fn = (float)(n_t + n_h);
+  Vec Gh, Gt, Gr;
+  if constexpr (MODEL == KGE_DISTMULT) {
+    // neg_t = sum A en, A = hn r ;  neg_h = sum en Bv, Bv = r tn ;  pos = sum hn r tn
+    Gh = vec_map3(r, Vt, tn, [=](float rr, float vt, float tt) { return g * rr * (vt - fn * tt); });
+    Gt = vec_map3(r, Vh, hn, [=](float rr, float vh, float hh) { return g * rr * (vh - fn * hh); });
+    const Vec tmp = vec_map3(hn, Vt, tn, [=](float hh, float vt, float tt) { return hh * (vt - fn * tt); });
+    Gr = vec_map3(tmp, tn, Vh, [=](float x, float tt, float vh) { return g * (x + tt * vh); });
+  } else if constexpr (MODEL == KGE_TRANSE_L2) {
+    // neg_t = -|A - en|^2 ; neg_h = -|en - Bv|^2 ; pos = -|x|^2, x = A - tn
+    const Vec x = vec_map(A, tn, [](float p, float q) { return p - q; });
+    const Vec dt = vec_map3(A, Vt, x, [=](float aa, float vt, float xx) {  // sum_t (A - en) - n x
+      return fn_t * aa - vt - fn * xx; });
+    const Vec dh = vec_map(Vh, Bv, [=](float vh, float bb) { return vh - fn_h * bb; });  // sum_h (en - Bv)
+    Gh = vec_scale(dt, -2.f * g);
+    Gt = vec_map3(dh, x, x, [=](float d, float xx, float) { return 2.f * g * (d - fn * xx); });
+    Gr = vec_map(dt, dh, [=](float p, float q) { return -2.f * g * (p + q); });
+  } else {
+    // neg_t = -|A - en|_1 (V = sign(A - en)) ; neg_h = -|Bv - en|_1 (V = sign(Bv - en)) ; pos = -|x|_1
+    const Vec sx = vec_map(A, tn, [](float p, float q) { return sgn(p - q); });
+    Gh = vec_map(Vt, sx, [=](float vt, float s_) { return g * (fn * s_ - vt); });
+    Gt = vec_map(Vh, sx, [=](float vh, float s_) { return g * (-vh - fn * s_); });
+    Gr = vec_map3(Vt, Vh, sx, [=](float vt, float vh, float s_) { return g * (vh - vt + fn * s_); });
+  }
+  float ph = vec_dot(hn, Gh), pt = vec_dot(tn, Gt);
+  warp_sum2(ph, pt);
+  const Vec gh = vec_map(Gh, hn, [=](float gg, float q) { return (gg - q * ph) * inv_h; });
+  const Vec gt = vec_map(Gt, tn, [=](float gg, float q) { return (gg - q * pt) * inv_t; });
+  vec_atomic_add(gr.ent0 + (size_t)hi * dim, dim, lane, gh);
+  vec_atomic_add(gr.ent0 + (size_t)ti * dim, dim, lane, gt);
+  vec_atomic_add(gr.rel0 + (size_t)ri * dim, dim, lane, Gr);
+}
+
+__host__ inline bool fast_step_ok(const MarginStepParams& a) {
+  return (a.model == KGE_TRANSE_L1 || a.model == KGE_TRANSE_L2 || a.model == KGE_DISTMULT) &&
+         a.dim % 4 == 0 && a.dim <= FAST_MAX_DIM;
+}
+
 __global__ void margin_loss_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ neg,
                                        long long n, float margin, float* __restrict__ loss) {
   float s = 0.f;
@@ -344,6 +603,45 @@ __global__ void margin_loss_bwd_kernel(const float* __restrict__ pos, const floa
   const float g = (margin - pos[i] + neg[i] > 0.f) ? *gloss : 0.f;
   gpos[i] = -g;
   gneg[i] = g;
+}
+
+// LogisticLoss / BinaryCrossEntropyLoss (utils/losses.py:47-112), sum-reduced.
+//   logistic: softplus(-pos) + softplus(neg), softplus(x) = max(x, 0) + log1p(exp(-|x|))
+//   bce     : -max(log(sig(pos)), -100) - max(log(1 - sig(neg)), -100), sig in fp32 as torch does
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void pair_loss_fwd_kernel(int kind, const float* __restrict__ pos, const float* __restrict__ neg,
+                                     long long n, float* __restrict__ loss) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (kind == KGE_LOSS_LOGISTIC) {
+      s += softplus_f(-pos[i]) + softplus_f(neg[i]);
+    } else {
+      const float pp = sigmoid_f(pos[i]), pn = sigmoid_f(neg[i]);
+      s += -fmaxf(logf(pp), -100.f) - fmaxf(logf(1.0f - pn), -100.f);
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(loss, s);
+}
+
+__global__ void pair_loss_bwd_kernel(int kind, const float* __restrict__ pos, const float* __restrict__ neg,
+                                     long long n, const float* __restrict__ gloss,
+                                     float* __restrict__ gpos, float* __restrict__ gneg) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float g = *gloss;
+  const float pp = sigmoid_f(pos[i]), pn = sigmoid_f(neg[i]);
+  if (kind == KGE_LOSS_LOGISTIC) {
+    gpos[i] = g * (pp - 1.0f);   // d/dx log(1 + exp(-x)) = -sig(-x) = sig(x) - 1
+    gneg[i] = g * pn;            // d/dx log(1 + exp(x))  = sig(x)
+  } else {
+    // torch's BCELoss backward: (p - y) / max(p (1 - p), 1e-12), chained with dp/dx = p (1 - p)
+    gpos[i] = g * (pp - 1.0f) / fmaxf(pp * (1.0f - pp), 1e-12f) * (pp * (1.0f - pp));
+    gneg[i] = g * pn / fmaxf(pn * (1.0f - pn), 1e-12f) * (pn * (1.0f - pn));
+  }
 }
 
 inline unsigned blocks_for_warps(long long warps) {
@@ -382,6 +680,16 @@ cudaError_t launch_corrupt_batch(const int64_t* h, const int64_t* t, const int64
 
 cudaError_t launch_margin_step_fwd(const MarginStepParams& a, cudaStream_t st) {
   if (a.b <= 0) return cudaSuccess;
+  if (fast_step_ok(a)) {
+    const TrainGrads none{nullptr, nullptr, nullptr, nullptr};
+    const unsigned blocks = blocks_for_warps(a.b);
+    switch (a.model) {
+      case KGE_TRANSE_L1: margin_step_fast_kernel<KGE_TRANSE_L1, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(a, none, nullptr); break;
+      case KGE_TRANSE_L2: margin_step_fast_kernel<KGE_TRANSE_L2, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(a, none, nullptr); break;
+      default: margin_step_fast_kernel<KGE_DISTMULT, false><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(a, none, nullptr); break;
+    }
+    return cudaGetLastError();
+  }
   margin_step_fwd_kernel<<<blocks_for_warps(a.b), WARPS_PER_BLOCK * 32, 0, st>>>(a);
   return cudaGetLastError();
 }
@@ -389,6 +697,15 @@ cudaError_t launch_margin_step_fwd(const MarginStepParams& a, cudaStream_t st) {
 cudaError_t launch_margin_step_bwd(const MarginStepParams& a, const TrainGrads& gr, const float* gloss,
                                    cudaStream_t st) {
   if (a.b <= 0) return cudaSuccess;
+  if (fast_step_ok(a)) {
+    const unsigned blocks = blocks_for_warps(a.b);
+    switch (a.model) {
+      case KGE_TRANSE_L1: margin_step_fast_kernel<KGE_TRANSE_L1, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(a, gr, gloss); break;
+      case KGE_TRANSE_L2: margin_step_fast_kernel<KGE_TRANSE_L2, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(a, gr, gloss); break;
+      default: margin_step_fast_kernel<KGE_DISTMULT, true><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(a, gr, gloss); break;
+    }
+    return cudaGetLastError();
+  }
   margin_step_bwd_kernel<<<blocks_for_warps(a.b), WARPS_PER_BLOCK * 32, 0, st>>>(a, gr, gloss);
   return cudaGetLastError();
 }
@@ -398,6 +715,21 @@ cudaError_t launch_margin_loss_fwd(const float* pos, const float* neg, int64_t n
   if (n <= 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
   margin_loss_fwd_kernel<<<blocks, 256, 0, st>>>(pos, neg, n, margin, loss);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pair_loss_fwd(int kind, const float* pos, const float* neg, int64_t n, float* loss,
+                                 cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  pair_loss_fwd_kernel<<<blocks, 256, 0, st>>>(kind, pos, neg, n, loss);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pair_loss_bwd(int kind, const float* pos, const float* neg, int64_t n,
+                                 const float* gloss, float* gpos, float* gneg, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  pair_loss_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kind, pos, neg, n, gloss, gpos, gneg);
   return cudaGetLastError();
 }
 

@@ -56,6 +56,10 @@ cudaError_t launch_margin_step_bwd(const MarginStepParams& a, const TrainGrads& 
                                    cudaStream_t st);
 cudaError_t launch_margin_loss_fwd(const float* pos, const float* neg, int64_t n, float margin,
                                    float* loss, cudaStream_t st);
+cudaError_t launch_pair_loss_fwd(int kind, const float* pos, const float* neg, int64_t n, float* loss,
+                                 cudaStream_t st);
+cudaError_t launch_pair_loss_bwd(int kind, const float* pos, const float* neg, int64_t n,
+                                 const float* gloss, float* gpos, float* gneg, cudaStream_t st);
 cudaError_t launch_margin_loss_bwd(const float* pos, const float* neg, int64_t n, float margin,
                                    const float* gloss, float* gpos, float* gneg, cudaStream_t st);
 

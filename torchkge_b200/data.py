@@ -131,6 +131,21 @@ class KnowledgeGraph:
     def dict_of_tails(self):
         return self._dicts()[1]
 
+    @property
+    def dict_of_rels(self):
+        """(h, t) -> set of relations, as ``evaluate_dicts`` builds it (data_structures.py:386-397);
+        built from this graph's own facts on first use unless ``dict_of_rels`` was assigned."""
+        if getattr(self, "_dict_of_rels", None) is None:
+            d = defaultdict(set)
+            for h, t, r in zip(self.head_idx.tolist(), self.tail_idx.tolist(), self.relations.tolist()):
+                d[(h, t)].add(r)
+            self._dict_of_rels = d
+        return self._dict_of_rels
+
+    @dict_of_rels.setter
+    def dict_of_rels(self, value):
+        self._dict_of_rels = value
+
     def __len__(self):
         return self.n_facts
 

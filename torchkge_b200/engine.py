@@ -117,6 +117,27 @@ class CudaEngine:
         #: use the tcgen05 bound-and-refine scan for models that have one (ranks unchanged)
         self.tensor_core = bool(tensor_core)
         self.tc_stats = []  # (device tensor [found, capacity]) per tensor-core call, for checks
+        #: KGE_TRACE=1: rank_link_prediction appends (label, host seconds, CUDA event) marks here
+        self.trace = [] if os.environ.get("KGE_TRACE") else None
+
+    def mark(self, label):
+        """Debug aid (KGE_TRACE=1): a host timestamp and a CUDA event on the current stream."""
+        if self.trace is None:
+            return
+        import time
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.trace.append((label, time.perf_counter(), ev))
+
+    def trace_report(self):
+        """[(label, host ms since first mark, device ms since first mark)] of the recorded marks."""
+        if not self.trace:
+            return []
+        torch.cuda.synchronize()
+        l0, t0, e0 = self.trace[0]
+        out = [(lab, 1e3 * (t - t0), e0.elapsed_time(ev)) for lab, t, ev in self.trace]
+        self.trace = []
+        return out
 
     # ---- table packing: once per evaluate() ----
     def pack(self, spec):
@@ -155,7 +176,8 @@ class CudaEngine:
         return out
 
     def rank_side(self, spec, packed, side, hrows, trows, r_idx, true_idx, filt, raw_count,
-                  filt_sub, true_score=None, tc_packed=None, tc_dump=None):
+                  filt_sub, true_score=None, tc_packed=None, tc_dump=None, true_rows=None,
+                  true_score_in=None):
         """Adds this shard's counts for one side into raw_count / filt_sub (int32, device)."""
         n = r_idx.shape[0] if r_idx is not None else hrows.shape[0]
         dev = raw_count.device
@@ -177,11 +199,13 @@ class CudaEngine:
             offs, ids = filt
             a.filt_offs, a.filt_ids, a.n_filt = _ptr(offs), _ptr(ids), ids.shape[0]
         a.raw_count, a.filt_sub, a.true_score = _ptr(raw_count), _ptr(filt_sub), _ptr(true_score)
+        a.true_rows, a.true_score_in = _ptr(true_rows), _ptr(true_score_in)
         a.workspace, a.workspace_bytes, a.stream = _ptr(ws), ws_bytes, _stream(dev)
         _lib.check(self.lib.kge_rank_side(ctypes.byref(a)), "kge_rank_side")
         # prep, pack_queries, pad fill, true scores, scan (+ filter)
         self.launches += 5 + (1 if filt is not None and filt[1].shape[0] > 0 else 0)
-        return (a, ws, packed, hrows, trows, tc_packed, stats)  # handle for filter_side; keeps buffers alive
+        # handle for filter_side; keeps buffers alive
+        return (a, ws, packed, hrows, trows, tc_packed, stats, true_rows, true_score_in)
 
     def filter_side(self, handle, filt, filt_sub):
         """Sparse filter pass for a side whose dense scan was enqueued earlier by rank_side
@@ -288,9 +312,13 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
         if (spec.ent_lo, spec.n_rows) != (shard.lo, shard.hi - shard.lo):
             spec = spec.narrowed(shard.lo, shard.hi)
             packed = None
+    mark = getattr(engine, "mark", lambda label: None)
+    mark("step begin")
     if packed is None:
         packed = engine.pack(spec)
+    mark("pack")
     tc_packed = engine.pack_tc(spec) if hasattr(engine, "pack_tc") else None
+    mark("pack_tc")
     dev = spec.ent0.device
     counters = torch.zeros((4, n), dtype=torch.int32, device=dev)  # raw_t, sub_t, raw_h, sub_h
     pending = []
@@ -312,6 +340,7 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
                 handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
                                           raw[lo:hi], sub[lo:hi])
             pending.append((handle, which, lo, hi, sub, side, (hrows, trows, r, true_idx)))
+            mark("rank_side %d enqueued" % side)
     filts = [filt_tail, filt_head]
     for k in (0, 1):
         if callable(filts[k]):
@@ -319,6 +348,7 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
     for handle, which, lo, hi, sub, side, inputs in pending:
         if filts[which] is not None:
             engine.filter_side(handle, _csr_slice(filts[which], lo, hi, n), sub[lo:hi])
+    mark("filters enqueued")
     if tc_packed is not None:
         # the near-tie list of a tensor-core call is bounded; on overflow (never seen on real
         # or synthetic embeddings, possible on adversarial ones) redo that side exactly
@@ -334,6 +364,61 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
     del pending
     if shard is not None and shard.world > 1:
         shard.all_reduce_sum(counters)  # the single collective on the rank counters
+    mark("overflow check (host sync)")
     rank_t, filt_t = engine.finalize(counters[0], counters[1])
     rank_h, filt_h = engine.finalize(counters[2], counters[3])
+    mark("finalize")
     return rank_h, rank_t, filt_h, filt_t
+
+
+def relation_spec(spec):
+    """The model seen from relation prediction: the candidate table is the RELATION table
+    (``inference_prepare_candidates(..., entities=False)``: translation.py:118-121,
+    bilinear.py:263-265, 551-554)."""
+    if spec.code in (_lib.TRANSE_L1, _lib.TRANSE_L2, _lib.DISTMULT):
+        cand0, cand1 = spec.rel0, None
+    elif spec.code == _lib.COMPLEX:
+        cand0, cand1 = spec.rel0, spec.rel1
+    else:
+        raise NotImplementedError(
+            "%s has no CUDA relation-prediction path (supported: TransE L1/L2, DistMult, ComplEx)"
+            % _lib.MODEL_NAMES.get(spec.code, spec.code))
+    return ModelSpec(spec.code, spec.dim, spec.n_rel, spec.n_rel, cand0, cand1, None, None)
+
+
+def rank_relation_prediction(spec, h_idx, t_idx, r_idx, filt, directed=True, engine=None,
+                             chunk=DEFAULT_CHUNK):
+    """Rank every fact's true relation against all relations (RelationPredictionEvaluator,
+    torchkge/evaluation.py:64-112).
+
+    filt       device CSR (offs, ids) of the relations to discount per fact (dict_of_rels[(h, t)]
+               minus the true one), or None
+    directed   False: the scores of (t, ?, h) are ranked together with those of (h, ?, t), against
+               the directed true score (evaluation.py:99-107)
+    Returns (rank_true_rels, filt_rank_true_rels), int64 device tensors.
+    """
+    engine = engine or default_engine()
+    rspec = relation_spec(spec)
+    n = h_idx.shape[0]
+    dev = spec.ent0.device
+    packed = engine.pack(rspec)
+    counters = torch.zeros((2, n), dtype=torch.int32, device=dev)
+    keep = []
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        h, t, r = h_idx[lo:hi], t_idx[lo:hi], r_idx[lo:hi]
+        hrows, trows = engine.gather_rows(spec, h), engine.gather_rows(spec, t)
+        rrows = engine.gather_rows(rspec, r)
+        f = None if filt is None else _csr_slice(filt, lo, hi, n)
+        s_true = torch.empty(hi - lo, dtype=torch.float32, device=dev)
+        keep.append(engine.rank_side(rspec, packed, _lib.SIDE_REL, hrows, trows, None, r, f,
+                                     counters[0][lo:hi], counters[1][lo:hi], true_score=s_true,
+                                     true_rows=rrows))
+        if not directed:
+            keep.append(engine.rank_side(rspec, packed, _lib.SIDE_REL, trows, hrows, None, r, f,
+                                         counters[0][lo:hi], counters[1][lo:hi], true_rows=rrows,
+                                         true_score_in=s_true))
+        keep.append((s_true, f))
+    ranks, filt_ranks = engine.finalize(counters[0], counters[1])
+    del keep
+    return ranks, filt_ranks

@@ -7,7 +7,8 @@ import torch
 
 from . import _lib
 from .data import filter_csr
-from .engine import DEFAULT_CHUNK, ModelSpec, default_engine, rank_link_prediction
+from .engine import (DEFAULT_CHUNK, ModelSpec, default_engine, rank_link_prediction,
+                     rank_relation_prediction)
 from .exceptions import NotYetEvaluatedError
 
 
@@ -150,6 +151,90 @@ class LinkPredictionEvaluator(object):
             print('Hit@{} : {} \t\t Filt. Hit@{} : {}'.format(
                 i, round(self.hit_at_k(k=i)[0], n_digits),
                 i, round(self.hit_at_k(k=i)[1], n_digits)))
+        print('Mean Rank : {} \t Filt. Mean Rank : {}'.format(
+            int(self.mean_rank()[0]), int(self.mean_rank()[1])))
+        print('MRR : {} \t\t Filt. MRR : {}'.format(
+            round(self.mrr()[0], n_digits), round(self.mrr()[1], n_digits)))
+
+
+class RelationPredictionEvaluator(object):
+    """Evaluate an embedding model by relation prediction (torchkge/evaluation.py:16-204): every
+    fact's true relation is ranked against all relations, raw and filtered by
+    ``knowledge_graph.dict_of_rels``.
+
+    Parameters
+    ----------
+    model: TransE (L1/L2), DistMult or ComplEx model on a CUDA device.
+    knowledge_graph: object exposing ``n_facts, head_idx, tail_idx, relations, dict_of_rels``.
+    directed: bool (default True).  False: both (h, ?, t) and (t, ?, h) are scored and ranked
+        together against the directed true score (evaluation.py:99-107).
+
+    Attributes: ``rank_true_rels``, ``filt_rank_true_rels`` (LongTensor (n_facts,), CPU after
+    ``evaluate``), ``evaluated``, ``directed``.
+    """
+
+    def __init__(self, model, knowledge_graph, directed=True):
+        self.model = model
+        self.kg = knowledge_graph
+        self.directed = directed
+        self.rank_true_rels = torch.empty(size=(knowledge_graph.n_facts,)).long()
+        self.filt_rank_true_rels = torch.empty(size=(knowledge_graph.n_facts,)).long()
+        self.evaluated = False
+
+    def evaluate(self, b_size, verbose=True):
+        """``b_size`` / ``verbose`` are accepted for signature compatibility (see
+        ``LinkPredictionEvaluator.evaluate``)."""
+        if b_size is None or int(b_size) < 1:
+            raise ValueError("b_size must be a positive integer")
+        spec = ModelSpec.from_model(self.model)
+        if not spec.ent0.is_cuda:
+            raise _lib.KgeLibraryError(
+                "RelationPredictionEvaluator.evaluate needs the model on a CUDA device "
+                "(model.cuda()); this package has no CPU execution path")
+        dev = spec.ent0.device
+        kg = self.kg
+        h_d, t_d, r_d = (x.to(dev, non_blocking=True) for x in (kg.head_idx, kg.tail_idx, kg.relations))
+        csr = filter_csr(kg.dict_of_rels, kg.head_idx, kg.tail_idx, kg.relations)
+        csr = tuple(x.to(dev, non_blocking=True) for x in csr)
+        rr, frr = rank_relation_prediction(spec, h_d, t_d, r_d, csr, directed=self.directed,
+                                           engine=default_engine(), chunk=DEFAULT_CHUNK)
+        self.rank_true_rels = rr.cpu()
+        self.filt_rank_true_rels = frr.cpu()
+        self.evaluated = True
+
+    def _check(self):
+        if not self.evaluated:
+            raise NotYetEvaluatedError('Evaluator not evaluated call '
+                                       'LinkPredictionEvaluator.evaluate')
+
+    def mean_rank(self):
+        """(mean rank, filtered mean rank) of the true relation (evaluation.py:114-131)."""
+        self._check()
+        return self.rank_true_rels.float().mean().item(), self.filt_rank_true_rels.float().mean().item()
+
+    def hit_at_k(self, k=10):
+        """(Hit@k, filtered Hit@k) (evaluation.py:133-154)."""
+        self._check()
+        return ((self.rank_true_rels <= k).float().mean().item(),
+                (self.filt_rank_true_rels <= k).float().mean().item())
+
+    def mrr(self):
+        """(MRR, filtered MRR) (evaluation.py:156-174)."""
+        self._check()
+        return ((self.rank_true_rels.float() ** (-1)).mean().item(),
+                (self.filt_rank_true_rels.float() ** (-1)).mean().item())
+
+    def print_results(self, k=None, n_digits=3):
+        """Same report as the reference (evaluation.py:176-204)."""
+        if k is None:
+            k = 10
+        if k is not None and type(k) == int:
+            print('Hit@{} : {} \t\t Filt. Hit@{} : {}'.format(
+                k, round(self.hit_at_k(k=k)[0], n_digits), k, round(self.hit_at_k(k=k)[1], n_digits)))
+        if k is not None and type(k) == list:
+            for i in k:
+                print('Hit@{} : {} \t\t Filt. Hit@{} : {}'.format(
+                    i, round(self.hit_at_k(k=i)[0], n_digits), i, round(self.hit_at_k(k=i)[1], n_digits)))
         print('Mean Rank : {} \t Filt. Mean Rank : {}'.format(
             int(self.mean_rank()[0]), int(self.mean_rank()[1])))
         print('MRR : {} \t\t Filt. MRR : {}'.format(

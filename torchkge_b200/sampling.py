@@ -58,6 +58,39 @@ class NegativeSampler:
         return torch.cat(nh).long().cpu(), torch.cat(nt).long().cpu()
 
 
+class UniformNegativeSampler(NegativeSampler):
+    """Uniform negative sampler (Bordes et al. 2013), torchkge/sampling.py:141-223: head or tail
+    with probability 1/2 each, replacement uniform on [1, n_ent) (entity 0 is never drawn, true
+    triples are not rejected -- as in the reference).  Same counter-based generator as
+    ``BernoulliNegativeSampler``; ``seed`` is an extension."""
+
+    def __init__(self, kg, kg_val=None, kg_test=None, n_neg=1, seed=None):
+        super().__init__(kg, kg_val, kg_test, n_neg)
+        self.seed = int(torch.initial_seed() if seed is None else seed) & 0xFFFFFFFFFFFFFFFF
+        self._calls = 0
+        self._half = None
+
+    def corrupt_batch(self, heads, tails, relations=None, n_neg=None):
+        if n_neg is None:
+            n_neg = self.n_neg
+        dev = heads.device
+        assert dev == tails.device
+        if not heads.is_cuda:
+            raise _lib.KgeLibraryError("corrupt_batch needs CUDA index tensors; there is no CPU path")
+        b = heads.shape[0]
+        if self._half is None or self._half.device != dev:
+            self._half = torch.full((1,), 0.5, dtype=torch.float32, device=dev)
+        h, t = heads.long().contiguous(), tails.long().contiguous()
+        r = torch.zeros(b, dtype=torch.int64, device=dev)   # every fact reads probs[0] = 1/2
+        nh = torch.empty(b * n_neg, dtype=torch.int64, device=dev)
+        nt = torch.empty(b * n_neg, dtype=torch.int64, device=dev)
+        self._calls += 1
+        _lib.check(_lib.load().kge_corrupt_batch(_ptr(h), _ptr(t), _ptr(r), b, n_neg, _ptr(self._half),
+                                                 self.n_ent, self.seed, self._calls, _ptr(nh), _ptr(nt),
+                                                 _stream(dev)), "kge_corrupt_batch")
+        return nh, nt
+
+
 class BernoulliNegativeSampler(NegativeSampler):
     """Bernoulli negative sampler (Wang et al. 2014), torchkge/sampling.py:226-327.
 

@@ -122,6 +122,37 @@ def margin_loss(pos, neg, margin):
     return _MarginLoss.apply(pos, neg, margin)
 
 
+class _PairLoss(torch.autograd.Function):
+    """LogisticLoss / BinaryCrossEntropyLoss (kge_pair_loss_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, pos, neg, kind):
+        _check_cuda(pos, neg)
+        pos, neg = pos.detach().contiguous().float(), neg.detach().contiguous().float()
+        if pos.shape != neg.shape:
+            raise ValueError("positive and negative score tensors must have the same shape")
+        loss = torch.zeros((), dtype=torch.float32, device=pos.device)
+        _lib.check(_lib.load().kge_pair_loss_fwd(kind, _ptr(pos), _ptr(neg), pos.numel(), _ptr(loss),
+                                                 _stream(pos.device)), "kge_pair_loss_fwd")
+        ctx.kind = kind
+        ctx.save_for_backward(pos, neg)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gl):
+        pos, neg = ctx.saved_tensors
+        gl = gl.contiguous().float()
+        gp, gn = torch.empty_like(pos), torch.empty_like(neg)
+        _lib.check(_lib.load().kge_pair_loss_bwd(ctx.kind, _ptr(pos), _ptr(neg), pos.numel(), _ptr(gl),
+                                                 _ptr(gp), _ptr(gn), _stream(pos.device)),
+                   "kge_pair_loss_bwd")
+        return gp, gn, None
+
+
+def pair_loss(pos, neg, kind):
+    return _PairLoss.apply(pos, neg, kind)
+
+
 class _MarginStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, code, dim, n_ent, margin, n_neg, h, t, r, nh, nt, probs, seed, offset,
