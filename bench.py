@@ -56,7 +56,7 @@ def parse_args():
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the warm-up and timed steps run."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -68,7 +68,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -332,15 +332,18 @@ def run_ours(args, rank, local, world):
         return out
 
     # ---- device-resident timing -------------------------------------------------------
+    # clocks / throttle reasons are sampled from the first warm-up step to the end of the timed
+    # region (same load throughout; a timed region of a few hundred ms alone may fall between two
+    # nvidia-smi samples)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         ranks_dev = device_step()
     barrier()
     _lib.scan_timing_enable(True)
     for kind in (0, 1, 2):
         _lib.scan_timing_read(kind)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -411,7 +414,11 @@ def run_ours(args, rank, local, world):
             "kernel": "tc_scan_kernel (tcgen05 bf16x3 split GEMM + threshold epilogue)", "bound": "tensor",
             "achieved": alg_flops / (ms_per_launch / 1000.0) / 1e12, "peak": tensor_peak[0],
             "unit": "TFLOP/s", "frac": alg_flops / (ms_per_launch / 1000.0) / 1e12 / tensor_peak[0],
-            "peak_source": tensor_peak[1], "traffic": None,
+            "peak_source": tensor_peak[1],
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at c2 (20,466 x 1M), from the
+            # committed capture profiles/r01_tc_scan_v2_ncu_summary.md; null for other shapes
+            "traffic": (1.029e9 + 0.177e9) if (args.workload == "c2" and world == 1) else None,
+            "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_tc_scan_v2_ncu_summary.md)",
             "launches_timed": tc_n, "ms_per_launch": ms_per_launch,
             "scan_share_of_step": tc_ms / dev_ms if dev_ms > 0 else None,
             "recheck_ms_per_launch": rc_ms / max(1, rc_n),
@@ -419,10 +426,11 @@ def run_ours(args, rank, local, world):
             "near_tie_pairs_per_step": near_ties,
             "near_tie_fraction": near_ties / (2.0 * max(1, n_my) * rows_here),
             "executed_bf16_tflops": 3 * alg_flops / (ms_per_launch / 1000.0) / 1e12,
+            "executed_frac_of_peak": 3 * alg_flops / (ms_per_launch / 1000.0) / 1e12 / tensor_peak[0],
             "note": "algorithmic flops = 2 x queries x rows x K (fp32 contraction); the kernel executes "
-                    "3 bf16 MMAs per product (hi*hi + lo*hi + hi*lo) and is L2->SM bandwidth bound "
-                    "(operand images stream at 12 B per (query, candidate)); near-ties are re-scored "
-                    "exactly so ranks stay bit-identical",
+                    "3 bf16 MMAs per product (hi*hi + lo*hi + hi*lo), i.e. 3x the algorithmic flops, and "
+                    "runs power-capped (sw_power_cap) like the sustained cuBLAS measurement the peak "
+                    "comes from; near-ties are re-scored exactly so ranks stay bit-identical",
         }
     else:
         # scalar fp32 scan.  algorithmic bytes per launch = queries x candidate rows x row_bytes

@@ -90,6 +90,9 @@ int kge_query_planes(int model, int side);
  * ATen's cascade sum (bilinear models / RotatE).  Exposed for CPU tests, which
  * replay the schedule in numpy and compare with ATen bit for bit. */
 int kge_build_schedule(int model, int dim, int32_t* perm_host, uint8_t* code_host);
+/* Depth of that reduction tree: the most rounded additions any term passes through (-1 if the
+ * model / dim is unsupported).  The tensor-core path's error bound uses it (host only). */
+int kge_schedule_depth(int model, int dim);
 
 /* ---- table packing ---------------------------------------------------------------
  * Re-lays an entity table shard (rows [0, n_rows) of ent0 / ent1, each row-major
@@ -153,7 +156,8 @@ typedef struct {
   int64_t n_ent;  /* global number of entities */
   int64_t ent_lo; /* first global entity id held in `packed` / ent0 / ent1 */
   int64_t n_rows; /* rows held */
-  const float* packed; /* kge_pack_table output for this shard */
+  const float* packed; /* kge_pack_table output for this shard (may be NULL when the tensor-core
+                          scan is used: KGE_FLAG_TENSOR_CORE and a model that has one) */
   const float* ent0;   /* row-major shard (used for the sparse filter pass) */
   const float* ent1;   /* second plane or NULL */
   const float* rel0;   /* relation table: rel_emb / re_rel_emb / rel_mat / phases */

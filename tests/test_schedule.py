@@ -57,3 +57,20 @@ def test_unsupported_dim_is_an_error_not_a_crash():
         _lib.build_schedule(_lib.DISTMULT, 8192)
     with pytest.raises(_lib.KgeLibraryError):
         _lib.build_schedule(99, 16)
+
+
+def test_schedule_depth_is_the_depth_of_the_reduction_tree():
+    """kge_schedule_depth: rounded additions on the longest path of the ATen-order reduction."""
+    lib = _lib.load()
+    # norm(p=1): one sequential chain over d terms -> d - 1 additions (the first is exact)
+    assert [lib.kge_schedule_depth(_lib.TRANSE_L1, d) for d in (1, 2, 50)] == [0, 1, 49]
+    # norm(p=2): 8 lanes of d/8 terms, lanes folded one after the other, short tail
+    for d in (8, 64, 200, 203, 1000):
+        depth = lib.kge_schedule_depth(_lib.TRANSE_L2, d)
+        assert d // 8 - 1 <= depth <= d // 8 + 15
+    # cascade sum: 32 chains of d/32 terms (+ spill levels), rows and lanes folded
+    for d in (7, 8, 100, 200, 400, 800, 2049):
+        depth = lib.kge_schedule_depth(_lib.DISTMULT, d)
+        assert 0 <= depth <= d // 32 + 21
+        assert depth == lib.kge_schedule_depth(_lib.COMPLEX, d)
+    assert lib.kge_schedule_depth(_lib.DISTMULT, 10 ** 6) == -1

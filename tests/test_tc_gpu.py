@@ -56,9 +56,10 @@ def test_approximate_scores_within_half_the_bound(kind, d, cuda_device):
         # the bound the kernel uses: gamma * |a| |b|  (dot) or gamma * (|a| + |b|)^2  (L2)
         l2 = kind == "transe_l2"
         k_total = 2 * d if kind == "complex" else (d + 3 if l2 else d)  # csrc/api.cu: tc_k_total
+        depth = _lib.load().kge_schedule_depth(spec.code, d)           # depth of the ATen reduction tree
         gamma = (3.0 * 2.0 ** -16 + 2.0 * (3.0 * ((k_total + 15) // 16) + 2.0) * 2.0 ** -22
-                 + (k_total + 4.0) * 2.0 ** -24)                       # csrc/tc.h: tc_gamma
-        gamma2 = (k_total + 42.0) * 2.0 ** -23                         # csrc/tc.h: tc_gamma2
+                 + (0.0 if l2 else (depth + 4.0) * 2.0 ** -24))        # csrc/tc.h: tc_gamma
+        gamma2 = (depth + 42.0) * 2.0 ** -24                           # csrc/tc.h: tc_gamma2
         # operand norms
         if kind == "complex":
             cand = torch.cat([P["re_ent"], P["im_ent"]], 1).double()

@@ -10,6 +10,7 @@ from .data import KnowledgeGraph  # noqa: F401
 from .models import (ComplExModel, DistMultModel, RESCALModel, RotatEModel,  # noqa: F401
                      TransEModel)
 from .evaluation import LinkPredictionEvaluator, RelationPredictionEvaluator  # noqa: F401
+from .inference import EntityInference, RelationInference  # noqa: F401
 from .losses import BinaryCrossEntropyLoss, LogisticLoss, MarginLoss  # noqa: F401
 from .sampling import BernoulliNegativeSampler, UniformNegativeSampler  # noqa: F401
 

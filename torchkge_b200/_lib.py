@@ -92,6 +92,7 @@ SIGNATURES = {
                                    _c.c_int64, _p, _p]),
     "kge_rank_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64,
                                                _c.c_int]),
+    "kge_schedule_depth": (_c.c_int, [_c.c_int, _c.c_int]),
     "kge_tc_packed_bytes": (_c.c_size_t, [_c.c_int, _c.c_int64, _c.c_int]),
     "kge_tc_configure": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     "kge_tc_pack_table": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _c.c_int, _p, _p]),

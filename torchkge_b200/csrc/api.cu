@@ -105,11 +105,13 @@ Workspace carve(void* base, int qw, int dim, int64_t n, int el = -1, int64_t n_r
     w.apack = static_cast<unsigned char*>(take(kge::tc::a_image_bytes(n, n_kb)));
     w.qbound = static_cast<float*>(take((size_t)n * sizeof(float)));
     w.qnorm2 = static_cast<float*>(take((size_t)n * sizeof(float)));
-    w.amb_count = static_cast<unsigned long long*>(take(256 * sizeof(unsigned long long)));  // per-CTA regions
-    // near-tie list: room for 1/256 of all pairs (the band is ~0.1 %), 1 Mi..128 Mi entries
-    unsigned long long cap = (unsigned long long)n * (unsigned long long)n_rows / 256ull;
-    if (cap < (1ull << 20)) cap = 1ull << 20;
-    if (cap > (1ull << 27)) cap = 1ull << 27;
+    const int64_t n_tc_qt = (n + kge::tc::TC_BM - 1) / kge::tc::TC_BM;
+    w.amb_count = static_cast<unsigned long long*>(take((size_t)n_tc_qt * sizeof(unsigned long long)));
+    // near-tie list, one region per query tile: room for 1/128 of all pairs (the band is
+    // 0.1-0.3 % on average), at least 8 Ki entries per tile, at most 256 Mi in total
+    unsigned long long cap = (unsigned long long)n * (unsigned long long)n_rows / 128ull;
+    if (cap < (unsigned long long)n_tc_qt * 8192ull) cap = (unsigned long long)n_tc_qt * 8192ull;
+    if (cap > (1ull << 28)) cap = 1ull << 28;
     w.amb_cap = cap;
     w.amb_pairs = static_cast<int2*>(take((size_t)cap * sizeof(int2)));
   }
@@ -195,6 +197,11 @@ int kge_build_schedule(int model, int dim, int32_t* perm_host, uint8_t* code_hos
   memcpy(perm_host, hs->s.perm.data(), (size_t)dim * sizeof(int32_t));
   memcpy(code_host, hs->s.code.data(), (size_t)dim);
   return KGE_OK;
+}
+
+int kge_schedule_depth(int model, int dim) {
+  const HostSchedule* hs = get_schedule(model, dim);
+  return hs ? kge::schedule_depth(hs->s) : -1;
 }
 
 size_t kge_packed_table_floats(int model, int64_t n_rows, int dim) {
@@ -287,8 +294,7 @@ int kge_rank_side(const kge_rank_args_t* a) {
   if (a->n == 0) return KGE_OK;
   if (a->n < 0 || a->n_rows < 0 || a->dim < 1) return fail(KGE_ERR_ARG, "kge_rank_side: bad sizes");
   const bool rel_side = a->side == KGE_SIDE_REL;
-  if (!a->packed || !a->ent0 || (!a->rel0 && !rel_side) || !a->hrows || !a->trows || !a->raw_count ||
-      !a->workspace)
+  if (!a->ent0 || (!a->rel0 && !rel_side) || !a->hrows || !a->trows || !a->raw_count || !a->workspace)
     return fail(KGE_ERR_ARG, "kge_rank_side: null pointer");
   if (kge::elem_cw(el) == 2 && !a->ent1) return fail(KGE_ERR_ARG, "kge_rank_side: ent1 required");
   if (!rel_side && model_needs_rel1(a->model) && !a->rel1)
@@ -302,6 +308,7 @@ int kge_rank_side(const kge_rank_args_t* a) {
   const int qw = kge::elem_qw(el);
   const bool use_tc = (a->flags & KGE_FLAG_TENSOR_CORE) && tc_supported(el) && a->n_rows > 0;
   if (use_tc && !a->tc_packed) return fail(KGE_ERR_ARG, "kge_rank_side: tc_packed required with KGE_FLAG_TENSOR_CORE");
+  if (!use_tc && !a->packed) return fail(KGE_ERR_ARG, "kge_rank_side: packed table required (scalar scan)");
   Workspace w = carve(a->workspace, qw, a->dim, a->n, el, a->n_rows, use_tc ? KGE_FLAG_TENSOR_CORE : 0);
   if (w.bytes > a->workspace_bytes) return fail(KGE_ERR_ARG, "kge_rank_side: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
@@ -340,10 +347,11 @@ int kge_rank_side(const kge_rank_args_t* a) {
     KGE_CUDA_TRY(kge::tc::launch_pack_a(w.qplain, qw, a->n, a->dim, k_total, n_kb,
                                         el == kge::EL_L2_HEAD ? 1 : 0, l2, w.apack, w.qbound, w.qnorm2, st),
                  "tc pack queries");
-    const int regions = kge::tc::scan_grid_size(a->n, a->n_rows, n_kb);
-    if (regions <= 0 || regions > 256) return fail(KGE_ERR_CUDA, "kge_rank_side: cannot size the tensor-core grid");
+    if (kge::tc::scan_grid_size(a->n, a->n_rows, n_kb) <= 0)
+      return fail(KGE_ERR_CUDA, "kge_rank_side: cannot size the tensor-core grid");
+    const int regions = (int)((a->n + kge::tc::TC_BM - 1) / kge::tc::TC_BM);  // one per query tile
     const unsigned long long region_cap = w.amb_cap / (unsigned long long)regions;
-    KGE_CUDA_TRY(cudaMemsetAsync(w.amb_count, 0, 256 * sizeof(unsigned long long), st), "tc reset list");
+    KGE_CUDA_TRY(cudaMemsetAsync(w.amb_count, 0, (size_t)regions * sizeof(unsigned long long), st), "tc reset list");
     const unsigned char* bpack = static_cast<const unsigned char*>(a->tc_packed);
     const float* cbound = reinterpret_cast<const float*>(bpack + kge::tc::b_image_bytes(a->n_rows, n_kb));
     kge::tc::TcScanParams tp;
@@ -352,7 +360,9 @@ int kge_rank_side(const kge_rank_args_t* a) {
     tp.cbound = cbound; tp.cnorm2 = cbound + (size_t)n_ct * kge::tc::TC_BN;
     tp.counts = a->raw_count; tp.amb_count = w.amb_count; tp.amb_pairs = w.amb_pairs;
     tp.amb_cap = region_cap; tp.dump = a->tc_dump;
-    tp.gamma = kge::tc::tc_gamma(k_total); tp.gamma2 = kge::tc::tc_gamma2(k_total); tp.l2 = l2 ? 1 : 0;
+    const int ref_depth = kge::schedule_depth(hs->s);
+    tp.gamma = kge::tc::tc_gamma(k_total, ref_depth, l2); tp.gamma2 = kge::tc::tc_gamma2(ref_depth);
+    tp.l2 = l2 ? 1 : 0;
     tp.n_kb = n_kb; tp.k_total = k_total; tp.ct_group = 0;
     tp.n_q = a->n; tp.n_rows = a->n_rows;
     tp.n_qt = (a->n + kge::tc::TC_BM - 1) / kge::tc::TC_BM; tp.n_ct = n_ct;
@@ -427,9 +437,10 @@ int kge_score_all(const kge_score_all_args_t* a) {
   const int el = kge::elem_kind_for(a->model, a->side);
   if (el < 0) return fail(KGE_ERR_ARG, "kge_score_all: unknown model/side");
   if (a->n == 0 || a->n_rows == 0) return KGE_OK;
-  if (!a->packed || !a->rel0 || !a->hrows || !a->trows || !a->scores || !a->workspace)
+  const bool rel_side = a->side == KGE_SIDE_REL;  // candidates = relation rows; rel0 / rel1 unused
+  if (!a->packed || (!a->rel0 && !rel_side) || !a->hrows || !a->trows || !a->scores || !a->workspace)
     return fail(KGE_ERR_ARG, "kge_score_all: null pointer");
-  if (model_needs_rel1(a->model) && !a->rel1)
+  if (!rel_side && model_needs_rel1(a->model) && !a->rel1)
     return fail(KGE_ERR_ARG, "kge_score_all: rel1 required");
   const HostSchedule* hs = get_schedule(a->model, a->dim);
   if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_score_all: unsupported dim");

@@ -102,6 +102,23 @@ bool build_sum(int dim, Builder& b) {
 
 }  // namespace
 
+int schedule_depth(const Schedule& s) {
+  // replay the micro-ops with depths instead of values; -1 = empty accumulator (exact zero)
+  auto add = [](int x, int y) { return x < 0 ? y : (y < 0 ? x : (x > y ? x : y) + 1); };
+  int a = -1, a1 = -1, p = -1, t = -1;
+  for (uint8_t code : s.code) {
+    const uint8_t mode = code & SC_MODE_MASK;
+    if (mode == SC_MODE_A) a = add(a, 0); else t = add(t, 0);
+    if (code & SC_CASC1) { a1 = add(a1, a); a = -1; }
+    if (code & SC_FOLD1) { a = add(a, a1); a1 = -1; }
+    if (code & SC_P_SET) { p = a; a = -1; }
+    if (code & SC_P_ADD) { p = add(p, a); a = -1; }
+    if (code & SC_T_ADD_P) { t = add(t, p); }
+    if (code & SC_T_ADD_A) { t = add(t, a); a = -1; }
+  }
+  return t < 0 ? 0 : t;
+}
+
 bool build_schedule(int kind, int dim, Schedule* out) {
   if (dim < 1 || dim > 8191) return false;
   out->kind = kind;

@@ -39,6 +39,12 @@ struct Schedule {
 };
 
 int reduce_kind_for_model(int model);
+// Depth of the reduction tree the schedule encodes: the largest number of ROUNDED additions any
+// single term passes through on its way into the result (adding to an empty accumulator is exact
+// and not counted).  The standard summation bound |fl(sum) - sum| <= depth * u * sum|terms|
+// (first order, u = 2^-24) then holds for exactly the order the reference uses; the tensor-core
+// path's error bound is built on it (tc.h).
+int schedule_depth(const Schedule& s);
 // returns false if dim is outside the supported range
 bool build_schedule(int kind, int dim, Schedule* out);
 

@@ -287,6 +287,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
           const long long pq = cur_qt * BM + row;
           if (pq < p.n_q) atomicAdd(&p.counts[pq], cnt);
         }
+        // the near-tie list is kept per QUERY TILE (region = qt) so that the exact recheck of a
+        // region touches only that tile's 128 query rows (they stay L1-resident there): flush
+        // what this warp buffered for the previous tile before moving on
+        if (cur_qt >= 0 && amb_n > 0) {
+          __syncwarp();
+          unsigned long long fbase = 0;
+          if (lane == 0) fbase = atomicAdd(p.amb_count + cur_qt, (unsigned long long)amb_n);
+          fbase = __shfl_sync(0xffffffffu, fbase, 0);
+          for (int i = lane; i < amb_n; i += 32)
+            if (fbase + i < p.amb_cap) p.amb_pairs[(size_t)cur_qt * p.amb_cap + fbase + i] = wbuf[i];
+          __syncwarp();
+          amb_n = 0;
+        }
         cnt = 0; cur_qt = qt;
         const bool vq = q < p.n_q;
         st = vq ? p.s_true[q] : INFINITY;
@@ -368,10 +381,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
             if (amb_n + total_new > AMB_BUF) {  // flush first (uniform decision)
               __syncwarp();
               unsigned long long base = 0;
-              if (lane == 0) base = atomicAdd(p.amb_count + blockIdx.x, (unsigned long long)amb_n);
+              if (lane == 0) base = atomicAdd(p.amb_count + cur_qt, (unsigned long long)amb_n);
               base = __shfl_sync(0xffffffffu, base, 0);
               for (int i = lane; i < amb_n; i += 32)
-                if (base + i < p.amb_cap) p.amb_pairs[(size_t)blockIdx.x * p.amb_cap + base + i] = wbuf[i];
+                if (base + i < p.amb_cap) p.amb_pairs[(size_t)cur_qt * p.amb_cap + base + i] = wbuf[i];
               __syncwarp();
               amb_n = 0;
             }
@@ -387,14 +400,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
             } else {
               // pathological block (more near-ties than the buffer holds): straight to global
               unsigned long long base = 0;
-              if (lane == 0) base = atomicAdd(p.amb_count + blockIdx.x, (unsigned long long)total_new);
+              if (lane == 0) base = atomicAdd(p.amb_count + cur_qt, (unsigned long long)total_new);
               base = __shfl_sync(0xffffffffu, base, 0) + (unsigned long long)(incl - mine);
               unsigned m = amb_mask;
               while (m) {
                 const int j = __ffs(m) - 1;
                 m &= m - 1;
                 if (base < p.amb_cap)
-                  p.amb_pairs[(size_t)blockIdx.x * p.amb_cap + base] = make_int2((int)q, (int)(ct * BN + c0 + j));
+                  p.amb_pairs[(size_t)cur_qt * p.amb_cap + base] = make_int2((int)q, (int)(ct * BN + c0 + j));
                 ++base;
               }
             }
@@ -414,10 +427,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
     if (amb_n > 0) {  // final flush of this warp's near-tie buffer
       __syncwarp();
       unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(p.amb_count + blockIdx.x, (unsigned long long)amb_n);
+      if (lane == 0) base = atomicAdd(p.amb_count + cur_qt, (unsigned long long)amb_n);
       base = __shfl_sync(0xffffffffu, base, 0);
       for (int i = lane; i < amb_n; i += 32)
-        if (base + i < p.amb_cap) p.amb_pairs[(size_t)blockIdx.x * p.amb_cap + base + i] = wbuf[i];
+        if (base + i < p.amb_cap) p.amb_pairs[(size_t)cur_qt * p.amb_cap + base + i] = wbuf[i];
     }
   }
   fence_before();
@@ -551,7 +564,7 @@ __global__ void recheck_kernel(int dim, const unsigned long long* __restrict__ r
                                int32_t* __restrict__ counts) {
   constexpr int QW = ElemTraits<EL>::QW, CW = ElemTraits<EL>::CW;
   constexpr bool NORM = ElemTraits<EL>::RED == RED_NORM2;
-  constexpr int PAIRS_PER_WARP = NORM ? 4 : 1;
+  constexpr int PAIRS_PER_WARP = 1;  // the whole warp on one pair: one 128-byte line per row and step
   const unsigned long long region = blockIdx.y;
   const unsigned long long n_pairs = min(region_counts[region], region_cap);
   const int lane = threadIdx.x & 31;
@@ -570,15 +583,17 @@ __global__ void recheck_kernel(int dim, const unsigned long long* __restrict__ r
     return;
   }
   for (unsigned long long base = warp_global * PAIRS_PER_WARP; base < n_pairs; base += n_warps * PAIRS_PER_WARP) {
-    const unsigned long long i = base + (NORM ? (lane >> 3) : 0);
+    const unsigned long long i = base;
     const bool valid = i < n_pairs;
     const int2 pr = list[valid ? i : base];  // idle groups redo the first pair (shuffles stay uniform)
     const float* q0 = qplain + (size_t)pr.x * QW * dim;
     const float* q1 = q0 + (size_t)(QW - 1) * dim;
     const float* c0 = ent0 + (size_t)pr.y * dim;
     const float* c1 = (CW == 2 ? ent1 : ent0) + (size_t)pr.y * dim;
-    const float sc = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane);
-    const bool leader = NORM ? ((lane & 7) == 0) : (lane == 0);
+    float sc;
+    if constexpr (NORM) sc = pair_score_norm2_warp<EL>(dim, q0, q1, c0, c1, lane);
+    else sc = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane);
+    const bool leader = lane == 0;
     if (valid && leader && sc >= s_true[pr.x]) atomicAdd(&counts[pr.x], 1);
   }
 }

@@ -26,8 +26,8 @@ struct TcScanParams {
   const float* cbound;         // [n_rows] >= |b|_2
   const float* cnorm2;         // [n_rows]
   int32_t* counts;             // [n_q] +=
-  unsigned long long* amb_count;  // [gridDim.x] per-CTA region fill counts
-  int2* amb_pairs;                // [gridDim.x][amb_cap]
+  unsigned long long* amb_count;  // [n_qt] fill count of each query tile's region
+  int2* amb_pairs;                // [n_qt][amb_cap]
   unsigned long long amb_cap;     // capacity of ONE region
   float* dump;                 // debug: write approximate scores [n_q][n_rows] instead of counting
   float gamma;                 // tc_gamma(k)
@@ -47,21 +47,27 @@ struct TcScanParams {
 //     dropped lo*lo, a*r_b, r_a*b                                   -> 3 * 2^-16       (exact bound)
 //   fp32 accumulation inside the tensor core: assumed <= 2 ulp of the running magnitude per
 //     MMA instruction, 3 instructions per 16 terms, doubled for safety -> 2 (3 ceil(k/16) + 2) 2^-22
-//   the reference's own fp32 evaluation of the products and their <= k-term sums (any order)
-//                                                                    -> (k + 4) * 2^-24 (exact bound)
-// gamma2 (L2 only) collects what is proportional to the squared norms: the reference's fp32 sum
-// of squares / sqrt / square, forming t - r in fp32, and the epilogue's |a|^2 + |b|^2 - 2ab.
+//   dot models only: the reference's own fp32 evaluation -- every product rounded once (ComplEx:
+//     two products and their sum), then summed in ATen's cascade order, whose tree depth
+//     `ref_depth` (schedule.h: schedule_depth, computed from the very schedule the exact kernels
+//     replay) gives |fl(sum) - sum| <= ref_depth * u * sum|terms|   -> (ref_depth + 4) * 2^-24
+// gamma2 (L2 only) collects what is proportional to the squared norms, (|a| + |b|)^2 >= |a - b|^2:
+//   the reference forms x_k = q_k - c_k (head side: (c_k + r_k) - t_k, two roundings, |x| bounded
+//   by |c| + |r| + |t| -- the head-side query bound is |t| + |r| for that reason), squares it,
+//   sums in the 8-lane norm order (depth ref_depth), takes an exactly rounded sqrt and squares it:
+//     relative (ref_depth + 10) u on sum x^2;
+//   this side: |a|^2 and |b|^2 rounded to fp32 (2u), |b|^2/2 carried as three bf16 pieces (u),
+//   the <= 6 MMA instructions that accumulate it (6 * 2^-21 * |b|^2 / 2 = 24 u |b|^2), threshold
+//   arithmetic is directed-rounded                                    -> (ref_depth + 42) * 2^-24
 // tests/test_tc_gpu.py measures the actual error on every model and requires it to stay below
-// half of the bound (it is ~10-20x smaller).
-inline float tc_gamma(int k_total) {
+// half of the bound.
+inline float tc_gamma(int k_total, int ref_depth, bool l2) {
   const double split = 3.0 * 0x1p-16;
   const double accum = 2.0 * (3.0 * ((k_total + 15) / 16) + 2.0) * 0x1p-22;
-  const double ref = (k_total + 4.0) * 0x1p-24;
+  const double ref = l2 ? 0.0 : (ref_depth + 4.0) * 0x1p-24;
   return (float)(split + accum + ref);
 }
-// + the three-piece bf16 representation of |b|^2/2 carried in the operand image (2^-24 |b|^2) and
-// the tensor-core accumulation of the (at most 6) MMAs that see it (<= 6 * 2^-21 * |b|^2 / 2).
-inline float tc_gamma2(int k_total) { return (float)((k_total + 42.0) * 0x1p-23); }
+inline float tc_gamma2(int ref_depth) { return (float)((ref_depth + 42.0) * 0x1p-24); }
 
 size_t a_image_bytes(long long n_q, int n_kb);
 size_t b_image_bytes(long long n_rows, int n_kb);
@@ -74,8 +80,9 @@ cudaError_t launch_pack_a(const float* qplain, int qw, long long n_q, int dim, i
                           int sub_mode, bool fold, unsigned char* apack, float* qbound, float* qnorm2,
                           cudaStream_t st);
 cudaError_t launch_tc_scan(const TcScanParams& p, cudaStream_t st);
-// The near-tie list is split into one region per CTA of the scan (regions = scan_grid_size):
-// region_counts[regions] (zeroed by the caller), pairs[regions][region_cap].
+// The near-tie list is split into one region per QUERY TILE (regions = n_qt): region_counts[regions]
+// (zeroed by the caller), pairs[regions][region_cap].  A region's pairs all belong to the same 128
+// queries, whose rows therefore stay L1-resident during the exact recheck of that region.
 int scan_grid_size(long long n_q, long long n_rows, int n_kb);
 cudaError_t launch_recheck(int el, int dim, const unsigned long long* region_counts, int regions,
                            unsigned long long region_cap, const int2* pairs, const float* qplain,

@@ -415,8 +415,9 @@ __device__ __forceinline__ void warp_sum2(float& a, float& b) {
 __device__ __forceinline__ float sgn(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 
 template <int MODEL, bool BWD>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)
 margin_step_fast_kernel(MarginStepParams a, TrainGrads gr, const float* __restrict__ gloss) {
+  constexpr int PF = BWD ? 2 : 4;  // negatives whose rows are in flight together, per warp
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= a.b) return;
@@ -467,9 +468,25 @@ margin_step_fast_kernel(MarginStepParams a, TrainGrads gr, const float* __restri
       if (!BWD && a.nh_out) { a.nh_out[idx] = my_nh; a.nt_out[idx] = my_nt; }
     }
     const int jn = min(32, a.n_neg - j0);
-#pragma unroll 2
-    for (int jj = 0; jj < jn; ++jj) {
-      const long long nh = __shfl_sync(0xffffffffu, my_nh, jj), nt = __shfl_sync(0xffffffffu, my_nt, jj);
+    // PF negatives at a time: their rows are requested together (memory-level parallelism:
+    // PF x 4 dim bytes in flight per warp), then reduced one after the other
+    for (int jj0 = 0; jj0 < jn; jj0 += PF) {
+     long long nhs[PF], nts[PF];
+     Vec evs[PF];
+#pragma unroll
+     for (int u = 0; u < PF; ++u) {
+       const int jj = min(jj0 + u, 31);
+       nhs[u] = __shfl_sync(0xffffffffu, my_nh, jj);
+       nts[u] = __shfl_sync(0xffffffffu, my_nt, jj);
+       const bool both = nhs[u] != hi && nts[u] != ti;
+       const long long e_ = nhs[u] != hi ? nhs[u] : nts[u];
+       if (jj0 + u < jn && !both) evs[u] = vec_load(ent + (size_t)e_ * dim, dim, lane);
+     }
+#pragma unroll
+     for (int u = 0; u < PF; ++u) {
+      if (jj0 + u >= jn) break;
+      const int jj = jj0 + u;
+      const long long nh = nhs[u], nt = nts[u];
       const long long idx = (long long)(j0 + jj) * a.b + w;
       if (nh != hi && nt != ti) {
         // both ends replaced (possible with caller-supplied negatives only): generic path
@@ -489,7 +506,7 @@ margin_step_fast_kernel(MarginStepParams a, TrainGrads gr, const float* __restri
       }
       const bool head = nh != hi;            // warp-uniform
       const long long e = head ? nh : nt;
-      const Vec ev = vec_load(ent + (size_t)e * dim, dim, lane);
+      const Vec ev = evs[u];
       const Vec& P = head ? Bv : A;
       float se = vec_dot(ev, ev), sp = vec_dot(ev, P);
       warp_sum2(se, sp);
@@ -539,6 +556,7 @@ margin_step_fast_kernel(MarginStepParams a, TrainGrads gr, const float* __restri
         if (head) { Vh = vec_map(Vh, V, [](float x, float y) { return x + y; }); ++n_h; }
         else { Vt = vec_map(Vt, V, [](float x, float y) { return x + y; }); ++n_t; }
       }
+     }
     }
   }
   if (!BWD) {

@@ -314,11 +314,11 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
             packed = None
     mark = getattr(engine, "mark", lambda label: None)
     mark("step begin")
-    if packed is None:
-        packed = engine.pack(spec)
-    mark("pack")
     tc_packed = engine.pack_tc(spec) if hasattr(engine, "pack_tc") else None
     mark("pack_tc")
+    if packed is None and tc_packed is None:
+        packed = engine.pack(spec)   # scalar-scan layout: only when there is no tensor-core path
+    mark("pack")
     dev = spec.ent0.device
     counters = torch.zeros((4, n), dtype=torch.int32, device=dev)  # raw_t, sub_t, raw_h, sub_h
     pending = []
@@ -357,6 +357,8 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
             if stats is not None:
                 found, cap = (int(x) for x in stats.tolist())
                 if found > cap:
+                    if packed is None:
+                        packed = engine.pack(spec)
                     raw = counters[0] if side == _lib.SIDE_TAIL else counters[2]
                     raw[lo:hi].zero_()
                     engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
