@@ -175,3 +175,62 @@ def test_filter_index_graph_gives_reference_ranks(kind, cuda_device):
     ref = oracle.link_prediction(kind, P, th, tt, tr, dh, dt, b_size=60)
     ev = _ranks_gpu(model, kg)
     _assert_ranks_equal(ev, ref, kind)
+
+
+@pytest.mark.parametrize("case", helpers.GOLDEN_CASES)
+@pytest.mark.parametrize("tensor_core", [True, False])
+def test_ranks_equal_the_unmodified_reference(case, tensor_core, cuda_device, monkeypatch):
+    """The committed outputs of torchkge's own LinkPredictionEvaluator (tests/golden/*.npz): all
+    four rank vectors and the metric getters, through both the tensor-core and the scalar scan."""
+    import torchkge_b200.engine as engine_mod
+    g = helpers.load_golden(case)
+    model = helpers.model_from_golden(g).to(cuda_device)
+    kg = tk.KnowledgeGraph(g["heads"], g["tails"], g["rels"], g["n_ent"], g["n_rel"],
+                           dict_of_heads=g["dh"], dict_of_tails=g["dt"])
+    monkeypatch.setattr(engine_mod, "_default_engine", engine_mod.CudaEngine(tensor_core=tensor_core))
+    ev = tk.LinkPredictionEvaluator(model, kg)
+    ev.evaluate(b_size=g["b_size"], verbose=False)
+    raw = g["raw"]
+    names = ["rank_true_heads", "rank_true_tails", "filt_rank_true_heads", "filt_rank_true_tails"]
+    if g["kind"] == "rescal":
+        # query preparation is an MKL batched GEMM in the reference: near-ties may flip (DESIGN.md 2.4)
+        for nm in names:
+            assert (getattr(ev, nm) - torch.from_numpy(raw[nm])).abs().max().item() <= 2
+    else:
+        for nm in names:
+            assert torch.equal(getattr(ev, nm), torch.from_numpy(raw[nm])), nm
+        got = [*ev.mean_rank(), *ev.hit_at_k(10), *ev.mrr()]
+        for a, b in zip(got, raw["metrics"]):
+            assert a == pytest.approx(float(b), rel=1e-6)
+
+
+def test_empty_and_single_fact_graphs(cuda_device):
+    model = helpers.make_model("distmult", 16, 40, 3, seed=0).to(cuda_device)
+    e = torch.zeros(0, dtype=torch.long)
+    kg = tk.KnowledgeGraph(e, e, e, 40, 3, dict_of_heads={}, dict_of_tails={})
+    ev = tk.LinkPredictionEvaluator(model, kg)
+    ev.evaluate(b_size=8, verbose=False)
+    assert ev.rank_true_heads.shape == (0,) and ev.evaluated
+    one = torch.tensor([0])          # entity 0 as head and tail, relation 0
+    kg1 = tk.KnowledgeGraph(one, one, one, 40, 3)
+    ev1 = tk.LinkPredictionEvaluator(model, kg1)
+    ev1.evaluate(b_size=8, verbose=False)
+    P = helpers.oracle_params("distmult", model)
+    dh, dt = oracle.build_filter_dicts(one, one, one)
+    ref = oracle.link_prediction("distmult", P, one, one, one, dh, dt, 8)
+    _assert_ranks_equal(ev1, ref, "distmult")
+
+
+def test_non_finite_embeddings_rank_like_the_reference(cuda_device):
+    """NaN / inf rows: comparisons with NaN are false on both sides (operations.py:61)."""
+    n_ent, n_rel, d = 300, 4, 24
+    kg, dh, dt = helpers.make_kg(n_ent, n_rel, n_facts=1500, n_test=120, seed=17)
+    model = helpers.make_model("distmult", d, n_ent, n_rel, seed=17)
+    with torch.no_grad():
+        model.ent_emb.weight[5] = float("nan")
+        model.ent_emb.weight[9, 3] = float("inf")
+        model.ent_emb.weight[11, 0] = -float("inf")
+    model = model.to(cuda_device)
+    P = helpers.oracle_params("distmult", model)
+    ref = oracle.link_prediction("distmult", P, kg.head_idx, kg.tail_idx, kg.relations, dh, dt, 64)
+    _assert_ranks_equal(_ranks_gpu(model, kg), ref, "distmult")

@@ -9,9 +9,11 @@ from .exceptions import (NotYetEvaluatedError, NotYetImplementedError, SanityErr
 from .data import KnowledgeGraph  # noqa: F401
 from .models import (ComplExModel, DistMultModel, RESCALModel, RotatEModel,  # noqa: F401
                      TransEModel)
-from .evaluation import LinkPredictionEvaluator, RelationPredictionEvaluator  # noqa: F401
+from .evaluation import (LinkPredictionEvaluator, RelationPredictionEvaluator,  # noqa: F401
+                         TripletClassificationEvaluator)
 from .inference import EntityInference, RelationInference  # noqa: F401
 from .losses import BinaryCrossEntropyLoss, LogisticLoss, MarginLoss  # noqa: F401
-from .sampling import BernoulliNegativeSampler, UniformNegativeSampler  # noqa: F401
+from .sampling import (BernoulliNegativeSampler, PositionalNegativeSampler,  # noqa: F401
+                       UniformNegativeSampler)
 
 __version__ = "0.1.0"

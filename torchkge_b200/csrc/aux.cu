@@ -275,7 +275,7 @@ __global__ void filter_kernel(int dim, long long n, long long n_filt,
                               int32_t* __restrict__ filt_sub) {
   constexpr int QW = ElemTraits<EL>::QW, CW = ElemTraits<EL>::CW;
   constexpr int RED = ElemTraits<EL>::RED;
-  constexpr int LANES = RED == RED_SEQ ? 1 : 32;  // lanes per entry
+  constexpr int LANES = RED == RED_SEQ ? 1 : (RED == RED_NORM2 ? 8 : 32);  // lanes per entry
   constexpr int PER_WARP = 32 / LANES;
   const int lane = threadIdx.x & 31;
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -303,8 +303,7 @@ __global__ void filter_kernel(int dim, long long n, long long n_filt,
     if constexpr (RED == RED_SEQ) {
       s = pair_score<EL, CASC>(dim, q0, q1, c0, c1, perm, code);
     } else {
-      if constexpr (RED == RED_NORM2) s = pair_score_norm2_warp<EL>(dim, q0, q1, c0, c1, lane);
-      else if (small_sum) s = pair_score_natural<EL>(dim, q0, q1, c0, c1);
+      if (small_sum) s = pair_score_natural<EL>(dim, q0, q1, c0, c1);
       else s = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane);
     }
     const bool leader = (lane % LANES) == 0;

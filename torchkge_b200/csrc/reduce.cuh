@@ -270,59 +270,6 @@ __device__ float pair_score_natural(int dim, const float* __restrict__ q0, const
   }
 }
 
-// L2-norm pair score with the WHOLE warp on one pair: lane j reads element 32 i + j of the two
-// rows (one 128-byte line per row and step instead of four lines for four pairs -- the sparse
-// passes are bound by L1 tag lookups, profiles/r01_recheck_ncu_summary.md), squares it, and the
-// eight lanes of the ATen norm (lane l owns k = l, l + 8, ...) pick their four terms of the block
-// up in ascending k through shuffles.  Same bits as pair_score_natural / pair_score_chains.
-template <int EL>
-__device__ __forceinline__ float pair_score_norm2_warp(int dim, const float* __restrict__ q0,
-                                                       const float* __restrict__ q1,
-                                                       const float* __restrict__ c0,
-                                                       const float* __restrict__ c1, int lane) {
-  static_assert(ElemTraits<EL>::RED == RED_NORM2, "L2-norm kinds only");
-  const int l8 = lane & 7;
-  const int main_len = dim - dim % 8;
-  float acc = 0.f;
-  int k0 = 0;
-#pragma unroll 2
-  for (; k0 + 32 <= main_len; k0 += 32) {
-    const float x = elem_at<EL>(q0, q1, c0, c1, k0 + lane);
-    const float v = __fmul_rn(x, x);
-#pragma unroll
-    for (int m = 0; m < 4; ++m) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v, l8 + 8 * m));
-  }
-  const int rem = main_len - k0;  // 0, 8, 16 or 24 elements of the 8-lane part left
-  if (rem > 0) {
-    float v = 0.f;
-    if (lane < rem) {
-      const float x = elem_at<EL>(q0, q1, c0, c1, k0 + lane);
-      v = __fmul_rn(x, x);
-    }
-    for (int m = 0; m < rem / 8; ++m) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v, l8 + 8 * m));
-  }
-  float t = 0.f;
-#pragma unroll
-  for (int l = 0; l < 8; ++l) {
-    const float v = __shfl_sync(0xffffffffu, acc, l);
-    if (main_len > 0) t = __fadd_rn(t, v);
-  }
-  int k = main_len;
-  for (; k + 4 <= dim; k += 4) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float x = elem_at<EL>(q0, q1, c0, c1, k + j);
-      t = __fadd_rn(t, __fmul_rn(x, x));
-    }
-  }
-  for (; k < dim; ++k) {
-    const float x = elem_at<EL>(q0, q1, c0, c1, k);
-    t = __fmaf_rn(x, x, t);
-  }
-  Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
-  return acc_finish<EL>(r);
-}
-
 // Exact adjudication of the near-tie band (the list is kept as one region per CTA of the scan).
 // Chain-parallel: the independent chains of the ATen reduction are spread over the lanes of a
 // warp -- 8 lanes per pair for the L2 norm (4 pairs per warp), 32 lanes per pair for the

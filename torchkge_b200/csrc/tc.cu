@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
     //   (eps is increasing in the candidate's norm bound), hence
     //   f >  T_hi = (st + E)            [L2: (qn + st + E) / 2]  =>  s(q,c) >  s_true : count
     //   f <  T_lo = (st - E)            [L2: (qn + st - E) / 2]  =>  s(q,c) <  s_true : skip
-    //   otherwise near-tie: exact recheck.  T_hi is rounded up, T_lo down.
+    //   otherwise (including any NaN) near-tie: exact recheck.  T_hi is rounded up, T_lo down.
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // query row within the tile
     const int col_half = (warp - 2) >> 2;     // which 128 columns of the tile this warp handles
@@ -348,7 +348,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
           if constexpr (L2) { t_hi = __fmul_ru(t_hi, 0.5f); t_lo = __fmul_rd(t_lo, 0.5f); }
         }
         // 32 independent threshold tests -> two bit masks per thread (no per-element branches)
-        unsigned ge_mask = 0, gt_mask = 0, amb_mask = 0;
+        // (NaN / inf anywhere -- accumulator, thresholds, norm bounds -- fails both tests and lands
+        // in the near-tie list, i.e. is adjudicated by the exact arithmetic)
+        unsigned lt_mask = 0, gt_mask = 0, amb_mask = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float f = __uint_as_float(v[j]);
@@ -357,10 +359,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
               p.dump[(size_t)q * p.n_rows + ct * BN + c0 + j] = L2 ? fmaf(2.f, f, -qn) : f;
           } else {
             gt_mask |= (f > t_hi ? 1u : 0u) << j;
-            ge_mask |= (f >= t_lo ? 1u : 0u) << j;
+            lt_mask |= (f < t_lo ? 1u : 0u) << j;
           }
         }
-        amb_mask = ge_mask & ~gt_mask;
+        amb_mask = ~(gt_mask | lt_mask);
         if constexpr (!DUMP) {
           if (lim < 32) {  // columns past the table (last tile only)
             const unsigned keep = (1u << lim) - 1u;
@@ -564,7 +566,7 @@ __global__ void recheck_kernel(int dim, const unsigned long long* __restrict__ r
                                int32_t* __restrict__ counts) {
   constexpr int QW = ElemTraits<EL>::QW, CW = ElemTraits<EL>::CW;
   constexpr bool NORM = ElemTraits<EL>::RED == RED_NORM2;
-  constexpr int PAIRS_PER_WARP = 1;  // the whole warp on one pair: one 128-byte line per row and step
+  constexpr int PAIRS_PER_WARP = NORM ? 4 : 1;
   const unsigned long long region = blockIdx.y;
   const unsigned long long n_pairs = min(region_counts[region], region_cap);
   const int lane = threadIdx.x & 31;
@@ -583,17 +585,15 @@ __global__ void recheck_kernel(int dim, const unsigned long long* __restrict__ r
     return;
   }
   for (unsigned long long base = warp_global * PAIRS_PER_WARP; base < n_pairs; base += n_warps * PAIRS_PER_WARP) {
-    const unsigned long long i = base;
+    const unsigned long long i = base + (NORM ? (lane >> 3) : 0);
     const bool valid = i < n_pairs;
     const int2 pr = list[valid ? i : base];  // idle groups redo the first pair (shuffles stay uniform)
     const float* q0 = qplain + (size_t)pr.x * QW * dim;
     const float* q1 = q0 + (size_t)(QW - 1) * dim;
     const float* c0 = ent0 + (size_t)pr.y * dim;
     const float* c1 = (CW == 2 ? ent1 : ent0) + (size_t)pr.y * dim;
-    float sc;
-    if constexpr (NORM) sc = pair_score_norm2_warp<EL>(dim, q0, q1, c0, c1, lane);
-    else sc = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane);
-    const bool leader = lane == 0;
+    const float sc = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane);
+    const bool leader = NORM ? ((lane & 7) == 0) : (lane == 0);
     if (valid && leader && sc >= s_true[pr.x]) atomicAdd(&counts[pr.x], 1);
   }
 }

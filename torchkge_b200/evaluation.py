@@ -239,3 +239,66 @@ class RelationPredictionEvaluator(object):
             int(self.mean_rank()[0]), int(self.mean_rank()[1])))
         print('MRR : {} \t\t Filt. MRR : {}'.format(
             round(self.mrr()[0], n_digits), round(self.mrr()[1], n_digits)))
+
+
+class TripletClassificationEvaluator(object):
+    """Evaluate an embedding model by triplet classification (Socher et al. 2013),
+    torchkge/evaluation.py:428-580: one threshold per relation (the best-scoring negative of the
+    validation facts of that relation), then accuracy on the test facts and their negatives.
+
+    Scores come from ``model.scoring_function`` (the CUDA per-triple scorer), negatives from
+    ``PositionalNegativeSampler(kg_val, kg_test=kg_test)`` as in the reference; ``sampler`` may be
+    replaced after construction.
+    """
+
+    def __init__(self, model, kg_val, kg_test):
+        from .sampling import PositionalNegativeSampler
+        self.model = model
+        self.kg_val = kg_val
+        self.kg_test = kg_test
+        self.is_cuda = next(self.model.parameters()).is_cuda
+        self.evaluated = False
+        self.thresholds = None
+        self.sampler = PositionalNegativeSampler(self.kg_val, kg_test=self.kg_test)
+
+    def get_scores(self, heads, tails, relations, batch_size):
+        """Scores of the given triplets, computed batch by batch (evaluation.py:478-511)."""
+        if not self.is_cuda:
+            raise _lib.KgeLibraryError("TripletClassificationEvaluator needs the model on a CUDA device")
+        dev = next(self.model.parameters()).device
+        scores = []
+        with torch.no_grad():
+            for lo in range(0, heads.shape[0], batch_size):
+                sl = slice(lo, lo + batch_size)
+                scores.append(self.model.scoring_function(heads[sl].to(dev), tails[sl].to(dev),
+                                                          relations[sl].to(dev)))
+        return torch.cat(scores, dim=0)
+
+    def evaluate(self, b_size):
+        """Thresholds from the validation graph (evaluation.py:513-541): for relation i the largest
+        score among the negatives of its validation facts; relations absent from the validation set
+        get the largest negative score overall."""
+        r_idx = self.kg_val.relations
+        neg_heads, neg_tails = self.sampler.corrupt_kg(b_size, self.is_cuda, which='main')
+        neg_scores = self.get_scores(neg_heads, neg_tails, r_idx, b_size)
+        n_rel = self.kg_val.n_rel
+        r_dev = r_idx.to(neg_scores.device)
+        per_rel = torch.full((n_rel,), -float("inf"), device=neg_scores.device)
+        per_rel = per_rel.scatter_reduce(0, r_dev, neg_scores, reduce="amax", include_self=True)
+        present = torch.bincount(r_dev, minlength=n_rel) > 0
+        self.thresholds = torch.where(present, per_rel, neg_scores.max()).detach().cpu()
+        self.evaluated = True
+
+    def accuracy(self, b_size):
+        """Share of test facts scored above, and of their negatives scored below, the threshold
+        of their relation (evaluation.py:543-580)."""
+        if not self.evaluated:
+            self.evaluate(b_size)
+        r_idx = self.kg_test.relations
+        neg_heads, neg_tails = self.sampler.corrupt_kg(b_size, self.is_cuda, which='test')
+        scores = self.get_scores(self.kg_test.head_idx, self.kg_test.tail_idx, r_idx, b_size)
+        neg_scores = self.get_scores(neg_heads, neg_tails, r_idx, b_size)
+        if self.is_cuda:
+            self.thresholds = self.thresholds.to(scores.device)
+        thr = self.thresholds[r_idx.to(self.thresholds.device)]
+        return ((scores > thr).sum().item() + (neg_scores < thr).sum().item()) / (2 * self.kg_test.n_facts)

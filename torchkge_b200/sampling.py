@@ -145,3 +145,79 @@ class BernoulliNegativeSampler(NegativeSampler):
         return fused_margin_step(model, heads, tails, relations, margin, n_neg=n_neg,
                                  bern_probs=self.bern_probs, seed=self.seed,
                                  offset=self._next_offset())
+
+
+class PositionalNegativeSampler(BernoulliNegativeSampler):
+    """Positional negative sampler (Socher et al. 2013), torchkge/sampling.py:330-503: head or tail
+    by Bernoulli(p_r) as in Wang et al. 2014; the replacement is drawn uniformly among the entities
+    that occupy the same position in some fact of the same relation (in ``kg`` and ``kg_val``, not
+    ``kg_test``); a relation never seen gets a uniform entity.  Always one negative per fact.
+
+    The reference walks Python lists fact by fact (sampling.py:476-501); here the candidate sets are
+    two CSR arrays on the device and a batch is three gathers.  Draws come from a ``torch.Generator``
+    on the batch's device (seeded by ``seed``): same law as the reference, not the same stream.
+
+    Attributes: ``possible_heads`` / ``possible_tails`` (dict relation -> sorted list),
+    ``n_poss_heads`` / ``n_poss_tails`` (LongTensor (n_rel,)), as in the reference.
+    """
+
+    def __init__(self, kg, kg_val=None, kg_test=None, seed=None):
+        super().__init__(kg, kg_val, kg_test, 1, seed=seed)
+        graphs = [kg] + ([kg_val] if kg_val is not None and kg_val.n_facts > 0 else [])
+        h = torch.cat([g.head_idx for g in graphs]).long()
+        t = torch.cat([g.tail_idx for g in graphs]).long()
+        r = torch.cat([g.relations for g in graphs]).long()
+        self._csr = {}
+        for name, e in (("heads", h), ("tails", t)):
+            key = torch.unique(r * self.n_ent + e)               # sorted by (relation, entity)
+            rel_of, ent_of = torch.div(key, self.n_ent, rounding_mode="floor"), key % self.n_ent
+            counts = torch.bincount(rel_of, minlength=kg.n_rel)
+            offs = torch.zeros(kg.n_rel + 1, dtype=torch.int64)
+            offs[1:] = torch.cumsum(counts, 0)
+            self._csr[name] = (offs, ent_of, counts)
+        self.n_poss_heads, self.n_poss_tails = self._csr["heads"][2], self._csr["tails"][2]
+        self._dev = {}
+        self._gen = {}
+
+    def _lists(self, name):
+        offs, ents, _ = self._csr[name]
+        return {rel: ents[offs[rel]:offs[rel + 1]].tolist() for rel in range(self.kg.n_rel)}
+
+    @property
+    def possible_heads(self):
+        return self._lists("heads")
+
+    @property
+    def possible_tails(self):
+        return self._lists("tails")
+
+    def _on(self, dev):
+        if dev not in self._dev:
+            self._dev[dev] = {k: tuple(x.to(dev) for x in v) for k, v in self._csr.items()}
+            g = torch.Generator(device=dev)
+            g.manual_seed(self.seed & 0x7FFFFFFFFFFFFFFF)
+            self._gen[dev] = g
+        return self._dev[dev], self._gen[dev]
+
+    def corrupt_batch(self, heads, tails, relations, n_neg=None):
+        dev = heads.device
+        assert dev == tails.device
+        if not heads.is_cuda:
+            raise _lib.KgeLibraryError("corrupt_batch needs CUDA index tensors; there is no CPU path")
+        csr, gen = self._on(dev)
+        self.bern_probs = self.bern_probs.to(dev)
+        rel = relations.long()
+        b = heads.shape[0]
+        head_mask = torch.rand(b, device=dev, generator=gen) < self.bern_probs[rel]
+        u = torch.rand(b, device=dev, generator=gen)
+        any_ent = torch.randint(0, self.n_ent, (b,), device=dev, generator=gen)
+        out = []
+        for name, orig, mask in (("heads", heads.long(), head_mask), ("tails", tails.long(), ~head_mask)):
+            offs, ents, counts = csr[name]
+            n_poss = counts[rel]
+            choice = (n_poss.float() * u).floor().long().clamp_(max=(n_poss - 1).clamp(min=0))
+            pos = (offs[rel] + choice).clamp_(max=max(ents.numel() - 1, 0))
+            drawn = ents[pos] if ents.numel() > 0 else any_ent
+            drawn = torch.where(n_poss > 0, drawn, any_ent)
+            out.append(torch.where(mask, drawn, orig))
+        return out[0], out[1]
