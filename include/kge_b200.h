@@ -191,6 +191,10 @@ typedef struct {
 } kge_rank_args_t;
 
 #define KGE_FLAG_TENSOR_CORE 1 /* use the tensor-core bound-and-refine scan when the model has one */
+#define KGE_FLAG_APPROX_SCAN 2 /* RotatE: bound-and-refine on the fp32 pipes -- approximate element
+                                  arithmetic (FMA + MUFU.SQRT, two-level sums) decides every pair
+                                  outside a rigorous relative error band around the true score, the
+                                  rest is re-scored exactly; ranks unchanged.  tc_stats as above. */
 
 /* n_rows / flags only matter for the tensor-core path (near-tie list capacity). */
 size_t kge_rank_workspace_bytes(int model, int side, int dim, int64_t n, int64_t n_rows, int flags);

@@ -155,3 +155,36 @@ def test_every_scan_geometry_gives_oracle_ranks(cfg, kind, d, cuda_device):
     assert len(eng.tc_stats) == 2
     for a, b in zip(got, ref):
         assert torch.equal(a.cpu(), b)
+
+
+@pytest.mark.parametrize("d", [16, 100, 1000])
+@pytest.mark.parametrize("refine", [True, False])
+def test_rotate_bound_and_refine_gives_oracle_ranks(d, refine, cuda_device):
+    """RotatE has no tensor-core form: its bound-and-refine (KGE_FLAG_APPROX_SCAN) runs on the fp32
+    pipes with approximate square roots; ranks must equal the oracle's with it on and off, and the
+    near-tie band must stay small."""
+    # the CPU oracle's RotatE is slow (stack + norm over (b, n_ent, d)): keep d * n_ent * n_test small
+    n_ent, n_rel, n_test = (1500, 9, 300) if d <= 100 else (400, 5, 70)
+    kg, dh, dt = helpers.make_kg(n_ent, n_rel, n_facts=7000 if d <= 100 else 1500, n_test=n_test, seed=200 + d)
+    model = helpers.make_model("rotate", d, n_ent, n_rel, seed=d)
+    with torch.no_grad():
+        model.re_ent_emb.weight[100:200] = model.re_ent_emb.weight[0:100].clone()   # exact ties
+        model.im_ent_emb.weight[100:200] = model.im_ent_emb.weight[0:100].clone()
+    model = model.to(cuda_device)
+    P = helpers.oracle_params("rotate", model)
+    ref = oracle.link_prediction("rotate", P, kg.head_idx, kg.tail_idx, kg.relations, dh, dt, 64)
+    eng = CudaEngine(tensor_core=refine)
+    spec = ModelSpec.from_model(model)
+    dev = cuda_device
+    csr_t = tuple(x.to(dev) for x in filter_csr(dt, kg.head_idx, kg.relations, kg.tail_idx))
+    csr_h = tuple(x.to(dev) for x in filter_csr(dh, kg.tail_idx, kg.relations, kg.head_idx))
+    got = rank_link_prediction(spec, kg.head_idx.to(dev), kg.tail_idx.to(dev), kg.relations.to(dev),
+                               csr_t, csr_h, engine=eng)
+    for a, b in zip(got, ref):
+        assert torch.equal(a.cpu(), b)
+    if refine:
+        assert len(eng.tc_stats) == 2
+        found = sum(int(s[0]) for s in eng.tc_stats)
+        assert 2 * n_test <= found < 0.05 * 2 * n_test * n_ent     # at least the true entities themselves
+    else:
+        assert len(eng.tc_stats) == 0

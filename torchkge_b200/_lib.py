@@ -17,6 +17,7 @@ SIDE_TAIL, SIDE_HEAD, SIDE_REL = 0, 1, 2
 TILE_C, TILE_Q = 128, 64
 ABI_VERSION = 4
 FLAG_TENSOR_CORE = 1
+FLAG_APPROX_SCAN = 2
 LOSS_LOGISTIC, LOSS_BCE = 1, 2
 
 MODEL_NAMES = {TRANSE_L1: "TransE-L1", TRANSE_L2: "TransE-L2", DISTMULT: "DistMult",

@@ -81,6 +81,8 @@ bool tc_supported(int el) {
 bool tc_is_l2(int el) { return el == kge::EL_L2_TAIL || el == kge::EL_L2_HEAD; }
 // contraction length of the operand images: both planes for ComplEx; L2 carries the candidate's
 // squared norm in three extra k slots (tc.h: launch_pack_b)
+// bound-and-refine on the fp32 pipes (approximate element arithmetic + exact recheck): RotatE
+bool approx_supported(int el) { return el == kge::EL_ROT; }
 int tc_k_total(int el, int dim) { return el == kge::EL_DOT2 ? 2 * dim : (tc_is_l2(el) ? dim + 3 : dim); }
 
 Workspace carve(void* base, int qw, int dim, int64_t n, int el = -1, int64_t n_rows = 0,
@@ -100,11 +102,15 @@ Workspace carve(void* base, int qw, int dim, int64_t n, int el = -1, int64_t n_r
   w.code = static_cast<uint8_t*>(take((size_t)dim));
   w.apack = nullptr; w.qbound = w.qnorm2 = nullptr; w.amb_count = nullptr; w.amb_pairs = nullptr;
   w.amb_cap = 0;
-  if ((flags & KGE_FLAG_TENSOR_CORE) && el >= 0 && tc_supported(el) && n_rows > 0) {
+  const bool want_tc = (flags & KGE_FLAG_TENSOR_CORE) && el >= 0 && tc_supported(el) && n_rows > 0;
+  const bool want_approx = (flags & KGE_FLAG_APPROX_SCAN) && approx_supported(el) && n_rows > 0;
+  if (want_tc) {
     const int n_kb = kge::tc::n_kblocks(tc_k_total(el, dim));
     w.apack = static_cast<unsigned char*>(take(kge::tc::a_image_bytes(n, n_kb)));
     w.qbound = static_cast<float*>(take((size_t)n * sizeof(float)));
     w.qnorm2 = static_cast<float*>(take((size_t)n * sizeof(float)));
+  }
+  if (want_tc || want_approx) {
     const int64_t n_tc_qt = (n + kge::tc::TC_BM - 1) / kge::tc::TC_BM;
     w.amb_count = static_cast<unsigned long long*>(take((size_t)n_tc_qt * sizeof(unsigned long long)));
     // near-tie list, one region per query tile: room for 1/128 of all pairs (the band is
@@ -309,7 +315,9 @@ int kge_rank_side(const kge_rank_args_t* a) {
   const bool use_tc = (a->flags & KGE_FLAG_TENSOR_CORE) && tc_supported(el) && a->n_rows > 0;
   if (use_tc && !a->tc_packed) return fail(KGE_ERR_ARG, "kge_rank_side: tc_packed required with KGE_FLAG_TENSOR_CORE");
   if (!use_tc && !a->packed) return fail(KGE_ERR_ARG, "kge_rank_side: packed table required (scalar scan)");
-  Workspace w = carve(a->workspace, qw, a->dim, a->n, el, a->n_rows, use_tc ? KGE_FLAG_TENSOR_CORE : 0);
+  const bool use_approx = !use_tc && (a->flags & KGE_FLAG_APPROX_SCAN) && approx_supported(el) && a->n_rows > 0;
+  Workspace w = carve(a->workspace, qw, a->dim, a->n, el, a->n_rows,
+                      use_tc ? KGE_FLAG_TENSOR_CORE : (use_approx ? KGE_FLAG_APPROX_SCAN : 0));
   if (w.bytes > a->workspace_bytes) return fail(KGE_ERR_ARG, "kge_rank_side: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   const bool casc = hs->s.has_cascade;
@@ -391,7 +399,29 @@ int kge_rank_side(const kge_rank_args_t* a) {
     p.n_rows = a->n_rows;
     p.n_ct = (a->n_rows + kge::TILE_C - 1) / kge::TILE_C;
     p.n_qt = n_qt;
-    KGE_CUDA_TRY(timed_scan(el, casc, p, st), "rank scan");
+    p.amb_count = nullptr; p.amb_pairs = nullptr; p.amb_cap = 0; p.rel_eps = 0.f; p.abs_eps = 0.f;
+    if (use_approx) {
+      // RotatE bound-and-refine: |s~ - s_ATen| <= rel_eps |s~| (all terms >= 0).  Per element the
+      // exact path is within 4 u and the approximate one within 3 u + 2^-21 (sqrt.approx) of the
+      // real modulus; the sums add depth * u each: ATen's cascade (schedule_depth) for the exact
+      // path, 32 per stage + one per stage for the approximate one.
+      const int regions = (int)((a->n + kge::tc::TC_BM - 1) / kge::tc::TC_BM);
+      const unsigned long long region_cap = w.amb_cap / (unsigned long long)regions;
+      KGE_CUDA_TRY(cudaMemsetAsync(w.amb_count, 0, (size_t)regions * sizeof(unsigned long long), st), "approx reset list");
+      const int depth_a = 32 + (a->dim + 31) / 32, depth_e = kge::schedule_depth(hs->s);
+      p.amb_count = w.amb_count; p.amb_pairs = w.amb_pairs; p.amb_cap = region_cap;
+      p.rel_eps = (float)((depth_a + depth_e + 4 + 11 + 8) * 0x1p-24 * 1.001);
+      p.abs_eps = (float)(a->dim * 1.1e-19);
+      KGE_CUDA_TRY(timed_launch(0, st, [&] { return kge::launch_scan(el, casc, p, st, true); }), "approx rank scan");
+      KGE_CUDA_TRY(timed_launch(2, st, [&] {
+                     return kge::tc::launch_recheck(el, a->dim, w.amb_count, regions, region_cap, w.amb_pairs,
+                                                    w.qplain, a->ent0, a->ent1, w.s_true, a->raw_count,
+                                                    reinterpret_cast<unsigned long long*>(a->tc_stats), st);
+                   }),
+                   "approx recheck");
+    } else {
+      KGE_CUDA_TRY(timed_scan(el, casc, p, st), "rank scan");
+    }
 
     if (a->filt_offs && a->n_filt > 0)
       KGE_CUDA_TRY(kge::launch_filter(el, casc, a->dim, a->n, a->n_filt, w.qplain, a->ent0, a->ent1,
@@ -459,6 +489,7 @@ int kge_score_all(const kge_score_all_args_t* a) {
   p.s_true = w.s_true;
   p.code_host = hs->s.code.data();
   p.counts = nullptr;
+  p.amb_count = nullptr; p.amb_pairs = nullptr; p.amb_cap = 0; p.rel_eps = 0.f; p.abs_eps = 0.f;
   p.scores = a->scores;
   p.dim = a->dim;
   p.n_q = a->n;

@@ -29,6 +29,13 @@ struct ScanParams {
   const uint8_t* code_host;  // [dim] schedule codes (HOST pointer; copied into `code` at launch)
   int32_t* counts;       // [n_q] (+=) or nullptr
   float* scores;         // [n_q][n_rows] or nullptr
+  // bound-and-refine form (RotatE): approximate element arithmetic, pairs whose approximate
+  // score is within rel_eps * |score| of s_true go to the near-tie list (regions of 128 queries)
+  unsigned long long* amb_count;  // [ceil(n_q / 128)] or nullptr (exact scan)
+  int2* amb_pairs;                // [regions][amb_cap]
+  unsigned long long amb_cap;
+  float rel_eps;
+  float abs_eps;   // flushed subnormal terms: dim * 1.1e-19
   int dim;
   int64_t n_q;
   int64_t n_rows;
@@ -39,7 +46,9 @@ struct ScanParams {
 };
 
 // dense scan: counts[q] += #{c < n_rows : score(q,c) >= s_true[q]}  (or writes scores)
-cudaError_t launch_scan(int el, bool cascade, const ScanParams& p, cudaStream_t stream);
+// approx = true (EL_ROT only): the bound-and-refine form above; p.amb_* and p.rel_eps must be set
+cudaError_t launch_scan(int el, bool cascade, const ScanParams& p, cudaStream_t stream,
+                        bool approx = false);
 
 // packed[ct][pos][plane][TILE_C] <- ent_plane[row][perm[pos]]
 cudaError_t launch_pack_table(const float* ent0, const float* ent1, int planes, int64_t n_rows,

@@ -60,6 +60,18 @@ __device__ __forceinline__ float elem_value(float q0, float q1, float c0, float 
   }
 }
 
+// Approximate element for the bound-and-refine scan (EL_ROT): fused multiply-add and the
+// hardware's approximate square root (MUFU), any association -- the result only has to be within
+// a known relative error of the exactly rounded one.
+__device__ __forceinline__ float elem_rot_fast(float q0, float q1, float c0, float c1) {
+  const float dr = q0 - c0, di = q1 - c1;
+  float r;
+  // .ftz: a squared modulus below 2^-126 reads as 0 -- an absolute error below 1.1e-19 per term,
+  // carried by the scan's thresholds (ScanParams::abs_eps)
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(di, di, dr * dr)));
+  return r;
+}
+
 template <int EL>
 __device__ __forceinline__ constexpr bool elem_is_l2() {
   return EL == EL_L2_TAIL || EL == EL_L2_HEAD;

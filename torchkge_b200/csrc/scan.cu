@@ -45,7 +45,13 @@ struct Cfg {
       (size_t)STAGES * STAGE_FLOATS * sizeof(float) + 2 * STAGES * sizeof(uint64_t);
 };
 
-template <int EL, bool CASC, int G>
+// APPROX (EL_ROT): bound-and-refine form.  The element is evaluated with FMA + MUFU.SQRT and
+// summed in two levels (per 32-position stage, then across stages: depth <= 32 + dim/32), which is
+// within  rel_eps * |s|  of the exactly rounded ATen-order score because every term is >= 0; pairs
+// that the approximate score cannot place on one side of s_true go to the near-tie list and are
+// re-scored exactly (tc.cu: recheck_kernel<EL_ROT>).  The exact form pays ~16 fp32 instructions
+// per element for the correctly rounded sqrt; this one 6 + one MUFU.
+template <int EL, bool CASC, int G, bool APPROX>
 __global__ void __launch_bounds__(Cfg<EL, G>::THREADS, 1)
     scan_kernel(const __grid_constant__ ScanParams p) {
   using L = Cfg<EL, G>;
@@ -111,9 +117,10 @@ __global__ void __launch_bounds__(Cfg<EL, G>::THREADS, 1)
   uint32_t phase = 0;
   long long cur_qt = -1;
   float st[TQ];
+  float t_hi[TQ], t_lo[TQ];  // APPROX only
   int cnt[TQ];
 #pragma unroll
-  for (int i = 0; i < TQ; ++i) { st[i] = 0.f; cnt[i] = 0; }
+  for (int i = 0; i < TQ; ++i) { st[i] = 0.f; cnt[i] = 0; t_hi[i] = t_lo[i] = 0.f; }
 
   auto flush_counts = [&](long long qt) {
     if (p.counts == nullptr || qt < 0) return;
@@ -137,6 +144,16 @@ __global__ void __launch_bounds__(Cfg<EL, G>::THREADS, 1)
       cur_qt = qt;
 #pragma unroll
       for (int i = 0; i < TQ; ++i) st[i] = p.s_true[qt * TILE_Q + q_off + i];
+      if constexpr (APPROX) {
+        // scores are <= 0 (minus a sum of moduli), |s_exact - s~| <= g |s~|:
+        //   s~ > st / (1 + g)  =>  s > st ;  s~ < st / (1 - g)  =>  s < st   (directed rounding)
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
+          t_hi[i] = __fadd_ru(__fdiv_ru(st[i], 1.f + p.rel_eps), p.abs_eps);
+          t_lo[i] = __fadd_rd(__fdiv_rd(st[i], 1.f - p.rel_eps), -p.abs_eps);
+          if (st[i] > 0.f) { t_hi[i] = INFINITY; t_lo[i] = -INFINITY; }  // cannot happen; stay exact
+        }
+      }
     }
 
     Acc acc[TQ][TC];
@@ -199,7 +216,15 @@ __global__ void __launch_bounds__(Cfg<EL, G>::THREADS, 1)
           if (code & SC_T_ADD_A) { KGE_FOR_PAIRS(acc_t_add_a(acc[i][c])) }
         }
       };
-      {
+      if constexpr (APPROX) {
+#pragma unroll 4
+        for (int kk = 0; kk < kn; ++kk) {
+          float qv[QW][TQ], cv[CW][TC];
+          load_operands(kk, qv, cv);
+          KGE_FOR_PAIRS(acc[i][c].a += elem_rot_fast(qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c]))
+        }
+        KGE_FOR_PAIRS(acc[i][c].t += acc[i][c].a; acc[i][c].a = 0.f)
+      } else {
         // run-length form: branch-free unrolled runs of ordinary positions between flagged ones
         uint32_t m = special;
         int kk = 0;
@@ -241,6 +266,27 @@ __global__ void __launch_bounds__(Cfg<EL, G>::THREADS, 1)
           if (c < p.n_rows) row[c] = acc_finish<EL>(acc[i][j]);
         }
       }
+    } else if constexpr (APPROX) {
+      const bool edge = (ct * TILE_C + TILE_C > p.n_rows);
+#pragma unroll
+      for (int j = 0; j < TC; ++j) {
+        const long long c = c_base + 32 * (j / 4) + (j % 4);
+        const bool valid = !edge || (c < p.n_rows);
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
+          const float s = -acc[i][j].t;
+          const bool gt = s > t_hi[i], lt = s < t_lo[i];
+          cnt[i] += (valid && gt) ? 1 : 0;
+          if (valid && !gt && !lt) {  // near-tie (or NaN): exact recheck decides
+            const long long q = qt * TILE_Q + q_off + i;
+            if (q < p.n_q) {
+              const long long region = q / 128;
+              const unsigned long long slot = atomicAdd(p.amb_count + region, 1ull);
+              if (slot < p.amb_cap) p.amb_pairs[(size_t)region * p.amb_cap + slot] = make_int2((int)q, (int)c);
+            }
+          }
+        }
+      }
     } else {
       const bool edge = (ct * TILE_C + TILE_C > p.n_rows);
 #pragma unroll
@@ -258,7 +304,7 @@ __global__ void __launch_bounds__(Cfg<EL, G>::THREADS, 1)
   flush_counts(cur_qt);
 }
 
-template <int EL, bool CASC, int G>
+template <int EL, bool CASC, int G, bool APPROX = false>
 cudaError_t launch_one(ScanParams& p, cudaStream_t stream) {
   using L = Cfg<EL, G>;
   // stage masks: which positions are NOT the plain "accumulate" code of this reduction kind
@@ -271,7 +317,7 @@ cudaError_t launch_one(ScanParams& p, cudaStream_t stream) {
     p.mask[kc] = m;
   }
   static bool configured = false;  // benign race: attribute set is idempotent
-  auto kern = scan_kernel<EL, CASC, G>;
+  auto kern = scan_kernel<EL, CASC, G, APPROX>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)L::SMEM_BYTES);
@@ -291,7 +337,12 @@ cudaError_t launch_one(ScanParams& p, cudaStream_t stream) {
 }
 
 template <int G>
-cudaError_t launch_scan_g(int el, bool cascade, ScanParams& p, cudaStream_t stream) {
+cudaError_t launch_scan_g(int el, bool cascade, ScanParams& p, cudaStream_t stream, bool approx) {
+  if (approx) {
+    if (el != EL_ROT || p.amb_count == nullptr || p.amb_pairs == nullptr || p.scores != nullptr)
+      return cudaErrorInvalidValue;
+    return cascade ? launch_one<EL_ROT, true, G, true>(p, stream) : launch_one<EL_ROT, false, G, true>(p, stream);
+  }
   switch (el) {
     case EL_DOT1:
       return cascade ? launch_one<EL_DOT1, true, G>(p, stream) : launch_one<EL_DOT1, false, G>(p, stream);
@@ -311,13 +362,13 @@ cudaError_t launch_scan_g(int el, bool cascade, ScanParams& p, cudaStream_t stre
 
 }  // namespace
 
-cudaError_t launch_scan(int el, bool cascade, const ScanParams& p_in, cudaStream_t stream) {
+cudaError_t launch_scan(int el, bool cascade, const ScanParams& p_in, cudaStream_t stream, bool approx) {
   if (p_in.dim < 1 || p_in.dim > SCAN_MAX_DIM - 1 || p_in.code_host == nullptr)
     return cudaErrorInvalidValue;
   ScanParams p = p_in;
   memcpy(p.code, p_in.code_host, (size_t)p.dim);
   // Thread tile 4 x 4 pairs, 16 warps per CTA (measured best on B200; G = 2 gives 4 x 8 / 8 warps).
-  return launch_scan_g<1>(el, cascade, p, stream);
+  return launch_scan_g<1>(el, cascade, p, stream, approx);
 }
 
 }  // namespace kge

@@ -752,6 +752,7 @@ cudaError_t launch_recheck(int el, int dim, const unsigned long long* region_cou
     case EL_DOT2: CALL_RC(EL_DOT2); break;
     case EL_L2_TAIL: CALL_RC(EL_L2_TAIL); break;
     case EL_L2_HEAD: CALL_RC(EL_L2_HEAD); break;
+    case EL_ROT: CALL_RC(EL_ROT); break;
     default: return cudaErrorInvalidValue;
   }
 #undef CALL_RC

@@ -177,17 +177,19 @@ class CudaEngine:
 
     def rank_side(self, spec, packed, side, hrows, trows, r_idx, true_idx, filt, raw_count,
                   filt_sub, true_score=None, tc_packed=None, tc_dump=None, true_rows=None,
-                  true_score_in=None):
+                  true_score_in=None, approx=False):
         """Adds this shard's counts for one side into raw_count / filt_sub (int32, device)."""
         n = r_idx.shape[0] if r_idx is not None else hrows.shape[0]
         dev = raw_count.device
         flags = _lib.FLAG_TENSOR_CORE if tc_packed is not None else 0
+        if tc_packed is None and approx and spec.code == _lib.ROTATE:
+            flags = _lib.FLAG_APPROX_SCAN
         ws_bytes = self.lib.kge_rank_workspace_bytes(spec.code, side, spec.dim, n, spec.n_rows, flags)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         a = _lib.RankArgs()
         a.model, a.side, a.dim, a.flags = spec.code, side, spec.dim, flags
         stats = None
-        if tc_packed is not None:
+        if flags:
             stats = torch.zeros(2, dtype=torch.int64, device=dev)
             a.tc_packed, a.tc_stats, a.tc_dump = _ptr(tc_packed), _ptr(stats), _ptr(tc_dump)
             self.tc_stats.append(stats)
@@ -320,6 +322,8 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
         packed = engine.pack(spec)   # scalar-scan layout: only when there is no tensor-core path
     mark("pack")
     dev = spec.ent0.device
+    # RotatE has no tensor-core form; its bound-and-refine runs on the fp32 pipes (KGE_FLAG_APPROX_SCAN)
+    refine = (tc_packed is None and spec.code == _lib.ROTATE and getattr(engine, "tensor_core", False))
     counters = torch.zeros((4, n), dtype=torch.int32, device=dev)  # raw_t, sub_t, raw_h, sub_h
     pending = []
     for lo in range(0, n, chunk):
@@ -336,6 +340,9 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
             if tc_packed is not None:
                 handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
                                           raw[lo:hi], sub[lo:hi], tc_packed=tc_packed)
+            elif refine:
+                handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
+                                          raw[lo:hi], sub[lo:hi], approx=True)
             else:
                 handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
                                           raw[lo:hi], sub[lo:hi])
@@ -349,8 +356,8 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
         if filts[which] is not None:
             engine.filter_side(handle, _csr_slice(filts[which], lo, hi, n), sub[lo:hi])
     mark("filters enqueued")
-    if tc_packed is not None:
-        # the near-tie list of a tensor-core call is bounded; on overflow (never seen on real
+    if tc_packed is not None or refine:
+        # the near-tie list of a bound-and-refine call is bounded; on overflow (never seen on real
         # or synthetic embeddings, possible on adversarial ones) redo that side exactly
         for handle, which, lo, hi, sub, side, (hrows, trows, r, true_idx) in pending:
             stats = handle[6]
