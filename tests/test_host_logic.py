@@ -132,3 +132,65 @@ def test_filter_index_equals_dictionary_semantics():
     assert kg.filter_index is not None
     assert all(kg.dict_of_tails[k] == v for k, v in dt.items())   # lazily materialised dicts
     assert all(kg.dict_of_heads[k] == v for k, v in dh.items())
+
+
+def test_positional_sampler_candidate_sets_match_reference_definition():
+    """possible_heads / possible_tails (sampling.py:371-409, operations.py get_possible_heads_tails):
+    entities seen at that position with that relation in kg and kg_val, not kg_test."""
+    h, t, r = helpers.random_graph(60, 4, 400, seed=2)
+    mk = lambda a, b: tk.KnowledgeGraph(h[a:b], t[a:b], r[a:b], 60, 4, dict_of_heads={}, dict_of_tails={})  # noqa: E731
+    kg, kg_val, kg_test = mk(0, 250), mk(250, 330), mk(330, 400)
+    s = tk.PositionalNegativeSampler(kg, kg_val=kg_val, kg_test=kg_test, seed=1)
+    hh, tt, rr = (torch.cat([kg.head_idx, kg_val.head_idx]), torch.cat([kg.tail_idx, kg_val.tail_idx]),
+                  torch.cat([kg.relations, kg_val.relations]))
+    for rel in range(4):
+        assert s.possible_heads[rel] == sorted(set(hh[rr == rel].tolist()))
+        assert s.possible_tails[rel] == sorted(set(tt[rr == rel].tolist()))
+    assert s.n_poss_heads.tolist() == [len(s.possible_heads[i]) for i in range(4)]
+    assert s.n_neg == 1 and s.bern_probs.shape == (4,)
+    with pytest.raises(_lib.KgeLibraryError):
+        s.corrupt_batch(kg.head_idx, kg.tail_idx, kg.relations)   # CPU tensors: no CPU path
+
+
+def test_inference_mask_csr_and_arguments():
+    from torchkge_b200.inference import _mask_csr
+    d = {(1, 0): {5, 7}, (2, 1): set(), (3, 0): {9}}
+    offs, ids = _mask_csr(d, torch.tensor([1, 2, 4, 3]), torch.tensor([0, 1, 0, 0]))
+    assert offs.tolist() == [0, 2, 2, 2, 3]
+    assert sorted(ids[:2].tolist()) == [5, 7] and ids[2].item() == 9
+    model = helpers.make_model("distmult", 8, 20, 3)
+    with pytest.raises(tk.WrongArgumentsError):
+        tk.EntityInference(model, torch.arange(4), torch.zeros(4, dtype=torch.long), missing="neither")
+    inf = tk.EntityInference(model, torch.arange(4), torch.zeros(4, dtype=torch.long), top_k=3)
+    assert inf.predictions.shape == (4, 3) and inf.scores.shape == (4, 3)
+    with pytest.raises(_lib.KgeLibraryError):
+        inf.evaluate(b_size=2)        # CPU model: refused loudly
+
+
+def test_relation_evaluator_and_knowledge_graph_dict_of_rels():
+    h = torch.tensor([0, 0, 1, 2]); t = torch.tensor([1, 1, 2, 0]); r = torch.tensor([0, 1, 0, 2])
+    kg = tk.KnowledgeGraph(h, t, r, 3, 3)
+    assert kg.dict_of_rels[(0, 1)] == {0, 1} and kg.dict_of_rels[(2, 0)] == {2}
+    kg.dict_of_rels = {(0, 1): {0}}
+    assert kg.dict_of_rels == {(0, 1): {0}}
+    ev = tk.RelationPredictionEvaluator(helpers.make_model("distmult", 8, 3, 3), kg, directed=False)
+    assert ev.rank_true_rels.shape == (4,) and not ev.evaluated and ev.directed is False
+    with pytest.raises(tk.NotYetEvaluatedError):
+        ev.hit_at_k(1)
+    with pytest.raises(_lib.KgeLibraryError):
+        ev.evaluate(b_size=2)
+
+
+def test_relation_side_element_kinds_and_flags():
+    lib = _lib.load()
+    assert lib.kge_query_planes(_lib.DISTMULT, _lib.SIDE_REL) == 2      # (h, t) around the candidate
+    assert lib.kge_query_planes(_lib.TRANSE_L2, _lib.SIDE_REL) == 2
+    assert lib.kge_query_planes(_lib.COMPLEX, _lib.SIDE_REL) == 2
+    assert lib.kge_query_planes(_lib.RESCAL, _lib.SIDE_REL) == 0         # not on the relation path
+    assert lib.kge_query_planes(_lib.ROTATE, _lib.SIDE_REL) == 0
+    # the bound-and-refine flags only change the workspace of the models that have such a path
+    base = lib.kge_rank_workspace_bytes(_lib.ROTATE, _lib.SIDE_TAIL, 64, 256, 50000, 0)
+    assert lib.kge_rank_workspace_bytes(_lib.ROTATE, _lib.SIDE_TAIL, 64, 256, 50000, _lib.FLAG_APPROX_SCAN) > base
+    assert lib.kge_rank_workspace_bytes(_lib.ROTATE, _lib.SIDE_TAIL, 64, 256, 50000, _lib.FLAG_TENSOR_CORE) == base
+    l1 = lib.kge_rank_workspace_bytes(_lib.TRANSE_L1, _lib.SIDE_TAIL, 64, 256, 50000, 0)
+    assert lib.kge_rank_workspace_bytes(_lib.TRANSE_L1, _lib.SIDE_TAIL, 64, 256, 50000, 3) == l1
