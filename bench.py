@@ -438,8 +438,9 @@ def run_ours(args, rank, local, world):
         alg_bytes_per_launch = float(q_hi - q_lo) * rows_here * rb
         scan_ms_per_launch = scan_ms / max(1, scan_n)
         achieved = alg_bytes_per_launch / (scan_ms_per_launch / 1000.0) / 1e9
+        refine_rot = code == _lib.ROTATE and eng.tensor_core   # approximate-sqrt bound-and-refine scan
         ops_per_elem = {_lib.TRANSE_L1: 2.5, _lib.TRANSE_L2: 3.5, _lib.DISTMULT: 2.0, _lib.RESCAL: 2.0,
-                        _lib.COMPLEX: 4.0, _lib.ROTATE: 7.0}[code]  # mean of tail/head fp32 ops per (q,c,k)
+                        _lib.COMPLEX: 4.0, _lib.ROTATE: 5.0 if refine_rot else 16.0}[code]  # fp32 ops per (q,c,k)
         lane_ops = float(q_hi - q_lo) * rows_here * dim * ops_per_elem
         fp32_peak = 148 * 128 * sm_mhz * 1e6
         roofline = {
@@ -456,6 +457,14 @@ def run_ours(args, rank, local, world):
                            "frac": lane_ops / (scan_ms_per_launch / 1000.0) / fp32_peak,
                            "ops_per_element": ops_per_elem},
         }
+        if refine_rot:
+            # one MUFU.SQRT per element at 16 per clock and SM is the binding unit of this form
+            elems = float(q_hi - q_lo) * rows_here * dim
+            mufu_peak = 148 * 16 * sm_mhz * 1e6
+            roofline["mufu"] = {"achieved_telem": elems / (scan_ms_per_launch / 1000.0) / 1e12,
+                                "peak_telem": mufu_peak / 1e12,
+                                "frac": elems / (scan_ms_per_launch / 1000.0) / mufu_peak}
+            roofline["kernel"] = "scan_kernel<EL_ROT, APPROX> (approximate-sqrt bound-and-refine, fp32 pipes + MUFU)"
 
     # ---- CPU baseline (oracle port) on a bounded sample + parity on that sample -----------
     cpu = None
