@@ -1,0 +1,94 @@
+"""CPU checks of the error bounds the bound-and-refine scans rest on (csrc/tc.h, csrc/api.cu).
+
+Two of the three terms of `tc_gamma` are pure arithmetic facts that need no GPU:
+  * split:  x = hi + lo + r with two bf16 roundings; dropping lo*lo and the residuals costs at
+            most 3 * 2^-16 * sum|a_k b_k|
+  * ref:    the reference's own fp32 evaluation (products rounded once, summed in ATen's order) is
+            within (depth + 4) * 2^-24 * sum|a_k b_k| of the real dot product, `depth` being
+            kge_schedule_depth of the schedule the exact kernels replay;
+            for the L2 norm: within (depth + 10) * 2^-24 of sum x_k^2 (relative)
+(the third, the tensor core's fp32 accumulation, is measured on the GPU by tests/test_tc_gpu.py).
+Random and adversarial (cancelling, wide dynamic range) vectors; float64 is the yardstick.
+"""
+import numpy as np
+import pytest
+import torch
+
+from torchkge_b200 import _lib
+
+
+def _bf16_round(x):
+    """round-to-nearest-even to bfloat16, returned as float32 (numpy)"""
+    return torch.from_numpy(x.astype(np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def _vectors(rng, n, d, kind):
+    a = rng.standard_normal((n, d)).astype(np.float32)
+    b = rng.standard_normal((n, d)).astype(np.float32)
+    if kind == "cancelling":          # products of alternating sign and equal magnitude
+        b = np.abs(b) * np.where(np.arange(d) % 2 == 0, 1, -1).astype(np.float32) * np.sign(a + 1e-30)
+    elif kind == "wide":              # 2^-20 .. 2^20 dynamic range
+        a *= np.exp2(rng.integers(-20, 21, (n, d))).astype(np.float32)
+        b *= np.exp2(rng.integers(-20, 21, (n, d))).astype(np.float32)
+    elif kind == "normalised":
+        a /= np.linalg.norm(a, axis=1, keepdims=True)
+        b /= np.linalg.norm(b, axis=1, keepdims=True)
+    return a, b
+
+
+@pytest.mark.parametrize("kind", ["normalised", "cancelling", "wide"])
+@pytest.mark.parametrize("d", [13, 64, 200, 800])
+def test_bf16_split_term_of_the_bound(kind, d):
+    rng = np.random.default_rng(d)
+    a, b = _vectors(rng, 400, d, kind)
+    a_hi = _bf16_round(a); a_lo = _bf16_round(a - a_hi)
+    b_hi = _bf16_round(b); b_lo = _bf16_round(b - b_hi)
+    A, B = a.astype(np.float64), b.astype(np.float64)
+    kept = (a_hi.astype(np.float64) * b_hi + a_lo.astype(np.float64) * b_hi
+            + a_hi.astype(np.float64) * b_lo).sum(1)            # what the three MMAs add up, exactly
+    exact = (A * B).sum(1)
+    bound = 3.0 * 2.0 ** -16 * (np.abs(A) * np.abs(B)).sum(1)
+    assert (np.abs(kept - exact) <= bound).all()
+    assert (bound <= 3.0 * 2.0 ** -16 * np.linalg.norm(A, axis=1) * np.linalg.norm(B, axis=1) * (1 + 1e-12)).all()
+
+
+@pytest.mark.parametrize("kind", ["normalised", "cancelling", "wide"])
+@pytest.mark.parametrize("d", [7, 13, 64, 200, 400, 1000])
+def test_reference_sum_is_within_depth_times_u_of_the_real_dot(kind, d):
+    """DistMult-style `(q * c).sum(dim=-1)` in ATen vs float64, against (depth + 4) u sum|terms|."""
+    lib = _lib.load()
+    depth = lib.kge_schedule_depth(_lib.DISTMULT, d)
+    assert depth >= 0
+    rng = np.random.default_rng(100 + d)
+    a, b = _vectors(rng, 300, d, kind)
+    ta, tb = torch.from_numpy(a), torch.from_numpy(b)
+    ref = (ta.view(300, 1, d) * tb.view(300, 1, d)).sum(dim=2).view(-1).double().numpy()
+    exact = (a.astype(np.float64) * b.astype(np.float64)).sum(1)
+    bound = (depth + 4) * 2.0 ** -24 * (np.abs(a.astype(np.float64)) * np.abs(b.astype(np.float64))).sum(1)
+    assert (np.abs(ref - exact) <= bound).all(), float((np.abs(ref - exact) / bound).max())
+
+
+@pytest.mark.parametrize("kind", ["normalised", "wide"])
+@pytest.mark.parametrize("d", [8, 50, 200, 203, 1000])
+def test_reference_l2_norm_is_within_depth_times_u(kind, d):
+    """`(q - c).norm(p=2, dim=-1) ** 2` in ATen vs float64, against (depth + 10) u sum x^2."""
+    lib = _lib.load()
+    depth = lib.kge_schedule_depth(_lib.TRANSE_L2, d)
+    rng = np.random.default_rng(200 + d)
+    a, b = _vectors(rng, 300, d, kind)
+    ta, tb = torch.from_numpy(a), torch.from_numpy(b)
+    ref = ((ta.view(300, 1, d) - tb.view(300, 1, d)).norm(p=2, dim=-1) ** 2).view(-1).double().numpy()
+    x = a.astype(np.float64) - b.astype(np.float64)
+    exact = (x * x).sum(1)
+    assert (np.abs(ref - exact) <= (depth + 10) * 2.0 ** -24 * exact).all()
+
+
+def test_gamma_formulas_match_the_header():
+    """The Python mirror of tc.h used by tests/test_tc_gpu.py, pinned to a few known values."""
+    lib = _lib.load()
+    d = 200
+    depth_sum, depth_norm = lib.kge_schedule_depth(_lib.DISTMULT, d), lib.kge_schedule_depth(_lib.TRANSE_L2, d)
+    assert (depth_sum, depth_norm) == (16, 31)
+    gamma_dot = 3 * 2.0 ** -16 + 2 * (3 * 13 + 2) * 2.0 ** -22 + (depth_sum + 4) * 2.0 ** -24
+    assert gamma_dot == pytest.approx(6.652e-5, rel=1e-3)
+    assert (depth_norm + 42) * 2.0 ** -24 == pytest.approx(4.351e-6, rel=1e-3)
