@@ -1,4 +1,4 @@
-"""Scratch perf probe: time the rank scan for one side on random tables (device-resident)."""
+"""Perf probe: time the rank scan of one side on random tables (device-resident), per model; QP_MODELS selects (l2,l1,dm,cx,rot,rot1k), QP_TC=0 forces the exact scalar scan."""
 import sys, time
 import torch
 sys.path.insert(0, '.')
