@@ -368,6 +368,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
             const unsigned keep = (1u << lim) - 1u;
             amb_mask &= keep; gt_mask &= keep;
           }
+          // padding rows of the last query tile have no list entries (their thresholds are +inf,
+          // but a non-finite candidate norm bound turns them into NaN, which fails both tests)
+          if (q >= p.n_q) amb_mask = 0u;
           cnt += __popc(gt_mask);
           if (__any_sync(0xffffffffu, amb_mask != 0)) {
             // near-ties in this 32 x 32 block: warp prefix sum of the per-lane counts, entries
