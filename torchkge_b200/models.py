@@ -106,9 +106,12 @@ def _as_planes(x):
 
 def _dense_scores(model, h, t, r):
     hp, tp, rp = _as_planes(h), _as_planes(t), _as_planes(r)
+    if (rp[0].dim() == 3 and hp[0].dim() == 2 and tp[0].dim() == 2
+            and type(model).__name__ != "RESCALModel"):
+        return _dense_relation_scores(model, hp, tp, rp)
     if rp[0].dim() != 2 and not (type(model).__name__ == "RESCALModel" and rp[0].dim() == 3):
         raise NotImplementedError("relation-prediction scoring (candidate relations) is not on "
-                                  "the CUDA path")
+                                  "the CUDA path for this model")
     if tp[0].dim() == 3 and hp[0].dim() == 2:
         side, cand, ent = _lib.SIDE_TAIL, tp, hp
     elif hp[0].dim() == 3 and tp[0].dim() == 2:
@@ -138,6 +141,34 @@ def _dense_scores(model, h, t, r):
     packed = model._packed_cache[1]
     rows = torch.stack([x.detach().contiguous() for x in ent], dim=1).contiguous()  # (b, planes, d)
     return eng.score_all(spec, packed, side, rows, rows, None)
+
+
+def _dense_relation_scores(model, hp, tp, rp):
+    """The relation case of ``inference_scoring_function`` (interfaces.py:261-272,
+    bilinear.py:241-245, 524-528): ``r`` is the (b, n_rel, d) candidates tensor returned by
+    ``inference_prepare_candidates(..., entities=False)``; scores of (h, c, t) for every relation c,
+    from ``kge_score_all`` with ``KGE_SIDE_REL`` (same arithmetic as RelationPredictionEvaluator)."""
+    from .engine import relation_spec
+    for c in rp:
+        if c.shape[0] > 1 and c.stride(0) != 0:
+            raise NotImplementedError("per-row candidate tensors are not supported: pass the "
+                                      "tensor returned by inference_prepare_candidates")
+    if not hp[0].is_cuda:
+        raise _lib.KgeLibraryError("inference_scoring_function needs CUDA tensors; there is no "
+                                   "CPU fallback")
+    b, n_rel, d = rp[0].shape
+    tables = [c[0].detach().contiguous() for c in rp]
+    code = model._kernel_code()
+    rspec = relation_spec(ModelSpec(code, d, model.n_ent, n_rel, tables[0], None, tables[0],
+                                    tables[1] if len(tables) > 1 else None))
+    eng = default_engine()
+    key = tuple((tb.data_ptr(), tb._version, tuple(tb.shape)) for tb in tables) + (code, "rel")
+    if model._packed_cache is None or model._packed_cache[0] != key:
+        model._packed_cache = (key, eng.pack(rspec))
+    packed = model._packed_cache[1]
+    hrows = torch.stack([x.detach().contiguous() for x in hp], dim=1).contiguous()  # (b, planes, d)
+    trows = torch.stack([x.detach().contiguous() for x in tp], dim=1).contiguous()
+    return eng.score_all(rspec, packed, _lib.SIDE_REL, hrows, trows, None)
 
 
 class TranslationModel(Model):
