@@ -107,7 +107,8 @@ int kge_schedule_depth(int model, int dim);
  * every (query, candidate) pair whose approximate score differs from the true score by more
  * than a rigorous error bound, the remaining near-ties being re-scored exactly -- ranks are
  * unchanged.  kge_tc_pack_table writes the operand image that path streams:
- * [hi/lo bf16 planes in 128-byte-swizzled shared-memory order | per-row norm bounds].
+ * [hi/lo bf16 planes in swizzled shared-memory order (64-byte swizzle spans by default, see
+ * kge_tc_configure) | per-row norm bounds and squared norms].
  * kge_tc_packed_bytes returns 0 for models without such a path (TransE-L1, RotatE). */
 size_t kge_tc_packed_bytes(int model, int64_t n_rows, int dim);
 /* Tuning / test hook of the tensor-core scan (process-wide; defaults also settable through the

@@ -5,19 +5,21 @@
 // last bit: it needs every score to be on the right SIDE of s_true.  This kernel computes an
 // approximation s~(q,c) on the 5th-generation tensor cores -- fp32 operands split into bf16
 // (hi, lo) pairs, three bf16 products per term (hi*hi + lo*hi + hi*lo), fp32 accumulation in
-// TMEM -- together with a rigorous bound eps(q,c) >= |s~ - s_ATen| (tc_bound.h).  Pairs with
-// |s~ - s_true| > eps are decided from s~; the few others (the "near-tie band", ~0.1 % of the
-// pairs) are appended to a list and re-scored exactly, with the ATen-order schedule replay, by
+// TMEM -- together with a rigorous bound eps(q,c) >= |s~ - s_ATen| (tc.h).  Pairs with
+// |s~ - s_true| > eps are decided from s~; the few others (the "near-tie band", 0.06-0.2 % of the
+// pairs) are appended to a list and re-scored exactly, with the ATen-order arithmetic, by
 // recheck_kernel.  Ranks therefore stay bit-identical to the reference's while ~99.9 % of the
 // arithmetic moves from the fp32 pipes to the tensor cores.
 //
-// Kernel shape: persistent CTAs, 6 warps.  Warp 0 (one lane): producer -- 1-D bulk async
-// copies (UBLKCP) of pre-swizzled operand images (the pack kernels write the exact
-// shared-memory image of the 128-byte-swizzled K-major tiles, so no tensor map is needed)
-// into a 2-stage ring.  Warp 1 (one lane): issues tcgen05.mma (M=128 queries x N=256
-// candidates x K=16, bf16 -> f32) into one of two 256-column TMEM accumulators and commits to
-// mbarriers.  Warps 2-5: epilogue -- tcgen05.ld the accumulator (one query row per thread),
-// apply norms / bound / threshold, count, append near-ties.
+// Kernel shape: persistent CTAs of 10 warps, one per SM.  Warp 0 (one lane): producer -- 1-D bulk
+// async copies (UBLKCP) of pre-swizzled operand images (the pack kernels write the exact
+// shared-memory image of K-major swizzled tiles, so no tensor map is needed): k-blocks of 32 bf16
+// (64-byte swizzle) with the query tile's image resident for a whole work unit and the candidate
+// image streaming through a 3-stage ring, or both streamed (4 x 48 KB; 2 x 96 KB with 128-byte
+// swizzle).  Warp 1 (one lane): issues tcgen05.mma (M=128 queries x N=256 candidates x K=16,
+// bf16 -> f32) into one of two 256-column TMEM accumulators and commits to mbarriers.
+// Warps 2-9: epilogue -- tcgen05.ld the accumulator (one query row per thread, two warps per TMEM
+// lane quadrant), compare with two per-thread thresholds, count, append near-ties.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
