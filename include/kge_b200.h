@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 4
+#define KGE_ABI_VERSION 5
 
 /* error codes */
 #define KGE_OK 0
@@ -54,7 +54,12 @@ typedef enum {
   KGE_DISTMULT = 2,  /* torchkge/models/bilinear.py:146 */
   KGE_RESCAL = 3,    /* torchkge/models/bilinear.py:14 */
   KGE_COMPLEX = 4,   /* torchkge/models/bilinear.py:414 */
-  KGE_ROTATE = 5     /* not in the reference; oracle/rotate restatement (Sun et al. 2019) */
+  KGE_ROTATE = 5,    /* not in the reference; oracle/rotate restatement (Sun et al. 2019) */
+  KGE_TORUSE_L1 = 6, /* torchkge/models/translation.py:655 + utils/dissimilarities.py:28-34 (torus_L1);
+                        link-prediction side only (kge_rank_side / kge_score_all), tables already
+                        reduced to their fractional parts (TorusEModel.normalize_parameters) */
+  KGE_TORUSE_L2 = 7  /* same + utils/dissimilarities.py:37-43 (torus_L2); torus_eL2 (cosine) is not
+                        on the path */
 } kge_model_t;
 
 /* Which element of the triple is being completed. */

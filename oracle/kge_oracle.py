@@ -34,7 +34,7 @@ from collections import defaultdict
 
 import torch
 
-KINDS = ("transe_l1", "transe_l2", "distmult", "rescal", "complex", "rotate")
+KINDS = ("transe_l1", "transe_l2", "distmult", "rescal", "complex", "rotate", "toruse_l1", "toruse_l2")
 
 
 # --------------------------------------------------------------------------- dissimilarities
@@ -46,6 +46,16 @@ def l1_diss(a, b):
 def l2_diss(a, b):
     """utils/dissimilarities.py:19-25 -- note: 2-norm first, THEN squared."""
     return (a - b).norm(p=2, dim=-1) ** 2
+
+
+def l1_torus_diss(a, b):
+    """utils/dissimilarities.py:28-34 (TorusE)"""
+    return 2 * torch.min(torch.abs(a - b), 1 - torch.abs(a - b)).sum(dim=-1)
+
+
+def l2_torus_diss(a, b):
+    """utils/dissimilarities.py:37-43 (TorusE)"""
+    return 4 * torch.min((a - b) ** 2, 1 - (a - b) ** 2).sum(dim=-1)
 
 
 # --------------------------------------------------------------------------- all-entity scores
@@ -61,8 +71,11 @@ def scores_all(kind, P, h_idx, t_idx, r_idx, side):
     """
     b = h_idx.shape[0]
     tail = side == "tail"
-    if kind in ("transe_l1", "transe_l2"):
-        diss = l1_diss if kind == "transe_l1" else l2_diss
+    if kind in ("transe_l1", "transe_l2", "toruse_l1", "toruse_l2"):
+        # TorusE (translation.py:655-767) is TransE's inference_scoring_function on tables that
+        # hold fractional parts (normalize_parameters), with the torus dissimilarities
+        diss = {"transe_l1": l1_diss, "transe_l2": l2_diss, "toruse_l1": l1_torus_diss,
+                "toruse_l2": l2_torus_diss}[kind]
         E, R = P["ent"], P["rel"]
         d = E.shape[1]
         cand = E.view(1, -1, d).expand(b, -1, d)

@@ -11,6 +11,8 @@ KIND_TO_CLASS = {
     "rescal": lambda d, ne, nr: tk.RESCALModel(d, ne, nr),
     "complex": lambda d, ne, nr: tk.ComplExModel(d, ne, nr),
     "rotate": lambda d, ne, nr: tk.RotatEModel(d, ne, nr),
+    "toruse_l1": lambda d, ne, nr: tk.TorusEModel(d, ne, nr, dissimilarity_type="torus_L1"),
+    "toruse_l2": lambda d, ne, nr: tk.TorusEModel(d, ne, nr, dissimilarity_type="torus_L2"),
 }
 
 
@@ -26,6 +28,9 @@ def oracle_params(kind, model):
     planes are computed there, and libm results differ between CPU and GPU in the last ulp."""
     g = lambda w: w.detach().cpu().clone()  # noqa: E731
     if kind in ("transe_l1", "transe_l2", "distmult"):
+        return {"ent": g(model.ent_emb.weight), "rel": g(model.rel_emb.weight)}
+    if kind in ("toruse_l1", "toruse_l2"):
+        model.normalize_parameters()      # the tables the evaluator reads hold fractional parts
         return {"ent": g(model.ent_emb.weight), "rel": g(model.rel_emb.weight)}
     if kind == "rescal":
         return {"ent": g(model.ent_emb.weight), "rel_mat": g(model.rel_mat.weight)}
@@ -115,6 +120,25 @@ def load_golden_rel(name):
     z = np.load(os.path.join(GOLDEN_DIR, "rel_" + name + ".npz"), allow_pickle=False)
     out = {k: z[k] for k in z.files}
     out["dr"] = _arrays_to_dict(z["dr_keys"], z["dr_offs"], z["dr_vals"])
+    return out
+
+
+TORUS_CASES = ["torus_l1", "torus_l2"]
+
+
+def load_golden_torus(name):
+    """TorusE fixture (tests/golden/make_golden_torus.py): same layout as load_golden, without the
+    training-side arrays."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    g = {k: z[k] for k in z.files}
+    out = {"kind": str(g["kind"]), "dim": int(g["dim"]), "n_ent": int(g["n_ent"]),
+           "n_rel": int(g["n_rel"]), "b_size": int(g["b_size"]), "raw": g}
+    out["state"] = {k[2:]: torch.from_numpy(v.copy()) for k, v in g.items() if k.startswith("w:")}
+    out["P"] = {_STATE_TO_ORACLE[k]: v for k, v in out["state"].items()}
+    for k in ("heads", "tails", "rels"):
+        out[k] = torch.from_numpy(g[k].copy()).long()
+    out["dh"] = _arrays_to_dict(g["dh_keys"], g["dh_offs"], g["dh_vals"])
+    out["dt"] = _arrays_to_dict(g["dt_keys"], g["dt_offs"], g["dt_vals"])
     return out
 
 

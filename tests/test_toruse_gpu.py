@@ -1,0 +1,63 @@
+"""TorusE (torus_L1 / torus_L2) link prediction on the GPU against the unmodified reference's
+golden outputs (tests/golden/torus_*.npz) and the oracle.
+
+These tests were written after round 1's GPU budget was spent: the element kinds compile and the
+oracle is pinned on the CPU (tests/test_oracle_golden.py::test_toruse_matches_reference), but the
+kernels have not run on a B200 yet -- hence xfail(strict=False): a pass is reported as XPASS."""
+import pytest
+import torch
+
+import torchkge_b200 as tk
+from oracle import kge_oracle as oracle
+from tests import helpers
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(reason="TorusE kernels not yet run on a B200 (added after the round's "
+                                       "GPU budget was spent)", strict=False)]
+
+
+def _model(g, dev):
+    diss = "torus_L1" if g["kind"] == "toruse_l1" else "torus_L2"
+    model = tk.TorusEModel(g["dim"], g["n_ent"], g["n_rel"], diss)
+    model.load_state_dict(g["state"])
+    return model.to(dev)
+
+
+@pytest.mark.parametrize("case", helpers.TORUS_CASES)
+def test_ranks_equal_the_unmodified_reference(case, cuda_device):
+    g = helpers.load_golden_torus(case)
+    model = _model(g, cuda_device)
+    kg = tk.KnowledgeGraph(g["heads"], g["tails"], g["rels"], g["n_ent"], g["n_rel"],
+                           dict_of_heads=g["dh"], dict_of_tails=g["dt"])
+    ev = tk.LinkPredictionEvaluator(model, kg)
+    ev.evaluate(b_size=g["b_size"], verbose=False)
+    for nm in ("rank_true_heads", "rank_true_tails", "filt_rank_true_heads", "filt_rank_true_tails"):
+        assert torch.equal(getattr(ev, nm), torch.from_numpy(g["raw"][nm])), nm
+    h, t, r = (g[k][:8].to(cuda_device) for k in ("heads", "tails", "rels"))
+    he, te, re_, cands = model.inference_prepare_candidates(h, t, r, entities=True)
+    assert helpers.bits_equal(model.inference_scoring_function(he, cands, re_),
+                              torch.from_numpy(g["raw"]["scores_tail"])).all()
+    assert helpers.bits_equal(model.inference_scoring_function(cands, te, re_),
+                              torch.from_numpy(g["raw"]["scores_head"])).all()
+    got = model.scoring_function(g["heads"].to(cuda_device), g["tails"].to(cuda_device), g["rels"].to(cuda_device))
+    torch.testing.assert_close(got.cpu(), torch.from_numpy(g["raw"]["triple_scores"]), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind,d", [("toruse_l1", 13), ("toruse_l2", 64), ("toruse_l1", 520)])
+def test_ranks_equal_oracle(kind, d, cuda_device):
+    n_ent, n_rel = 700, 6
+    kg, dh, dt = helpers.make_kg(n_ent, n_rel, n_facts=4000, n_test=200, seed=31 + d)
+    model = helpers.make_model(kind, d, n_ent, n_rel, seed=d)
+    with torch.no_grad():
+        model.ent_emb.weight.mul_(37.0)
+        model.rel_emb.weight.mul_(37.0)
+        model.normalize_parameters()
+        model.ent_emb.weight[50:90] = model.ent_emb.weight[0:40].clone()   # exact ties
+    model = model.to(cuda_device)
+    P = helpers.oracle_params(kind, model)
+    ref = oracle.link_prediction(kind, P, kg.head_idx, kg.tail_idx, kg.relations, dh, dt, 64)
+    ev = tk.LinkPredictionEvaluator(model, kg)
+    ev.evaluate(b_size=64, verbose=False)
+    for got, want in zip((ev.rank_true_heads, ev.rank_true_tails, ev.filt_rank_true_heads,
+                          ev.filt_rank_true_tails), ref):
+        assert torch.equal(got, want)

@@ -29,13 +29,15 @@ int elem_kind_for(int model, int side) {
     case KGE_RESCAL: return EL_DOT1;
     case KGE_COMPLEX: return EL_DOT2;
     case KGE_ROTATE: return EL_ROT;
+    case KGE_TORUSE_L1: return tail ? EL_TL1_TAIL : EL_TL1_HEAD;
+    case KGE_TORUSE_L2: return tail ? EL_TL2_TAIL : EL_TL2_HEAD;
     default: return -1;
   }
 }
 
 int elem_qw(int el) {
   switch (el) {
-    case EL_DOT1: case EL_L1_TAIL: case EL_L2_TAIL: return 1;
+    case EL_DOT1: case EL_L1_TAIL: case EL_L2_TAIL: case EL_TL1_TAIL: case EL_TL2_TAIL: return 1;
     default: return 2;
   }
 }
@@ -136,7 +138,9 @@ __global__ void prep_queries_kernel(int model, int side, int dim, long long n,
   const long long r = r_idx ? r_idx[i] : i;  // null r_idx: rel tables hold one row per query
   switch (model) {
     case KGE_TRANSE_L1:
-    case KGE_TRANSE_L2: {
+    case KGE_TRANSE_L2:
+    case KGE_TORUSE_L1:
+    case KGE_TORUSE_L2: {
       const float rv = rel0[(size_t)r * dim + k];
       if (tail) {
         qplain[(size_t)i * dim + k] = __fadd_rn(hrows[(size_t)i * dim + k], rv);
@@ -392,6 +396,10 @@ cudaError_t launch_fill_f32(float* dst, float value, int64_t n, cudaStream_t str
     case EL_DOT2: if (cascade) { CALL(EL_DOT2, true); } else { CALL(EL_DOT2, false); } break; \
     case EL_ROT: if (cascade) { CALL(EL_ROT, true); } else { CALL(EL_ROT, false); } break;    \
     case EL_DOT_MID: if (cascade) { CALL(EL_DOT_MID, true); } else { CALL(EL_DOT_MID, false); } break; \
+    case EL_TL1_TAIL: if (cascade) { CALL(EL_TL1_TAIL, true); } else { CALL(EL_TL1_TAIL, false); } break; \
+    case EL_TL1_HEAD: if (cascade) { CALL(EL_TL1_HEAD, true); } else { CALL(EL_TL1_HEAD, false); } break; \
+    case EL_TL2_TAIL: if (cascade) { CALL(EL_TL2_TAIL, true); } else { CALL(EL_TL2_TAIL, false); } break; \
+    case EL_TL2_HEAD: if (cascade) { CALL(EL_TL2_HEAD, true); } else { CALL(EL_TL2_HEAD, false); } break; \
     case EL_L1_TAIL: CALL(EL_L1_TAIL, false); break;                        \
     case EL_L1_HEAD: CALL(EL_L1_HEAD, false); break;                        \
     case EL_L2_TAIL: CALL(EL_L2_TAIL, false); break;                        \

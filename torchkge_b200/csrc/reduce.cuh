@@ -22,7 +22,12 @@ enum ElemKind : int {
   EL_L2_HEAD = 5,  // ((c0 + q0) - q1)^2         interfaces.py:258-260 + dissimilarities.py:25
   EL_ROT = 6,      // sqrt((q0-c0)^2+(q1-c1)^2)  oracle RotatE restatement
   EL_DOT_MID = 7,  // (q0*c0)*q1                 DistMult relation prediction, bilinear.py:243-245
-  EL_COUNT = 8
+  // TorusE (translation.py:655-767), x = q0 - c0 (tail) or (c0 + q0) - q1 (head):
+  EL_TL1_TAIL = 8,   // 2*min(|x|, 1-|x|)         dissimilarities.py:28-34
+  EL_TL1_HEAD = 9,
+  EL_TL2_TAIL = 10,  // 4*min(x^2, 1-x^2)         dissimilarities.py:37-43
+  EL_TL2_HEAD = 11,
+  EL_COUNT = 12
 };
 
 template <int EL> struct ElemTraits;
@@ -34,6 +39,13 @@ template <> struct ElemTraits<EL_L2_TAIL> { static constexpr int QW = 1, CW = 1,
 template <> struct ElemTraits<EL_L2_HEAD> { static constexpr int QW = 2, CW = 1, RED = RED_NORM2; };
 template <> struct ElemTraits<EL_ROT> { static constexpr int QW = 2, CW = 2, RED = RED_SUM; };
 template <> struct ElemTraits<EL_DOT_MID> { static constexpr int QW = 2, CW = 1, RED = RED_SUM; };
+template <> struct ElemTraits<EL_TL1_TAIL> { static constexpr int QW = 1, CW = 1, RED = RED_SUM; };
+template <> struct ElemTraits<EL_TL1_HEAD> { static constexpr int QW = 2, CW = 1, RED = RED_SUM; };
+template <> struct ElemTraits<EL_TL2_TAIL> { static constexpr int QW = 1, CW = 1, RED = RED_SUM; };
+template <> struct ElemTraits<EL_TL2_HEAD> { static constexpr int QW = 2, CW = 1, RED = RED_SUM; };
+
+// torch.min(a, b) element-wise: NaN propagates (ATen minimum), otherwise the smaller
+__device__ __forceinline__ float aten_min(float a, float b) { return (a != a || a < b) ? a : b; }
 
 // For the L2 kinds returns the difference x (the caller squares it, fused or not); for all
 // other kinds returns the finished term.
@@ -53,6 +65,16 @@ __device__ __forceinline__ float elem_value(float q0, float q1, float c0, float 
     return __fsub_rn(__fadd_rn(c0, q0), q1);
   } else if constexpr (EL == EL_DOT_MID) {
     return __fmul_rn(__fmul_rn(q0, c0), q1);
+  } else if constexpr (EL == EL_TL1_TAIL || EL == EL_TL1_HEAD) {
+    // 2 * min(abs(a - b), 1 - abs(a - b)) summed: the factor is applied per element in the
+    // reference (exact in fp32), before the cascade sum
+    const float x = EL == EL_TL1_TAIL ? __fsub_rn(q0, c0) : __fsub_rn(__fadd_rn(c0, q0), q1);
+    const float ax = fabsf(x);
+    return __fmul_rn(2.f, aten_min(ax, __fsub_rn(1.f, ax)));
+  } else if constexpr (EL == EL_TL2_TAIL || EL == EL_TL2_HEAD) {
+    const float x = EL == EL_TL2_TAIL ? __fsub_rn(q0, c0) : __fsub_rn(__fadd_rn(c0, q0), q1);
+    const float x2 = __fmul_rn(x, x);
+    return __fmul_rn(4.f, aten_min(x2, __fsub_rn(1.f, x2)));
   } else {  // EL_ROT
     const float dr = __fsub_rn(q0, c0);
     const float di = __fsub_rn(q1, c1);

@@ -28,7 +28,9 @@ int reduce_kind_for_model(int model) {
     case KGE_DISTMULT:
     case KGE_RESCAL:
     case KGE_COMPLEX:
-    case KGE_ROTATE: return RED_SUM;
+    case KGE_ROTATE:
+    case KGE_TORUSE_L1:
+    case KGE_TORUSE_L2: return RED_SUM;
     default: return -1;
   }
 }

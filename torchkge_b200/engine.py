@@ -71,6 +71,16 @@ class ModelSpec:
                 raise NotImplementedError("TransE dissimilarity %s is not on the CUDA path" % dname)
             return cls(code, model.emb_dim, model.n_ent, model.n_rel,
                        f(model.ent_emb.weight), None, f(model.rel_emb.weight), None)
+        if name == "TorusEModel":
+            dname = getattr(model.dissimilarity, "__name__", str(model.dissimilarity))
+            code = {"l1_torus_dissimilarity": _lib.TORUSE_L1, "l2_torus_dissimilarity": _lib.TORUSE_L2,
+                    "l1_dissimilarity": _lib.TRANSE_L1}.get(dname)
+            if code is None:
+                raise NotImplementedError("TorusE dissimilarity %s is not on the CUDA path" % dname)
+            if not getattr(model, "normalized", False):
+                model.normalize_parameters()   # as inference_prepare_candidates does (translation.py:745-746)
+            return cls(code, model.emb_dim, model.n_ent, model.n_rel,
+                       f(model.ent_emb.weight), None, f(model.rel_emb.weight), None)
         if name == "DistMultModel":
             return cls(_lib.DISTMULT, model.emb_dim, model.n_ent, model.n_rel,
                        f(model.ent_emb.weight), None, f(model.rel_emb.weight), None)
@@ -86,8 +96,8 @@ class ModelSpec:
             return cls(_lib.ROTATE, model.emb_dim, model.n_ent, model.n_rel,
                        f(model.re_ent_emb.weight), f(model.im_ent_emb.weight), f(re_r), f(im_r))
         raise NotImplementedError(
-            "%s has no CUDA link-prediction path (supported: TransE L1/L2, DistMult, RESCAL, "
-            "ComplEx, RotatE)" % name)
+            "%s has no CUDA link-prediction path (supported: TransE L1/L2, TorusE torus_L1/torus_L2, "
+            "DistMult, RESCAL, ComplEx, RotatE)" % name)
 
 
 def _ptr(t):

@@ -171,8 +171,19 @@ def _dense_relation_scores(model, hp, tp, rp):
     return eng.score_all(rspec, packed, _lib.SIDE_REL, hrows, trows, None)
 
 
+def l1_torus_dissimilarity(a, b):
+    """torchkge/utils/dissimilarities.py:28-34 (also the selector of the torus-L1 kernels)."""
+    return 2 * torch.min(torch.abs(a - b), 1 - torch.abs(a - b)).sum(dim=-1)
+
+
+def l2_torus_dissimilarity(a, b):
+    """torchkge/utils/dissimilarities.py:37-43 (also the selector of the torus-L2 kernels)."""
+    return 4 * torch.min((a - b) ** 2, 1 - (a - b) ** 2).sum(dim=-1)
+
+
 class TranslationModel(Model):
-    """torchkge/models/interfaces.py:177-272; only 'L1' and 'L2' have kernels."""
+    """torchkge/models/interfaces.py:177-272; 'L1', 'L2', 'torus_L1' and 'torus_L2' have kernels
+    ('torus_eL2' goes through a cosine and is not on the CUDA path)."""
 
     def __init__(self, n_entities, n_relations, dissimilarity_type):
         super().__init__(n_entities, n_relations)
@@ -181,8 +192,12 @@ class TranslationModel(Model):
             self.dissimilarity = l1_dissimilarity
         elif dissimilarity_type == 'L2':
             self.dissimilarity = l2_dissimilarity
+        elif dissimilarity_type == 'torus_L1':
+            self.dissimilarity = l1_torus_dissimilarity
+        elif dissimilarity_type == 'torus_L2':
+            self.dissimilarity = l2_torus_dissimilarity
         else:
-            raise NotImplementedError("torus dissimilarities (TorusE) are outside the CUDA path")
+            raise NotImplementedError("torus_eL2 (cosine-based) is outside the CUDA path")
 
 
 class BilinearModel(Model):
@@ -355,3 +370,53 @@ class RotatEModel(BilinearModel):
         r = (torch.cos(ph), torch.sin(ph))
         cands = (self._expand(self.re_ent_emb.weight, b), self._expand(self.im_ent_emb.weight, b))
         return h, t, r, cands
+
+
+class TorusEModel(TranslationModel):
+    """TorusE (Ebisu & Ichise 2018) -- torchkge/models/translation.py:655-767: TransE on the torus
+    [0, 1)^d (all parameters are kept as their fractional parts) with the torus dissimilarities.
+
+    ``dissimilarity_type`` is 'torus_L1' or 'torus_L2' ('L1' on fractional parts is accepted too;
+    'torus_eL2' is not on the CUDA path).  Link prediction (``LinkPredictionEvaluator``,
+    ``inference_scoring_function``, ``EntityInference``) runs on the scan kernels with their own
+    element kinds; ``scoring_function`` (training) is composed from torch ops on the model's device
+    -- TorusE has no hand-written training kernel yet.
+    """
+
+    def __init__(self, emb_dim, n_entities, n_relations, dissimilarity_type):
+        assert dissimilarity_type in ['L1', 'torus_L1', 'torus_L2', 'torus_eL2']
+        super().__init__(n_entities, n_relations, dissimilarity_type)
+        self.emb_dim = emb_dim
+        self.ent_emb = init_embedding(self.n_ent, self.emb_dim)
+        self.rel_emb = init_embedding(self.n_rel, self.emb_dim)
+        self.normalized = False
+        self.normalize_parameters()
+
+    def scoring_function(self, h_idx, t_idx, r_idx):
+        """-dissimilarity(frac(h) + frac(r), frac(t)) (translation.py:706-720)."""
+        self.normalized = False
+        h, t, r = self.ent_emb(h_idx), self.ent_emb(t_idx), self.rel_emb(r_idx)
+        h.data.frac_()
+        t.data.frac_()
+        r.data.frac_()
+        if self.dissimilarity is l1_dissimilarity:
+            return -(h + r - t).norm(p=1, dim=-1)
+        return -self.dissimilarity(h + r, t)
+
+    def normalize_parameters(self):
+        self.ent_emb.weight.data.frac_()
+        self.rel_emb.weight.data.frac_()
+        self.normalized = True
+
+    def get_embeddings(self):
+        self.normalize_parameters()
+        return self.ent_emb.weight.data, self.rel_emb.weight.data
+
+    def inference_prepare_candidates(self, h_idx, t_idx, r_idx, entities=True):
+        b = h_idx.shape[0]
+        if not self.normalized:
+            self.normalize_parameters()
+        h, t, r = self.ent_emb(h_idx), self.ent_emb(t_idx), self.rel_emb(r_idx)
+        cands = self._expand(self.ent_emb.weight if entities else self.rel_emb.weight, b)
+        return h, t, r, cands
+

@@ -88,6 +88,8 @@ class _ScoreTriples(torch.autograd.Function):
 def score_triples(model, h_idx, t_idx, r_idx):
     """``model.scoring_function(h_idx, t_idx, r_idx)`` -> (n,) float scores, differentiable with
     respect to the model's embedding tables."""
+    if type(model).__name__ == "TorusEModel":
+        raise NotImplementedError("TorusE scores triples with torch ops (models.TorusEModel.scoring_function)")
     code = ModelSpec.from_model(model).code
     ent0, ent1, rel0, rel1 = _param_tensors(model, code)
     return _ScoreTriples.apply(code, model.emb_dim, h_idx, t_idx, r_idx, ent0, ent1, rel0, rel1)
@@ -223,6 +225,9 @@ def fused_margin_step(model, heads, tails, relations, margin, n_neg=1, negatives
         loss = criterion(pos, neg)
     without materialising nh, nt, pos, neg.
     """
+    if type(model).__name__ == "TorusEModel":
+        raise NotImplementedError("TorusE has no fused training step (its scoring_function works on "
+                                  "fractional parts, not on L2-normalised rows)")
     spec_code = ModelSpec.from_model(model).code
     ent0, ent1, rel0, rel1 = _param_tensors(model, spec_code)
     nh = nt = None
