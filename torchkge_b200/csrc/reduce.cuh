@@ -90,7 +90,11 @@ __device__ __forceinline__ float elem_rot_fast(float q0, float q1, float c0, flo
   float r;
   // .ftz: a squared modulus below 2^-126 reads as 0 -- an absolute error below 1.1e-19 per term,
   // carried by the scan's thresholds (ScanParams::abs_eps)
+#if defined(__CUDACC__)
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(di, di, dr * dr)));
+#else
+  r = sqrtf(fmaf(di, di, dr * dr));  // host build of this header (tests/host_arith.cpp) only
+#endif
   return r;
 }
 
