@@ -92,3 +92,34 @@ def test_gamma_formulas_match_the_header():
     gamma_dot = 3 * 2.0 ** -16 + 2 * (3 * 13 + 2) * 2.0 ** -22 + (depth_sum + 4) * 2.0 ** -24
     assert gamma_dot == pytest.approx(6.652e-5, rel=1e-3)
     assert (depth_norm + 42) * 2.0 ** -24 == pytest.approx(4.351e-6, rel=1e-3)
+
+
+@pytest.mark.parametrize("d", [16, 200, 1000])
+def test_rotate_two_level_sum_stays_inside_the_relative_bound(d):
+    """RotatE bound-and-refine (csrc/api.cu: rel_eps): an fp32 evaluation with FMA and a two-level
+    sum (32 terms per stage, then the stage sums) is within g |s~| of the ATen-order score, with
+    g = (depth_exact + 32 + ceil(d/32) + 23) * 2^-24.  numpy float32 stands in for the fp32 pipes
+    (its correctly rounded sqrt is inside the 2^-21 allowed for MUFU.SQRT)."""
+    lib = _lib.load()
+    depth_e = lib.kge_schedule_depth(_lib.ROTATE, d)
+    g = (32 + (d + 31) // 32 + depth_e + 4 + 11 + 8) * 2.0 ** -24 * 1.001
+    rng = np.random.default_rng(d)
+    nq, nc = 40, 60
+    q = (rng.random((nq, 2, d)).astype(np.float32) * 2 - 1) * 0.05
+    c = (rng.random((nc, 2, d)).astype(np.float32) * 2 - 1) * 0.05
+    tq, tc_ = torch.from_numpy(q), torch.from_numpy(c)
+    dre = tq[:, 0].view(nq, 1, d) - tc_[:, 0].view(1, nc, d)
+    dim_ = tq[:, 1].view(nq, 1, d) - tc_[:, 1].view(1, nc, d)
+    exact = (-torch.stack([dre, dim_], dim=0).norm(dim=0).sum(dim=2)).numpy().astype(np.float64)
+    dr = (q[:, None, 0, :] - c[None, :, 0, :]).astype(np.float32)
+    di = (q[:, None, 1, :] - c[None, :, 1, :]).astype(np.float32)
+    x = (di.astype(np.float64) * di + (dr * dr).astype(np.float32)).astype(np.float32)   # fma(di, di, dr*dr)
+    m = np.sqrt(x).astype(np.float32)
+    total = np.zeros((nq, nc), dtype=np.float32)
+    for k0 in range(0, d, 32):
+        stage = np.zeros((nq, nc), dtype=np.float32)
+        for k in range(k0, min(d, k0 + 32)):
+            stage = (stage + m[:, :, k]).astype(np.float32)
+        total = (total + stage).astype(np.float32)
+    approx = -total.astype(np.float64)
+    assert (np.abs(approx - exact) <= g * np.abs(approx)).all()
