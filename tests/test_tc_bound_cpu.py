@@ -123,3 +123,79 @@ def test_rotate_two_level_sum_stays_inside_the_relative_bound(d):
         total = (total + stage).astype(np.float32)
     approx = -total.astype(np.float64)
     assert (np.abs(approx - exact) <= g * np.abs(approx)).all()
+
+
+def _tc_constants(k_total, depth, l2):
+    gamma = 3.0 * 2.0 ** -16 + 2.0 * (3.0 * ((k_total + 15) // 16) + 2.0) * 2.0 ** -22 + (0.0 if l2 else (depth + 4.0) * 2.0 ** -24)
+    gamma2 = (depth + 42.0) * 2.0 ** -24
+    return np.float32(gamma), np.float32(gamma2)
+
+
+@pytest.mark.parametrize("l2", [False, True])
+@pytest.mark.parametrize("d", [50, 200])
+def test_threshold_decisions_never_contradict_the_exact_comparison(l2, d):
+    """The tensor-core scan's decision rule (csrc/tc.cu epilogue), restated in numpy: the
+    accumulator f = sum(a_hi b_hi + a_lo b_hi + a_hi b_lo) [L2: - |b|^2/2 from three bf16 pieces],
+    thresholds T_hi / T_lo from the per-block largest candidate bound.  Wherever the rule says
+    "greater" (f > T_hi) the ATen-order score must be >= s_true, wherever it says "smaller"
+    (f < T_lo) it must be < s_true -- on random rows, near-duplicates (near ties) and exact
+    duplicates; and the undecided band must stay small."""
+    lib = _lib.load()
+    model = _lib.TRANSE_L2 if l2 else _lib.DISTMULT
+    depth = lib.kge_schedule_depth(model, d)
+    k_total = d + 3 if l2 else d
+    gamma, gamma2 = _tc_constants(k_total, depth, l2)
+    rng = np.random.default_rng(7 * d + l2)
+    nq, nc = 48, 512
+    a = rng.standard_normal((nq, d)).astype(np.float32)
+    b = rng.standard_normal((nc, d)).astype(np.float32)
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    b[1::7] = b[0:-1:7] * np.float32(1 + 2 ** -20) + np.float32(1e-7) * rng.standard_normal((len(b[1::7]), d)).astype(np.float32)
+    b[2::7] = b[0:-2:7]                                    # exact duplicates
+    ta, tb = torch.from_numpy(a), torch.from_numpy(b)
+    if l2:
+        S = -((ta.view(nq, 1, d) - tb.view(1, nc, d)).norm(p=2, dim=-1) ** 2)
+    else:
+        S = (ta.view(nq, 1, d) * tb.view(1, nc, d)).sum(dim=2)
+    S = S.numpy()
+    true_idx = rng.integers(0, nc, nq)
+    st = S[np.arange(nq), true_idx]
+    a_hi = _bf16_round(a); a_lo = _bf16_round(a - a_hi)
+    b_hi = _bf16_round(b); b_lo = _bf16_round(b - b_hi)
+    f = (a_hi.astype(np.float64) @ b_hi.T.astype(np.float64) + a_lo.astype(np.float64) @ b_hi.T.astype(np.float64)
+         + a_hi.astype(np.float64) @ b_lo.T.astype(np.float64))
+    qb = (np.linalg.norm(a.astype(np.float64), axis=1) * (1 + 1e-6)).astype(np.float32) + np.float32(1e-30)
+    cb = (np.linalg.norm(b.astype(np.float64), axis=1) * (1 + 1e-6)).astype(np.float32) + np.float32(1e-30)
+    infl = np.float32(1 + 2.0 ** -19)
+    if l2:
+        cn = (b.astype(np.float64) ** 2).sum(1).astype(np.float32)
+        qn = (a.astype(np.float64) ** 2).sum(1).astype(np.float32)
+        rest = (-0.5 * cn).astype(np.float32)
+        pieces = np.zeros_like(rest, dtype=np.float64)
+        for _ in range(3):
+            p = _bf16_round(rest)
+            pieces += p
+            rest = (rest - p).astype(np.float32)
+        f = f + pieces[None, :]
+    f = f.astype(np.float32)                                # the fp32 accumulator the epilogue reads
+    up = lambda x: np.nextafter(x.astype(np.float32), np.float32(np.inf))       # noqa: E731
+    down = lambda x: np.nextafter(x.astype(np.float32), np.float32(-np.inf))    # noqa: E731
+    cbmax = cb.reshape(-1, 32).max(1).repeat(32)            # largest bound of each 32-candidate block
+    if l2:
+        k1 = (np.float32(2) * (gamma + gamma2) * qb * infl).astype(np.float32)
+        k0 = (gamma2 * qb * qb * infl).astype(np.float32)
+        E = ((cbmax[None, :] * (gamma2 * infl * cbmax[None, :] + k1[:, None]) + k0[:, None]) * infl).astype(np.float32)
+        base = (qn + st).astype(np.float32)[:, None]
+        t_hi = up(up(base + E) * np.float32(0.5))
+        t_lo = down(down(base - E) * np.float32(0.5))
+    else:
+        E = ((gamma * qb * infl)[:, None] * cbmax[None, :]).astype(np.float32)
+        t_hi = up(st[:, None] + E)
+        t_lo = down(st[:, None] - E)
+    gt, lt = f > t_hi, f < t_lo
+    assert (S[gt] >= np.broadcast_to(st[:, None], S.shape)[gt]).all()
+    assert (S[lt] < np.broadcast_to(st[:, None], S.shape)[lt]).all()
+    amb = ~(gt | lt)
+    assert amb[np.arange(nq), true_idx].all()               # the true entity itself is always rechecked
+    assert amb.mean() < 0.02
