@@ -274,7 +274,8 @@ def l2_policy(wl):
 def run_ours(args, rank, local, world):
     import torch.distributed as dist
     from torchkge_b200 import _lib, synthetic as S
-    from torchkge_b200.engine import (CudaEngine, EntityShard, ModelSpec, rank_link_prediction)
+    from torchkge_b200.engine import (CudaEngine, EntityShard, ModelSpec, QueryShard,
+                                      rank_link_prediction)
     import torchkge_b200.engine as engine_mod
     from torchkge_b200.evaluation import LinkPredictionEvaluator
 
@@ -303,15 +304,12 @@ def run_ours(args, rank, local, world):
     torch.cuda.synchronize()
     csr_build_s = time.perf_counter() - t0
     n_test = graph["test_h"].numel()
-    if mode == "queries":
-        # this rank's contiguous slice of the test set (and of the filter CSRs)
-        per = (n_test + world - 1) // world
-        q_lo, q_hi = min(n_test, rank * per), min(n_test, (rank + 1) * per)
-    else:
-        q_lo, q_hi = 0, n_test
-    from torchkge_b200.engine import _csr_slice
-    my_h, my_t, my_r = (graph[k][q_lo:q_hi].contiguous() for k in ("test_h", "test_t", "test_r"))
-    my_csr_t, my_csr_h = _csr_slice(csr_t, q_lo, q_hi, n_test), _csr_slice(csr_h, q_lo, q_hi, n_test)
+    # this rank's contiguous slice of the test set and of the filter CSRs (all of it unless the
+    # test triples are what is sharded)
+    qshard = QueryShard(n_test, rank, world) if mode == "queries" else QueryShard(n_test, 0, 1)
+    q_lo, q_hi = qshard.lo, qshard.hi
+    my_h, my_t, my_r = qshard.slice(graph["test_h"], graph["test_t"], graph["test_r"])
+    my_csr_t, my_csr_h = qshard.csr(csr_t), qshard.csr(csr_h)
     spec = ModelSpec(code, dim, n_ent, n_rel, tabs["ent0"], tabs["ent1"], tabs["rel0"], tabs["rel1"],
                      ent_lo=lo)
     eng = CudaEngine()
@@ -327,16 +325,7 @@ def run_ours(args, rank, local, world):
 
     def gather_ranks(parts):
         """all ranks' slices -> full-length vectors (query-sharded mode only)"""
-        if mode != "queries":
-            return parts
-        out = []
-        for x in parts:
-            pad = torch.zeros(per, dtype=x.dtype, device=dev)
-            pad[:x.numel()] = x
-            bufs = [torch.empty_like(pad) for _ in range(world)]
-            dist.all_gather(bufs, pad)
-            out.append(torch.cat(bufs)[:n_test])
-        return out
+        return qshard.all_gather(parts) if mode == "queries" else parts
 
     # ---- device-resident timing -------------------------------------------------------
     # clocks / throttle reasons are sampled from the first warm-up step to the end of the timed

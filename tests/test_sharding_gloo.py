@@ -128,3 +128,49 @@ def test_single_process_stand_in_agrees_with_oracle():
                                  kg.head_idx, kg.tail_idx, kg.relations, dh, dt, 64)
     for a, b in zip(out, ref):
         assert torch.equal(a, b)
+
+
+def _worker_queries(rank, world, port, kind, n_test, ret):
+    """The second decomposition (bench.py at N > 1 for tables that fit one GPU): replicated table,
+    test triples split over the ranks, rank vectors all-gathered."""
+    from torchkge_b200.engine import QueryShard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_ent, n_rel, d = 150, 4, 16
+        kg, dh, dt = helpers.make_kg(n_ent, n_rel, n_facts=1200, n_test=n_test, seed=33)
+        model = helpers.make_model(kind, d, n_ent, n_rel, seed=33)
+        spec = ModelSpec.from_model(model)
+        n = kg.n_facts
+        csr_t = filter_csr(dt, kg.head_idx, kg.relations, kg.tail_idx)
+        csr_h = filter_csr(dh, kg.tail_idx, kg.relations, kg.head_idx)
+        qs = QueryShard.from_group(n)
+        h, t, r = qs.slice(kg.head_idx, kg.tail_idx, kg.relations)
+        local = rank_link_prediction(spec, h, t, r, qs.csr(csr_t), qs.csr(csr_h), engine=OracleEngine(),
+                                     chunk=16)
+        assert all(x.shape[0] == qs.hi - qs.lo for x in local)
+        full = qs.all_gather(local)
+        P = helpers.oracle_params(kind, model)
+        ref = oracle.link_prediction(kind, P, kg.head_idx, kg.tail_idx, kg.relations, dh, dt, 30)
+        ret[rank] = bool(all(torch.equal(a, b) for a, b in zip(full, ref)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,n_test,world", [("distmult", 75, 2), ("transe_l1", 1, 2), ("complex", 50, 3)])
+def test_query_sharded_ranking_equals_single_process(kind, n_test, world):
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_queries, args=(world, port, kind, n_test, ret), nprocs=world, join=True)
+    assert dict(ret) == {i: True for i in range(world)}
+
+
+def test_query_shard_bounds():
+    from torchkge_b200.engine import QueryShard
+    for n, world in ((20466, 8), (5, 8), (0, 2), (7, 1)):
+        shards = [QueryShard(n, r, world) for r in range(world)]
+        assert shards[0].lo == 0 and shards[-1].hi == n
+        assert all(a.hi == b.lo for a, b in zip(shards, shards[1:]))
+        assert all(s.hi - s.lo <= s.per for s in shards)

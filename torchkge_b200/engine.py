@@ -295,6 +295,46 @@ class EntityShard:
         return t
 
 
+class QueryShard:
+    """Contiguous split of n test triples over the ranks of a process group, for tables that fit
+    one GPU (second form): the entity table is replicated, every rank ranks
+    ITS triples against all entities -- independent units, no collective on the data path -- and
+    the rank vectors are all-gathered at the end."""
+
+    def __init__(self, n, rank=0, world=1, group=None):
+        self.n, self.rank, self.world, self.group = int(n), rank, world, group
+        self.per = (self.n + world - 1) // world
+        self.lo = min(self.n, rank * self.per)
+        self.hi = min(self.n, (rank + 1) * self.per)
+
+    @classmethod
+    def from_group(cls, n, group=None):
+        import torch.distributed as dist
+        return cls(n, dist.get_rank(group), dist.get_world_size(group), group)
+
+    def slice(self, *tensors):
+        """This rank's rows of each (n,) tensor."""
+        return tuple(x[self.lo:self.hi].contiguous() for x in tensors)
+
+    def csr(self, filt):
+        """This rank's rows of a CSR over the n triples (offsets rebased)."""
+        return None if filt is None else _csr_slice(filt, self.lo, self.hi, self.n)
+
+    def all_gather(self, parts):
+        """Per-rank result vectors (one entry per local triple) -> full-length vectors on every rank."""
+        if self.world == 1:
+            return list(parts)
+        import torch.distributed as dist
+        out = []
+        for x in parts:
+            pad = torch.zeros(self.per, dtype=x.dtype, device=x.device)
+            pad[:x.numel()] = x
+            bufs = [torch.empty_like(pad) for _ in range(self.world)]
+            dist.all_gather(bufs, pad, group=self.group)
+            out.append(torch.cat(bufs)[:self.n])
+        return out
+
+
 def _csr_slice(filt, lo, hi, n):
     """CSR rows [lo, hi) with offsets rebased to 0."""
     offs, ids = filt
