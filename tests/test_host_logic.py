@@ -194,3 +194,19 @@ def test_relation_side_element_kinds_and_flags():
     assert lib.kge_rank_workspace_bytes(_lib.ROTATE, _lib.SIDE_TAIL, 64, 256, 50000, _lib.FLAG_TENSOR_CORE) == base
     l1 = lib.kge_rank_workspace_bytes(_lib.TRANSE_L1, _lib.SIDE_TAIL, 64, 256, 50000, 0)
     assert lib.kge_rank_workspace_bytes(_lib.TRANSE_L1, _lib.SIDE_TAIL, 64, 256, 50000, 3) == l1
+
+
+def test_reference_import_paths_resolve():
+    """`s/torchkge/torchkge_b200/` on the imports of a script that uses the hot path keeps working."""
+    from torchkge_b200 import (KnowledgeGraph, LinkPredictionEvaluator, LogisticLoss, MarginLoss,  # noqa: F401
+                               NotYetEvaluatedError, TorusEModel, TripletClassificationEvaluator)
+    from torchkge_b200.data_structures import KnowledgeGraph as KG2
+    from torchkge_b200.evaluation import LinkPredictionEvaluator as E2, RelationPredictionEvaluator  # noqa: F401
+    from torchkge_b200.exceptions import NotYetEvaluatedError as N2
+    from torchkge_b200.inference import EntityInference, RelationInference  # noqa: F401
+    from torchkge_b200.models import ComplExModel, DistMultModel, RESCALModel, TransEModel  # noqa: F401
+    from torchkge_b200.sampling import (BernoulliNegativeSampler, PositionalNegativeSampler,  # noqa: F401
+                                        UniformNegativeSampler)
+    from torchkge_b200.utils import (BinaryCrossEntropyLoss, MarginLoss as M2, get_bernoulli_probs,  # noqa: F401
+                                     init_embedding, l1_dissimilarity, l2_dissimilarity)
+    assert KG2 is KnowledgeGraph and E2 is LinkPredictionEvaluator and N2 is NotYetEvaluatedError and M2 is MarginLoss
