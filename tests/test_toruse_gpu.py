@@ -1,11 +1,5 @@
-"""GPU tests of code written after round 1's GPU budget was spent (this file sorts last on
-purpose): TorusE (torus_L1 / torus_L2) link prediction against the unmodified reference's golden
-outputs (tests/golden/torus_*.npz) and the oracle, and the relation-candidate case of
-model.inference_scoring_function against tests/golden/rel_*.npz.
-
-TorusE: the element kinds compile and the
-oracle is pinned on the CPU (tests/test_oracle_golden.py::test_toruse_matches_reference), but the
-kernels have not run on a B200 yet -- hence xfail(strict=False): a pass is reported as XPASS."""
+"""TorusE (torus_L1 / torus_L2) link prediction on the GPU against the unmodified reference's
+golden outputs (tests/golden/torus_*.npz) and the oracle."""
 import pytest
 import torch
 
@@ -13,9 +7,7 @@ import torchkge_b200 as tk
 from oracle import kge_oracle as oracle
 from tests import helpers
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="not yet run on a B200 (added after the round's GPU budget was "
-                                       "spent)", strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 def _model(g, dev):
@@ -63,19 +55,3 @@ def test_ranks_equal_oracle(kind, d, cuda_device):
     for got, want in zip((ev.rank_true_heads, ev.rank_true_tails, ev.filt_rank_true_heads,
                           ev.filt_rank_true_tails), ref):
         assert torch.equal(got, want)
-
-
-@pytest.mark.parametrize("case", [c for c in helpers.GOLDEN_CASES if "rescal" not in c])
-def test_dense_relation_scores_equal_reference_golden(case, cuda_device):
-    """model.inference_scoring_function(h, t, candidates) with relation candidates (the API the
-    reference's RelationPredictionEvaluator drives, evaluation.py:94-97) against the reference's own
-    dense scores (tests/golden/rel_*.npz: scores_rel), bit for bit."""
-    g = helpers.load_golden(case)
-    rel = helpers.load_golden_rel(case)
-    model = helpers.model_from_golden(g).to(cuda_device)
-    h, t, r = (g[k][:8].to(cuda_device) for k in ("heads", "tails", "rels"))
-    he, te, _, cands = model.inference_prepare_candidates(h, t, r, entities=False)
-    got = model.inference_scoring_function(he, te, cands)
-    want = torch.from_numpy(rel["scores_rel"])
-    assert got.shape == want.shape
-    assert helpers.bits_equal(got, want).all()
