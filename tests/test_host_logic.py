@@ -210,3 +210,28 @@ def test_reference_import_paths_resolve():
     from torchkge_b200.utils import (BinaryCrossEntropyLoss, MarginLoss as M2, get_bernoulli_probs,  # noqa: F401
                                      init_embedding, l1_dissimilarity, l2_dissimilarity)
     assert KG2 is KnowledgeGraph and E2 is LinkPredictionEvaluator and N2 is NotYetEvaluatedError and M2 is MarginLoss
+
+
+def test_dict_filter_csr_equals_filter_csr_and_caches():
+    """The fast route from the reference's dictionaries (distinct keys flattened once, rows
+    expanded with tensor ops, cached on the graph) gives filter_csr's rows, quirks included."""
+    from torchkge_b200.data import dict_filter_csr
+    h, t, r = helpers.random_graph(200, 5, 3000, seed=4)
+    dh, dt = oracle.build_filter_dicts(h, t, r)
+    g = torch.Generator().manual_seed(1)
+    qh = torch.cat([h[:250], h[:50], torch.randint(0, 200, (120,), generator=g)])   # repeated keys too
+    qt = torch.cat([t[:250], t[:50], torch.randint(0, 200, (120,), generator=g)])
+    qr = torch.cat([r[:250], r[:50], torch.randint(0, 5, (120,), generator=g)])
+    kg = tk.KnowledgeGraph(qh, qt, qr, 200, 5, dict_of_heads=dh, dict_of_tails=dt)
+    for which, d, k1, k2, tr in (("tail", dt, qh, qr, qt), ("head", dh, qt, qr, qh)):
+        o1, i1 = filter_csr(d, k1, k2, tr)
+        o2, i2, nbytes = dict_filter_csr(kg, which, k1, k2, tr, torch.device("cpu"))
+        assert torch.equal(o1, o2) and nbytes > 0
+        for q in range(k1.shape[0]):
+            assert sorted(i1[o1[q]:o1[q + 1]].tolist()) == sorted(i2[o2[q]:o2[q + 1]].tolist())
+        again = dict_filter_csr(kg, which, k1, k2, tr, torch.device("cpu"))
+        assert again[0] is o2 and again[1] is i2          # served from the cache on the graph
+    # editing a dictionary (its size changes) invalidates the cached rows
+    dt[(999, 0)] = {1, 2}
+    o3, i3, _ = dict_filter_csr(kg, "tail", qh, qr, qt, torch.device("cpu"))
+    assert torch.equal(o3, filter_csr(dt, qh, qr, qt)[0])

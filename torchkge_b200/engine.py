@@ -116,6 +116,15 @@ def _need_cuda(*tensors):
                 "move the model to a GPU -- there is no CPU fallback" % t.device)
 
 
+def _device_guard(device):
+    """The library launches on the CURRENT device (cudaGetDevice) with the stream it is handed:
+    every public entry point runs its calls under the device of the tensors it was given."""
+    if getattr(device, "type", None) == "cuda":
+        return torch.cuda.device(device)
+    import contextlib
+    return contextlib.nullcontext()
+
+
 class CudaEngine:
     """Direct calls into libkge_b200.so on the current CUDA stream."""
 
@@ -187,8 +196,10 @@ class CudaEngine:
 
     def rank_side(self, spec, packed, side, hrows, trows, r_idx, true_idx, filt, raw_count,
                   filt_sub, true_score=None, tc_packed=None, tc_dump=None, true_rows=None,
-                  true_score_in=None, approx=False):
-        """Adds this shard's counts for one side into raw_count / filt_sub (int32, device)."""
+                  true_score_in=None, approx=False, stats=None):
+        """Adds this shard's counts for one side into raw_count / filt_sub (int32, device).
+        ``stats``: optional int64[2] device tensor receiving (near-ties found, capacity) of a
+        bound-and-refine call (one is allocated when absent)."""
         n = r_idx.shape[0] if r_idx is not None else hrows.shape[0]
         dev = raw_count.device
         flags = _lib.FLAG_TENSOR_CORE if tc_packed is not None else 0
@@ -198,11 +209,14 @@ class CudaEngine:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         a = _lib.RankArgs()
         a.model, a.side, a.dim, a.flags = spec.code, side, spec.dim, flags
-        stats = None
         if flags:
-            stats = torch.zeros(2, dtype=torch.int64, device=dev)
+            if stats is None:
+                stats = torch.zeros(2, dtype=torch.int64, device=dev)
             a.tc_packed, a.tc_stats, a.tc_dump = _ptr(tc_packed), _ptr(stats), _ptr(tc_dump)
             self.tc_stats.append(stats)
+            del self.tc_stats[:-256]
+        else:
+            stats = None
         a.n, a.n_ent, a.ent_lo, a.n_rows = n, spec.n_ent, spec.ent_lo, spec.n_rows
         a.packed, a.ent0, a.ent1 = _ptr(packed), _ptr(spec.ent0), _ptr(spec.ent1)
         a.rel0, a.rel1 = _ptr(spec.rel0), _ptr(spec.rel1)
@@ -320,6 +334,12 @@ class QueryShard:
         """This rank's rows of a CSR over the n triples (offsets rebased)."""
         return None if filt is None else _csr_slice(filt, self.lo, self.hi, self.n)
 
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
     def all_gather(self, parts):
         """Per-rank result vectors (one entry per local triple) -> full-length vectors on every rank."""
         if self.world == 1:
@@ -345,8 +365,27 @@ def _csr_slice(filt, lo, hi, n):
     return (offs[lo:hi + 1] - base).contiguous(), ids[base:end].contiguous()
 
 
+class LazyRanks:
+    """Result of ``rank_link_prediction(..., sync=False)``: the four rank vectors are enqueued on
+    the device but nothing has been synchronised yet.  ``overflow`` is a device scalar > 0 iff
+    some bound-and-refine call ran out of room in its near-tie list (adversarial tables only);
+    ``get()`` looks at it (one host sync) and, in that case, recomputes everything on the exact
+    scalar scan.  Callers that copy the ranks to the host anyway pass the flag along in that copy
+    (``get(flag_host=...)``)."""
+
+    def __init__(self, ranks, overflow, redo):
+        self.ranks, self.overflow, self._redo = ranks, overflow, redo
+
+    def get(self, flag_host=None):
+        if self.overflow is not None:
+            flag = int(self.overflow.item()) if flag_host is None else int(flag_host)
+            if flag > 0:
+                self.ranks, self.overflow = self._redo(), None
+        return self.ranks
+
+
 def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=None,
-                         engine=None, chunk=DEFAULT_CHUNK, packed=None):
+                         engine=None, chunk=DEFAULT_CHUNK, packed=None, exact=False, sync=True):
     """Rank every triple's true tail and head against all entities, raw and filtered.
 
     spec       ModelSpec holding either the full entity table or exactly this rank's shard
@@ -356,6 +395,8 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
                after every dense scan has been enqueued, so that building the CSR on the host
                overlaps with the scans on the device
     shard      EntityShard when the table is range-partitioned over a process group
+    exact      True: scalar ATen-order scan only (no tensor-core / approximate bound-and-refine)
+    sync       False: return a LazyRanks (no host synchronisation at all inside this call)
     Returns (rank_heads, rank_tails, filt_rank_heads, filt_rank_tails), int64 device tensors.
     """
     engine = engine or default_engine()
@@ -366,68 +407,79 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
             packed = None
     mark = getattr(engine, "mark", lambda label: None)
     mark("step begin")
-    tc_packed = engine.pack_tc(spec) if hasattr(engine, "pack_tc") else None
-    mark("pack_tc")
-    if packed is None and tc_packed is None:
-        packed = engine.pack(spec)   # scalar-scan layout: only when there is no tensor-core path
-    mark("pack")
     dev = spec.ent0.device
-    # RotatE has no tensor-core form; its bound-and-refine runs on the fp32 pipes (KGE_FLAG_APPROX_SCAN)
-    refine = (tc_packed is None and spec.code == _lib.ROTATE and getattr(engine, "tensor_core", False))
-    counters = torch.zeros((4, n), dtype=torch.int32, device=dev)  # raw_t, sub_t, raw_h, sub_h
-    pending = []
-    for lo in range(0, n, chunk):
-        hi = min(n, lo + chunk)
-        h, t, r = h_idx[lo:hi], t_idx[lo:hi], r_idx[lo:hi]
-        hrows = engine.gather_rows(spec, h)
-        trows = engine.gather_rows(spec, t)
+    with _device_guard(dev):
+        tc_packed = engine.pack_tc(spec) if (hasattr(engine, "pack_tc") and not exact) else None
+        mark("pack_tc")
+        if packed is None and tc_packed is None:
+            packed = engine.pack(spec)   # scalar-scan layout: only when there is no tensor-core path
+        mark("pack")
+        # RotatE has no tensor-core form; its bound-and-refine runs on the fp32 pipes (KGE_FLAG_APPROX_SCAN)
+        refine = (not exact and tc_packed is None and spec.code == _lib.ROTATE
+                  and getattr(engine, "tensor_core", False))
+        # counters raw_t, sub_t, raw_h, sub_h and, behind them, one slot for the overflow flag so
+        # that a sharded run needs a single all-reduce
+        buf = torch.zeros(4 * n + 1, dtype=torch.int32, device=dev)
+        counters = buf[:4 * n].view(4, n)
+        n_calls = 2 * ((n + chunk - 1) // chunk)
+        stats_all = (torch.zeros((max(n_calls, 1), 2), dtype=torch.int64, device=dev)
+                     if (tc_packed is not None or refine) else None)
+        pending = []
+        call = 0
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            h, t, r = h_idx[lo:hi], t_idx[lo:hi], r_idx[lo:hi]
+            hrows = engine.gather_rows(spec, h)
+            trows = engine.gather_rows(spec, t)
+            if shard is not None and shard.world > 1:
+                # every row is owned by exactly one rank; the others contribute zeros
+                shard.all_reduce_sum(hrows)
+                shard.all_reduce_sum(trows)
+            for side, true_idx, which, raw, sub in ((_lib.SIDE_TAIL, t, 0, counters[0], counters[1]),
+                                                    (_lib.SIDE_HEAD, h, 1, counters[2], counters[3])):
+                if tc_packed is not None:
+                    handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
+                                              raw[lo:hi], sub[lo:hi], tc_packed=tc_packed,
+                                              stats=stats_all[call])
+                elif refine:
+                    handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
+                                              raw[lo:hi], sub[lo:hi], approx=True, stats=stats_all[call])
+                else:
+                    handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
+                                              raw[lo:hi], sub[lo:hi])
+                call += 1
+                pending.append((handle, which, lo, hi, sub))
+                mark("rank_side %d enqueued" % side)
+        filts = [filt_tail, filt_head]
+        for k in (0, 1):
+            if callable(filts[k]):
+                filts[k] = filts[k]()
+        for handle, which, lo, hi, sub in pending:
+            if filts[which] is not None:
+                engine.filter_side(handle, _csr_slice(filts[which], lo, hi, n), sub[lo:hi])
+        mark("filters enqueued")
+        del pending
+        overflow = None
+        if stats_all is not None:
+            # the near-tie list of a bound-and-refine call is bounded; a call that ran out of room
+            # (never seen on real or synthetic embeddings, possible on adversarial ones) reports
+            # found = capacity + 1.  The flag travels with the counters; nobody waits for it here.
+            buf[4 * n:] = (stats_all[:, 0] > stats_all[:, 1]).sum().to(torch.int32)
+            overflow = buf[4 * n]
         if shard is not None and shard.world > 1:
-            # every row is owned by exactly one rank; the others contribute zeros
-            shard.all_reduce_sum(hrows)
-            shard.all_reduce_sum(trows)
-        for side, true_idx, which, raw, sub in ((_lib.SIDE_TAIL, t, 0, counters[0], counters[1]),
-                                                (_lib.SIDE_HEAD, h, 1, counters[2], counters[3])):
-            if tc_packed is not None:
-                handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
-                                          raw[lo:hi], sub[lo:hi], tc_packed=tc_packed)
-            elif refine:
-                handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
-                                          raw[lo:hi], sub[lo:hi], approx=True)
-            else:
-                handle = engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
-                                          raw[lo:hi], sub[lo:hi])
-            pending.append((handle, which, lo, hi, sub, side, (hrows, trows, r, true_idx)))
-            mark("rank_side %d enqueued" % side)
-    filts = [filt_tail, filt_head]
-    for k in (0, 1):
-        if callable(filts[k]):
-            filts[k] = filts[k]()
-    for handle, which, lo, hi, sub, side, inputs in pending:
-        if filts[which] is not None:
-            engine.filter_side(handle, _csr_slice(filts[which], lo, hi, n), sub[lo:hi])
-    mark("filters enqueued")
-    if tc_packed is not None or refine:
-        # the near-tie list of a bound-and-refine call is bounded; on overflow (never seen on real
-        # or synthetic embeddings, possible on adversarial ones) redo that side exactly
-        for handle, which, lo, hi, sub, side, (hrows, trows, r, true_idx) in pending:
-            stats = handle[6]
-            if stats is not None:
-                found, cap = (int(x) for x in stats.tolist())
-                if found > cap:
-                    if packed is None:
-                        packed = engine.pack(spec)
-                    raw = counters[0] if side == _lib.SIDE_TAIL else counters[2]
-                    raw[lo:hi].zero_()
-                    engine.rank_side(spec, packed, side, hrows, trows, r, true_idx, None,
-                                     raw[lo:hi], sub[lo:hi])
-    del pending
-    if shard is not None and shard.world > 1:
-        shard.all_reduce_sum(counters)  # the single collective on the rank counters
-    mark("overflow check (host sync)")
-    rank_t, filt_t = engine.finalize(counters[0], counters[1])
-    rank_h, filt_h = engine.finalize(counters[2], counters[3])
-    mark("finalize")
-    return rank_h, rank_t, filt_h, filt_t
+            shard.all_reduce_sum(buf)  # the single collective on the rank counters (+ flag)
+        mark("collective")
+        rank_t, filt_t = engine.finalize(counters[0], counters[1])
+        rank_h, filt_h = engine.finalize(counters[2], counters[3])
+        mark("finalize")
+    result = (rank_h, rank_t, filt_h, filt_t)
+
+    def redo():
+        return rank_link_prediction(spec, h_idx, t_idx, r_idx, filts[0], filts[1], shard=shard,
+                                    engine=engine, chunk=chunk, exact=True)
+
+    lazy = LazyRanks(result, overflow, redo)
+    return lazy.get() if sync else lazy
 
 
 def relation_spec(spec):

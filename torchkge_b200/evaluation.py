@@ -6,8 +6,8 @@ CUDA engine; no (batch, n_entities) score matrix exists at any point.
 import torch
 
 from . import _lib
-from .data import filter_csr
-from .engine import (DEFAULT_CHUNK, ModelSpec, default_engine, rank_link_prediction,
+from .data import dict_filter_csr, filter_csr
+from .engine import (DEFAULT_CHUNK, ModelSpec, QueryShard, default_engine, rank_link_prediction,
                      rank_relation_prediction)
 from .exceptions import NotYetEvaluatedError
 
@@ -22,9 +22,11 @@ class LinkPredictionEvaluator(object):
     knowledge_graph: object exposing ``n_facts, head_idx, tail_idx, relations,
         dict_of_heads, dict_of_tails`` (``torchkge.data_structures.KnowledgeGraph`` or
         ``torchkge_b200.data.KnowledgeGraph``).
-    shard: ``torchkge_b200.engine.EntityShard``, optional (extension).  When given, every
-        rank of the group scans only its range of entity rows and the per-fact counters are
-        summed with one all-reduce; all ranks end up with the full rank vectors.
+    shard: ``torchkge_b200.engine.EntityShard`` or ``QueryShard``, optional (extension).
+        EntityShard: every rank of the group scans only its range of entity rows and the
+        per-fact counters are summed with one all-reduce.  QueryShard: every rank ranks its
+        contiguous slice of the facts against the whole (replicated) table and the rank vectors
+        are all-gathered.  Either way all ranks end up with the full rank vectors.
 
     Attributes (as in the reference, evaluation.py:236-261)
     ----------
@@ -57,8 +59,10 @@ class LinkPredictionEvaluator(object):
         if b_size is None or int(b_size) < 1:
             raise ValueError("b_size must be a positive integer")
         spec = ModelSpec.from_model(self.model)
-        if self.shard is not None and self.shard.local_storage:
-            spec.ent_lo, spec.n_ent = self.shard.lo, self.shard.n_ent
+        qshard = self.shard if isinstance(self.shard, QueryShard) else None
+        eshard = None if qshard is not None else self.shard
+        if eshard is not None and eshard.local_storage:
+            spec.ent_lo, spec.n_ent = eshard.lo, eshard.n_ent
         if not spec.ent0.is_cuda:
             raise _lib.KgeLibraryError(
                 "LinkPredictionEvaluator.evaluate needs the model on a CUDA device "
@@ -66,40 +70,52 @@ class LinkPredictionEvaluator(object):
         dev = spec.ent0.device
         kg = self.kg
         heads, tails, rels = kg.head_idx, kg.tail_idx, kg.relations
+        if qshard is not None:      # this rank's contiguous slice of the facts
+            heads, tails, rels = (x[qshard.lo:qshard.hi] for x in (heads, tails, rels))
+        n_here = int(heads.shape[0])
         h_d = heads.to(dev, non_blocking=True)
         t_d = tails.to(dev, non_blocking=True)
         r_d = rels.to(dev, non_blocking=True)
-        stats = {"h2d_bytes": 8 * 3 * kg.n_facts, "d2h_bytes": 8 * 4 * kg.n_facts}
+        stats = {"h2d_bytes": 8 * 3 * n_here, "d2h_bytes": 8 * (4 * kg.n_facts + 1)}
 
-        # Filter sets -> CSR on the host (same per-row semantics as get_true_targets).  Built
-        # lazily: the engine asks for them after the dense scans are enqueued, so this Python
-        # work overlaps with the GPU.
-        def lazy_csr(dictionary, k1, k2, true_idx):
-            def build():
-                csr = filter_csr(dictionary, k1, k2, true_idx)
-                stats["h2d_bytes"] += 8 * sum(x.numel() for x in csr)
-                return tuple(x.to(dev, non_blocking=True) for x in csr)
-            return build
-
+        # Filter sets -> CSR (same per-row semantics as get_true_targets).  Built lazily: the
+        # engine asks for them after the dense scans are enqueued, so host work overlaps the GPU.
         index = getattr(kg, "filter_index", None)
         if index is not None:
             # sorted-array filters (torchkge_b200.data.KnowledgeGraph): the index is resident on
             # the device (uploaded at first use, like weights); the per-row lists of this test set
-            # come from searchsorted + gather on the device, after the scans are enqueued
+            # come from searchsorted + gather on the device
             csr_tail = lambda: index.csr("tail", h_d, r_d, t_d)   # noqa: E731
             csr_head = lambda: index.csr("head", t_d, r_d, h_d)   # noqa: E731
-        else:                  # the reference's dictionaries
-            csr_tail = lazy_csr(kg.dict_of_tails, heads, rels, tails)
-            csr_head = lazy_csr(kg.dict_of_heads, tails, rels, heads)
+        else:
+            # the reference's dictionaries (torchkge.data_structures.KnowledgeGraph): distinct
+            # keys flattened once on the host, expanded on the device, cached on the graph
+            def from_dicts(which, k1, k2, true):
+                def build():
+                    offs, ids, nbytes = dict_filter_csr(kg, which, k1, k2, true, dev)
+                    stats["h2d_bytes"] += nbytes
+                    return offs, ids
+                return build
+            csr_tail = from_dicts("tail", heads, rels, tails)
+            csr_head = from_dicts("head", tails, rels, heads)
         engine = default_engine()
-        rh, rt, frh, frt = rank_link_prediction(spec, h_d, t_d, r_d, csr_tail, csr_head,
-                                                shard=self.shard, engine=engine,
-                                                chunk=DEFAULT_CHUNK)
+        lazy = rank_link_prediction(spec, h_d, t_d, r_d, csr_tail, csr_head, shard=eshard,
+                                    engine=engine, chunk=DEFAULT_CHUNK, sync=False)
+
+        def to_host(ranks, flag):
+            flag = torch.zeros(1, dtype=torch.int64, device=dev) if flag is None else flag.long().view(1)
+            if qshard is not None:
+                ranks = qshard.all_gather(ranks)
+                flag = qshard.all_reduce_sum(flag)   # every rank takes the same decision below
+            return torch.cat([x.view(-1) for x in ranks] + [flag]).cpu()   # ONE device -> host copy
+
+        host = to_host(lazy.ranks, lazy.overflow)
+        if int(host[-1]) > 0:        # near-tie list overflow somewhere: exact recomputation
+            host = to_host(lazy.get(flag_host=int(host[-1])), None)
+        n = kg.n_facts
         self.last_stats = stats
-        self.rank_true_heads = rh.cpu()
-        self.rank_true_tails = rt.cpu()
-        self.filt_rank_true_heads = frh.cpu()
-        self.filt_rank_true_tails = frt.cpu()
+        self.rank_true_heads, self.rank_true_tails = host[0:n], host[n:2 * n]
+        self.filt_rank_true_heads, self.filt_rank_true_tails = host[2 * n:3 * n], host[3 * n:4 * n]
         self.evaluated = True
 
     def _check(self):

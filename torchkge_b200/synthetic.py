@@ -24,6 +24,9 @@ WORKLOADS = {
     "tiny": dict(model="TransE", diss="L2", dim=32, n_ent=2000, n_rel=20, n_facts=30000, n_test=512),
 }
 
+# C5 (BASELINE.json configs[4]): DistMult training step, Bernoulli corruption fused with scoring + margin loss
+C5 = dict(model="DistMult", dim=200, n_ent=1000000, n_rel=1000, n_neg=256)
+
 MODEL_CODE = {("TransE", "L1"): _lib.TRANSE_L1, ("TransE", "L2"): _lib.TRANSE_L2,
               ("DistMult", None): _lib.DISTMULT, ("RESCAL", None): _lib.RESCAL,
               ("ComplEx", None): _lib.COMPLEX, ("RotatE", None): _lib.ROTATE}
@@ -78,6 +81,25 @@ def make_tables(code, dim, n_ent, n_rel, lo, hi, seed, device):
         if code == _lib.COMPLEX:
             t["rel1"] = _xavier_small(n_rel, dim, seed + 4, device, False)
     return t
+
+
+def rows_by_id(code, dim, n_ent, seed, ids, device):
+    """{"ent0": (len(ids), dim), "ent1": ... or None}: the rows ``ids`` of the entity tables
+    ``make_tables`` generates, without materialising the tables (each needed block of 65,536 rows is
+    regenerated from its seed)."""
+    norm_ent = code in (_lib.TRANSE_L1, _lib.TRANSE_L2, _lib.DISTMULT, _lib.RESCAL)
+    ids = ids.long().cpu()
+    out = {"ent0": torch.empty((ids.numel(), dim), dtype=torch.float32, device=device), "ent1": None}
+    if code in (_lib.COMPLEX, _lib.ROTATE):
+        out["ent1"] = torch.empty_like(out["ent0"])
+    for b in torch.unique(ids // BLOCK).tolist():
+        lo, hi = b * BLOCK, min(n_ent, (b + 1) * BLOCK)
+        sel = torch.nonzero(ids // BLOCK == b).view(-1)
+        local = (ids[sel] - lo).to(device)
+        out["ent0"][sel.to(device)] = _xavier_rows(lo, hi, dim, n_ent, seed + 1, device, norm_ent)[local]
+        if out["ent1"] is not None:
+            out["ent1"][sel.to(device)] = _xavier_rows(lo, hi, dim, n_ent, seed + 2, device, False)[local]
+    return out
 
 
 def make_graph(n_ent, n_rel, n_facts, n_test, seed, device):
