@@ -153,3 +153,79 @@ def bits_equal(a, b):
     a = a.detach().cpu().float().contiguous()
     b = b.detach().cpu().float().contiguous()
     return (a.numpy().view(np.uint32) == b.numpy().view(np.uint32)) | (a == b).numpy()
+
+
+# ---------------------------------------------------------------------------- RESCAL query prep
+def _fma32(a, b, c):
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def rescal_prep_emulated(side, vec, M):
+    """numpy restatement of the summation order of `matmul(h.view(b, 1, d), M)` (side 'tail') /
+    `matmul(M, t.view(b, d, 1))` (side 'head') as oneMKL 2024.2 (AVX-512 path) + ATen execute it
+    for batches of >= 2 facts -- the order csrc/reduce.cuh:rescal_query_component replays.
+    vec (d,), M (d, d) float32 numpy; returns (d,).  Used to tell whether THIS machine's MKL takes
+    the same code path as the authoring machine (rescal_order_matches_here)."""
+    d = vec.shape[0]
+    vec, M = vec.astype(np.float32), M.astype(np.float32)
+    y = np.zeros(d, np.float32)
+    if side == "tail":
+        H = lambda k: np.full(d, vec[k], np.float32)   # noqa: E731
+        if d < 20:
+            for k in range(d):
+                y = y + H(k) * M[k]
+            return y
+        k = 0
+        while k + 8 <= d:
+            y = _fma32(H(k + 6), M[k + 6], y)
+            y = _fma32(H(k + 4), M[k + 4], y)
+            y = y + _fma32(H(k + 5), M[k + 5], H(k + 7) * M[k + 7])
+            y = y + (_fma32(H(k), M[k], H(k + 2) * M[k + 2]) + _fma32(H(k + 1), M[k + 1], H(k + 3) * M[k + 3]))
+            k += 8
+        while k < d:
+            y = _fma32(H(k), M[k], y)
+            k += 1
+        jm = 16 * (d // 16)
+        if jm < d:
+            yy = np.zeros(d, np.float32)
+            for k in range(d):
+                yy = _fma32(H(k), M[k], yy)
+            y[jm:] = yy[jm:]
+        return y
+    T = lambda k: np.full(d, vec[k], np.float32)   # noqa: E731
+    if d < 20:
+        for k in range(d):
+            y = y + M[:, k] * T(k)
+        return y
+    bounds = [0, d] if d <= 384 else [0, (d + 1) // 2, d]
+    parts = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        acc = np.zeros(d, np.float32)
+        for k in range(a, b):
+            acc = _fma32(M[:, k], T(k), acc)
+        parts.append(acc)
+    y = parts[0]
+    for p in parts[1:]:
+        y = y + p
+    return y
+
+
+_RESCAL_ORDER = {}
+
+
+def rescal_order_matches_here(d):
+    """True when torch.matmul on THIS machine sums RESCAL's query preparation in the order the CUDA
+    kernel replays (it does on the authoring machine: tests/test_host_arith.py).  oneMKL picks its
+    kernels by CPU: on a machine where this is False the reference's own RESCAL bits differ from the
+    committed golden fixtures, and oracle-vs-GPU rank equality cannot be expected there."""
+    if d not in _RESCAL_ORDER:
+        g = torch.Generator().manual_seed(d)
+        v, M = torch.randn(3, d, generator=g), torch.randn(3, d, d, generator=g)
+        wt = torch.matmul(v.view(3, 1, d), M).view(3, d).numpy()
+        wh = torch.matmul(M, v.view(3, d, 1)).view(3, d).numpy()
+        ok = True
+        for i in range(3):
+            ok &= bool((rescal_prep_emulated("tail", v[i].numpy(), M[i].numpy()) == wt[i]).all())
+            ok &= bool((rescal_prep_emulated("head", v[i].numpy(), M[i].numpy()) == wh[i]).all())
+        _RESCAL_ORDER[d] = ok
+    return _RESCAL_ORDER[d]

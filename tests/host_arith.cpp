@@ -65,3 +65,13 @@ extern "C" int host_scores(int el, int mode, int casc, int dim, int nq, int nc, 
   }
   return 0;
 }
+
+// RESCAL query preparation (reduce.cuh: rescal_query_component): out[i][j] for n facts;
+// vec: [n][dim], mats: [n][dim][dim]
+extern "C" int host_rescal_prep(int tail, int dim, int n, const float* vec, const float* mats, float* out) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < dim; ++j)
+      out[(size_t)i * dim + j] =
+          rescal_query_component(tail != 0, dim, j, vec + (size_t)i * dim, mats + (size_t)i * dim * dim);
+  return 0;
+}

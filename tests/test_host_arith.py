@@ -96,3 +96,27 @@ def test_device_arithmetic_equals_aten(kind, d, host_lib):
         got = torch.from_numpy(out)
         same = (got.view(torch.int32) == want.contiguous().view(torch.int32)) | (got == want)
         assert same.all(), "%s d=%d mode=%d: %d of %d scores differ" % (kind, d, mode, int((~same).sum()), same.numel())
+
+
+@pytest.mark.parametrize("d", [1, 2, 7, 13, 16, 19, 20, 21, 31, 32, 33, 50, 64, 100, 129, 200, 203, 256, 300, 384, 385, 400, 512])
+def test_rescal_query_preparation_equals_the_reference_matmul(d, host_lib):
+    """`matmul(h.view(b, 1, d), M)` and `matmul(M, t.view(b, d, 1))` (bilinear.py:108, 113) against
+    the device function the prep kernel is made of -- bit for bit.  This pins the oneMKL / ATen
+    summation order the kernel replays (batches of >= 2 facts: a batch of one takes MKL's gemv path,
+    whose order depends on memory alignment)."""
+    g = torch.Generator().manual_seed(d)
+    b = 3
+    v = torch.randn(b, d, generator=g)
+    M = torch.randn(b, d, d, generator=g)
+    v[1, : d // 2] = 0.0
+    want_tail = torch.matmul(v.view(b, 1, d), M).view(b, d)
+    want_head = torch.matmul(M, v.view(b, d, 1)).view(b, d)
+    vn, Mn = v.numpy().copy(), M.numpy().copy()
+    P = ctypes.c_void_p
+    for tail, want in ((1, want_tail), (0, want_head)):
+        out = np.full((b, d), np.nan, dtype=np.float32)
+        assert host_lib.host_rescal_prep(tail, d, b, P(vn.ctypes.data), P(Mn.ctypes.data), P(out.ctypes.data)) == 0
+        got = torch.from_numpy(out)
+        same = (got.view(torch.int32) == want.contiguous().view(torch.int32)) | (got == want)
+        assert same.all(), "rescal %s d=%d: %d of %d components differ" % (
+            "tail" if tail else "head", d, int((~same).sum()), same.numel())

@@ -42,7 +42,7 @@ def test_entity_inference_topk(kind, d, missing, cuda_device):
         s = dictionary.get((known[i].item(), rels[i].item()))
         if s:
             dense[i][torch.tensor(list(s))] = -float("inf")
-    if kind == "rescal":      # query preparation is a GEMM on both sides: tolerance parity
+    if kind == "rescal" and not helpers.rescal_order_matches_here(d):   # this CPU's MKL sums differently
         want_v = torch.sort(dense, dim=1, descending=True)[0][:, :k]
         torch.testing.assert_close(inf.scores, want_v, rtol=1e-5, atol=1e-6)
     else:

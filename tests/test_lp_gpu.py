@@ -2,9 +2,9 @@
 the C ABI) against the CPU oracle on the same seeded inputs.
 
 Bar (north_star): ranks bit-identical, ties broken identically; scores within 1e-5 relative
--- and in fact required bit-identical here wherever the reduction is an ATen order we
-replay (everything except RESCAL's query preparation, which goes through MKL's batched GEMM
-on the CPU side).
+-- and in fact required bit-identical here: every reduction is an ATen / oneMKL order we replay
+(RESCAL's query preparation `h^T M_r`, `M_r t` goes through MKL's batched GEMM on the CPU side; its
+summation order is replayed too, see csrc/reduce.cuh:rescal_query_component and DESIGN.md 2.4).
 """
 import numpy as np
 import pytest
@@ -36,9 +36,21 @@ def _assert_ranks_equal(ev, ref, kind):
             kind, name, bad.numel(), want.numel(), bad[0], got[bad[0]], want[bad[0]])
 
 
-@pytest.mark.parametrize("kind", EXACT_KINDS)
+def _needs_reference_mkl_order(kind, d):
+    """RESCAL vs an oracle computed on THIS machine: only meaningful where this machine's MKL sums
+    the query preparation like the authoring machine's (the committed golden fixtures are compared
+    unconditionally in test_ranks_equal_the_unmodified_reference)."""
+    if kind == "rescal" and not helpers.rescal_order_matches_here(d):
+        pytest.skip("oneMKL on this CPU sums RESCAL's batched matmul in another order than the machine "
+                    "the golden fixtures come from: the reference's own bits differ here")
+
+
+@pytest.mark.parametrize("kind", ALL_KINDS)
 @pytest.mark.parametrize("d", [50, 64, 100, 13])
 def test_ranks_match_oracle_exactly(kind, d, cuda_device):
+    if kind == "rescal" and d > 64:
+        pytest.skip("rescal d^2 tables: small dims only")
+    _needs_reference_mkl_order(kind, d)
     n_ent, n_rel = 1000, 11
     kg, dh, dt = helpers.make_kg(n_ent, n_rel, n_facts=6000, n_test=300, seed=d)
     model = helpers.make_model(kind, d, n_ent, n_rel, seed=d).to(cuda_device)
@@ -65,9 +77,8 @@ def test_dense_scores_match_oracle(kind, cuda_device):
         got = model.inference_scoring_function(*args).cpu()
         want = oracle.scores_all(kind, P, h, t, r, side)
         assert got.shape == want.shape == (b, n_ent)
-        if kind == "rescal":
-            # h^T M_r / M_r t are computed by MKL on the CPU side: same maths, other order
-            torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+        if kind == "rescal" and not helpers.rescal_order_matches_here(d):
+            torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)   # this CPU's MKL sums differently
         else:
             same = (got.numpy().view(np.uint32) == want.numpy().view(np.uint32)) | (got == want).numpy()
             assert same.all(), "%s %s: %d scores differ in bits (max abs diff %g)" % (
@@ -192,16 +203,11 @@ def test_ranks_equal_the_unmodified_reference(case, tensor_core, cuda_device, mo
     ev.evaluate(b_size=g["b_size"], verbose=False)
     raw = g["raw"]
     names = ["rank_true_heads", "rank_true_tails", "filt_rank_true_heads", "filt_rank_true_tails"]
-    if g["kind"] == "rescal":
-        # query preparation is an MKL batched GEMM in the reference: near-ties may flip
-        for nm in names:
-            assert (getattr(ev, nm) - torch.from_numpy(raw[nm])).abs().max().item() <= 2
-    else:
-        for nm in names:
-            assert torch.equal(getattr(ev, nm), torch.from_numpy(raw[nm])), nm
-        got = [*ev.mean_rank(), *ev.hit_at_k(10), *ev.mrr()]
-        for a, b in zip(got, raw["metrics"]):
-            assert a == pytest.approx(float(b), rel=1e-6)
+    for nm in names:     # RESCAL included: its MKL query preparation is replayed in the reference's order
+        assert torch.equal(getattr(ev, nm), torch.from_numpy(raw[nm])), nm
+    got = [*ev.mean_rank(), *ev.hit_at_k(10), *ev.mrr()]
+    for a, b in zip(got, raw["metrics"]):
+        assert a == pytest.approx(float(b), rel=1e-6)
 
 
 def test_empty_and_single_fact_graphs(cuda_device):

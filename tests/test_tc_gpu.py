@@ -89,8 +89,8 @@ def test_approximate_scores_within_half_the_bound(kind, d, cuda_device):
 @pytest.mark.parametrize("kind", TC_KINDS)
 @pytest.mark.parametrize("d", [13, 50, 100])
 def test_ranks_equal_oracle_with_tensor_cores(kind, d, cuda_device):
-    if kind == "rescal":
-        pytest.skip("rescal ranks are tolerance-parity (MKL query prep); covered by score tests")
+    if kind == "rescal" and not helpers.rescal_order_matches_here(d):
+        pytest.skip("oneMKL on this CPU sums RESCAL's batched matmul in another order than the authoring machine")
     n_ent, n_rel = 1500, 9
     kg, dh, dt = helpers.make_kg(n_ent, n_rel, n_facts=7000, n_test=300, seed=100 + d)
     model = helpers.make_model(kind, d, n_ent, n_rel, seed=d).to(cuda_device)

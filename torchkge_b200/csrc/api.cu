@@ -32,6 +32,26 @@ int fail_cuda(cudaError_t e, const char* where) {
     if (_e != cudaSuccess) return fail_cuda(_e, where); \
   } while (0)
 
+// The kernels are launched on the CURRENT device with the stream the caller hands in; a caller whose
+// current device is not the one its buffers live on (a model on cuda:1 while cuda:0 is current)
+// would otherwise launch on the wrong device.  Every launching entry point therefore switches to
+// the device that owns its first device pointer for the duration of the call.
+struct DeviceScope {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceScope(const void* device_ptr) {
+    if (!device_ptr) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, device_ptr) != cudaSuccess) { cudaGetLastError(); return; }
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    if (prev != at.device && cudaSetDevice(at.device) == cudaSuccess) switched = true;
+  }
+  ~DeviceScope() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 struct HostSchedule {
   kge::Schedule s;
   std::vector<int32_t> inv_perm;
@@ -225,6 +245,7 @@ int kge_pack_table(int model, const float* ent0, const float* ent1, int64_t n_ro
     return fail(KGE_ERR_ARG, "kge_pack_table: null table pointer");
   const HostSchedule* hs = get_schedule(model, dim);
   if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_pack_table: unsupported dim");
+  DeviceScope device_scope(ent0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // inv_perm is staged in the tail of the packed buffer?  No: it would be overwritten.  Use a
   // small stream-ordered allocation instead (freed on the same stream).
@@ -249,6 +270,7 @@ int kge_gather_rows(int model, const float* ent0, const float* ent1, int64_t ent
   if (n == 0) return KGE_OK;
   if (!ent0 || !idx || !out || (planes == 2 && !ent1))
     return fail(KGE_ERR_ARG, "kge_gather_rows: null pointer");
+  DeviceScope device_scope(ent0);
   KGE_CUDA_TRY(kge::launch_gather_rows(ent0, ent1, planes, ent_lo, n_rows, dim, idx, n, out,
                                        static_cast<cudaStream_t>(stream)),
                "gather_rows");
@@ -281,6 +303,7 @@ int kge_tc_pack_table(int model, const float* ent0, const float* ent1, int64_t n
   if (n_rows <= 0) return KGE_OK;
   if (!ent0 || !tc_packed || (kge::elem_cw(el) == 2 && !ent1))
     return fail(KGE_ERR_ARG, "kge_tc_pack_table: null pointer");
+  DeviceScope device_scope(ent0);
   const int k_total = tc_k_total(el, dim);
   const int n_kb = kge::tc::n_kblocks(k_total);
   const int64_t n_ct = (n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
@@ -311,6 +334,7 @@ int kge_rank_side(const kge_rank_args_t* a) {
     return fail(KGE_ERR_ARG, "kge_rank_side: filter arrays incomplete");
   const HostSchedule* hs = get_schedule(a->model, a->dim);
   if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_rank_side: unsupported dim");
+  DeviceScope device_scope(a->ent0);
   const int qw = kge::elem_qw(el);
   const bool use_tc = (a->flags & KGE_FLAG_TENSOR_CORE) && tc_supported(el) && a->n_rows > 0;
   if (use_tc && !a->tc_packed) return fail(KGE_ERR_ARG, "kge_rank_side: tc_packed required with KGE_FLAG_TENSOR_CORE");
@@ -442,6 +466,7 @@ int kge_filter_side(const kge_rank_args_t* a) {
   if (kge::elem_cw(el) == 2 && !a->ent1) return fail(KGE_ERR_ARG, "kge_filter_side: ent1 required");
   const HostSchedule* hs = get_schedule(a->model, a->dim);
   if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_filter_side: unsupported dim");
+  DeviceScope device_scope(a->ent0);
   Workspace w = carve(a->workspace, kge::elem_qw(el), a->dim, a->n);  // leading part only
   if (w.bytes > a->workspace_bytes) return fail(KGE_ERR_ARG, "kge_filter_side: workspace too small");
   KGE_CUDA_TRY(kge::launch_filter(el, hs->s.has_cascade, a->dim, a->n, a->n_filt, w.qplain, a->ent0,
@@ -456,6 +481,7 @@ int kge_finalize_ranks(const int32_t* raw_count, const int32_t* filt_sub, int64_
   if (n == 0) return KGE_OK;
   if (!raw_count || !filt_sub || !ranks || !filt_ranks)
     return fail(KGE_ERR_ARG, "kge_finalize_ranks: null pointer");
+  DeviceScope device_scope(raw_count);
   KGE_CUDA_TRY(kge::launch_finalize(raw_count, filt_sub, n, ranks, filt_ranks,
                                     static_cast<cudaStream_t>(stream)),
                "finalize");
@@ -474,6 +500,7 @@ int kge_score_all(const kge_score_all_args_t* a) {
     return fail(KGE_ERR_ARG, "kge_score_all: rel1 required");
   const HostSchedule* hs = get_schedule(a->model, a->dim);
   if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_score_all: unsupported dim");
+  DeviceScope device_scope(a->packed);
   const int qw = kge::elem_qw(el);
   Workspace w = carve(a->workspace, qw, a->dim, a->n);
   if (w.bytes > a->workspace_bytes) return fail(KGE_ERR_ARG, "kge_score_all: workspace too small");
@@ -541,6 +568,7 @@ int kge_score_triples_fwd(const kge_tables_t* tb, const int64_t* h, const int64_
   if (!tables_ok(tb)) return fail(KGE_ERR_ARG, "kge_score_triples_fwd: bad tables");
   if (n == 0) return KGE_OK;
   if (n < 0 || !h || !t || !r || !scores) return fail(KGE_ERR_ARG, "kge_score_triples_fwd: null pointer");
+  DeviceScope device_scope(tb->ent0);
   KGE_CUDA_TRY(kge::launch_score_triples_fwd(tb->model, tb->dim, to_tables(tb), h, t, r, n, scores,
                                              static_cast<cudaStream_t>(stream)),
                "score_triples_fwd");
@@ -554,6 +582,7 @@ int kge_score_triples_bwd(const kge_tables_t* tb, const kge_grads_t* g, const in
   if (n == 0) return KGE_OK;
   if (n < 0 || !h || !t || !r || !grad_scores)
     return fail(KGE_ERR_ARG, "kge_score_triples_bwd: null pointer");
+  DeviceScope device_scope(tb->ent0);
   KGE_CUDA_TRY(kge::launch_score_triples_bwd(tb->model, tb->dim, to_tables(tb), to_grads(g), h, t, r, n,
                                              grad_scores, static_cast<cudaStream_t>(stream)),
                "score_triples_bwd");
@@ -566,6 +595,7 @@ int kge_corrupt_batch(const int64_t* h, const int64_t* t, const int64_t* r, int6
   if (b == 0) return KGE_OK;
   if (b < 0 || n_neg < 1 || n_ent < 1 || !h || !t || !r || !bern_probs || !nh || !nt)
     return fail(KGE_ERR_ARG, "kge_corrupt_batch: bad argument");
+  DeviceScope device_scope(h);
   KGE_CUDA_TRY(kge::launch_corrupt_batch(h, t, r, b, n_neg, bern_probs, n_ent, seed, offset, nh, nt,
                                          static_cast<cudaStream_t>(stream)),
                "corrupt_batch");
@@ -576,6 +606,7 @@ int kge_margin_loss_fwd(const float* pos, const float* neg, int64_t n, float mar
                         void* stream) {
   if (n == 0) return KGE_OK;
   if (n < 0 || !pos || !neg || !loss) return fail(KGE_ERR_ARG, "kge_margin_loss_fwd: bad argument");
+  DeviceScope device_scope(pos);
   KGE_CUDA_TRY(kge::launch_margin_loss_fwd(pos, neg, n, margin, loss, static_cast<cudaStream_t>(stream)),
                "margin_loss_fwd");
   return KGE_OK;
@@ -586,6 +617,7 @@ int kge_margin_loss_bwd(const float* pos, const float* neg, int64_t n, float mar
   if (n == 0) return KGE_OK;
   if (n < 0 || !pos || !neg || !grad_loss || !grad_pos || !grad_neg)
     return fail(KGE_ERR_ARG, "kge_margin_loss_bwd: bad argument");
+  DeviceScope device_scope(pos);
   KGE_CUDA_TRY(kge::launch_margin_loss_bwd(pos, neg, n, margin, grad_loss, grad_pos, grad_neg,
                                            static_cast<cudaStream_t>(stream)),
                "margin_loss_bwd");
@@ -596,6 +628,7 @@ int kge_pair_loss_fwd(int kind, const float* pos, const float* neg, int64_t n, f
   if (kind != KGE_LOSS_LOGISTIC && kind != KGE_LOSS_BCE) return fail(KGE_ERR_ARG, "kge_pair_loss_fwd: unknown loss kind");
   if (n == 0) return KGE_OK;
   if (n < 0 || !pos || !neg || !loss) return fail(KGE_ERR_ARG, "kge_pair_loss_fwd: bad argument");
+  DeviceScope device_scope(pos);
   KGE_CUDA_TRY(kge::launch_pair_loss_fwd(kind, pos, neg, n, loss, static_cast<cudaStream_t>(stream)),
                "pair_loss_fwd");
   return KGE_OK;
@@ -607,6 +640,7 @@ int kge_pair_loss_bwd(int kind, const float* pos, const float* neg, int64_t n, c
   if (n == 0) return KGE_OK;
   if (n < 0 || !pos || !neg || !grad_loss || !grad_pos || !grad_neg)
     return fail(KGE_ERR_ARG, "kge_pair_loss_bwd: bad argument");
+  DeviceScope device_scope(pos);
   KGE_CUDA_TRY(kge::launch_pair_loss_bwd(kind, pos, neg, n, grad_loss, grad_pos, grad_neg,
                                          static_cast<cudaStream_t>(stream)),
                "pair_loss_bwd");
@@ -615,6 +649,7 @@ int kge_pair_loss_bwd(int kind, const float* pos, const float* neg, int64_t n, c
 
 int kge_margin_step_fwd(const kge_margin_step_args_t* a) {
   if (!step_ok(a)) return fail(KGE_ERR_ARG, "kge_margin_step_fwd: bad argument");
+  DeviceScope device_scope(a->tb.ent0);
   KGE_CUDA_TRY(kge::launch_margin_step_fwd(to_step(a), static_cast<cudaStream_t>(a->stream)),
                "margin_step_fwd");
   return KGE_OK;
@@ -624,6 +659,7 @@ int kge_margin_step_bwd(const kge_margin_step_args_t* a, const kge_grads_t* g,
                         const float* grad_loss) {
   if (!step_ok(a) || !grads_ok(&a->tb, g) || !grad_loss)
     return fail(KGE_ERR_ARG, "kge_margin_step_bwd: bad argument");
+  DeviceScope device_scope(a->tb.ent0);
   KGE_CUDA_TRY(kge::launch_margin_step_bwd(to_step(a), to_grads(g), grad_loss,
                                            static_cast<cudaStream_t>(a->stream)),
                "margin_step_bwd");

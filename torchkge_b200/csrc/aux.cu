@@ -182,7 +182,9 @@ __global__ void prep_queries_kernel(int model, int side, int dim, long long n,
 
 // RESCAL query preparation: tail q = h^T M_r (bilinear.py:113), head q = M_r t
 // (bilinear.py:108); M_r = rel_mat[r] viewed (dim, dim) row-major.  One thread per output
-// component, fp32 fma chain over the contraction index in ascending order.
+// component, in the reference's (oneMKL / ATen) summation order: reduce.cuh,
+// rescal_query_component.  Consecutive threads own consecutive components: the tail side reads
+// M[k][j..] coalesced, the head side walks its own row (L1-resident, tiny next to the scan).
 __global__ void prep_rescal_kernel(int side, int dim, long long n,
                                    const float* __restrict__ hrows,
                                    const float* __restrict__ trows,
@@ -194,15 +196,9 @@ __global__ void prep_rescal_kernel(int side, int dim, long long n,
   const long long i = gid / dim;
   const int j = (int)(gid - i * dim);
   const float* M = rel_mat + (size_t)(r_idx ? r_idx[i] : i) * dim * dim;
-  float acc = 0.f;
-  if (side == KGE_SIDE_TAIL) {
-    const float* h = hrows + (size_t)i * dim;
-    for (int k = 0; k < dim; ++k) acc = __fmaf_rn(h[k], M[(size_t)k * dim + j], acc);
-  } else {
-    const float* t = trows + (size_t)i * dim;
-    for (int k = 0; k < dim; ++k) acc = __fmaf_rn(M[(size_t)j * dim + k], t[k], acc);
-  }
-  qplain[(size_t)i * dim + j] = acc;
+  const bool tail = side == KGE_SIDE_TAIL;
+  const float* vec = (tail ? hrows : trows) + (size_t)i * dim;
+  qplain[(size_t)i * dim + j] = rescal_query_component(tail, dim, j, vec, M);
 }
 
 // qpacked[qt][pos][plane][TILE_Q]; thread per output float, zero padded past n.

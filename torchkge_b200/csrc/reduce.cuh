@@ -308,6 +308,61 @@ __device__ float pair_score_natural(int dim, const float* __restrict__ q0, const
   }
 }
 
+// RESCAL query preparation, one output component (bilinear.py:108 `matmul(r, t.view(b, d, 1))`,
+// :113 `matmul(h.view(b, 1, d), r)`): the reference's batched matmul runs in oneMKL (ATen bmm ->
+// cblas_sgemm_batch) for d >= 20 and in ATen's own scalar loop (baddbmm_cpu_kernel, mul and add
+// rounded separately) below that (contraction * rows * cols < 400).  The summation ORDER below was
+// recovered by probing torch 2.11 / oneMKL 2024.2 (AVX-512 code path) with absorption tests
+// (2^25, 1, -2^25 at three positions of the contraction) and confirmed bit for bit on random data
+// for every d in 1..512 (tests/test_host_arith.py replays this very function on the host):
+//   tail  q_j = sum_k h_k M[k][j], columns j < 16*floor(d/16) (full 16-lane vectors):
+//           per chunk of 8 k:  y = fma(h6,M6,y); y = fma(h4,M4,y); y += fma(h5,M5,h7*M7);
+//                              y += fma(h0,M0,h2*M2) + fma(h1,M1,h3*M3);   then a plain fma chain
+//           over the d % 8 leftover k;  remainder columns: one fma chain over all k
+//   head  q_j = sum_k M[j][k] t_k: one fma chain over k for d <= 384, two chains over the halves
+//           [0, ceil(d/2)) and [ceil(d/2), d) added at the end for 385 <= d <= 768 (beyond that
+//           MKL's K-blocking was not probed: tolerance parity only)
+// `vec` = h (tail) or t (head); M row-major (d, d).  A batch of exactly ONE fact takes a different
+// MKL path in the reference (sgemv with alignment-dependent peeling, not reproducible): documented.
+__device__ __forceinline__ float rescal_query_component(bool tail, int d, int j, const float* __restrict__ vec,
+                                                        const float* __restrict__ M) {
+  float acc = 0.f;
+  if (tail) {
+    const float* col = M + j;  // M[k][j] = col[k * d]
+    if (d < 20) {
+      for (int k = 0; k < d; ++k) acc = __fadd_rn(acc, __fmul_rn(vec[k], col[(size_t)k * d]));
+    } else if (j < (d / 16) * 16) {
+      int k = 0;
+      for (; k + 8 <= d; k += 8) {
+        const float* c = col + (size_t)k * d;
+        acc = __fmaf_rn(vec[k + 6], c[(size_t)6 * d], acc);
+        acc = __fmaf_rn(vec[k + 4], c[(size_t)4 * d], acc);
+        acc = __fadd_rn(acc, __fmaf_rn(vec[k + 5], c[(size_t)5 * d], __fmul_rn(vec[k + 7], c[(size_t)7 * d])));
+        const float e = __fmaf_rn(vec[k], c[0], __fmul_rn(vec[k + 2], c[(size_t)2 * d]));
+        const float o = __fmaf_rn(vec[k + 1], c[d], __fmul_rn(vec[k + 3], c[(size_t)3 * d]));
+        acc = __fadd_rn(acc, __fadd_rn(e, o));
+      }
+      for (; k < d; ++k) acc = __fmaf_rn(vec[k], col[(size_t)k * d], acc);
+    } else {
+      for (int k = 0; k < d; ++k) acc = __fmaf_rn(vec[k], col[(size_t)k * d], acc);
+    }
+  } else {
+    const float* row = M + (size_t)j * d;
+    if (d < 20) {
+      for (int k = 0; k < d; ++k) acc = __fadd_rn(acc, __fmul_rn(row[k], vec[k]));
+    } else if (d <= 384) {
+      for (int k = 0; k < d; ++k) acc = __fmaf_rn(row[k], vec[k], acc);
+    } else {
+      const int half = (d + 1) / 2;
+      float a1 = 0.f;
+      for (int k = 0; k < half; ++k) acc = __fmaf_rn(row[k], vec[k], acc);
+      for (int k = half; k < d; ++k) a1 = __fmaf_rn(row[k], vec[k], a1);
+      acc = __fadd_rn(acc, a1);
+    }
+  }
+  return acc;
+}
+
 // Exact adjudication of the near-tie band (the list is kept as one region per CTA of the scan).
 // Chain-parallel: the independent chains of the ATen reduction are spread over the lanes of a
 // warp -- 8 lanes per pair for the L2 norm (4 pairs per warp), 32 lanes per pair for the

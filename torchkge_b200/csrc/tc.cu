@@ -711,8 +711,11 @@ template <int BKT, bool RES>
 cudaError_t launch_variant(const TcScanParams& p, int grid, cudaStream_t st) {
   const size_t smem = smem_bytes<BKT, RES>(p.n_kb);
   if (smem > SMEM_LIMIT) return cudaErrorInvalidValue;
-  static bool configured = false;  // one flag per template instantiation
-  if (!configured) {
+  // per template instantiation AND per device (the attribute is a per-device property)
+  static bool configured[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cudaErrorInvalidDevice;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaError_t e = cudaSuccess;
     auto set = [&](auto kern) {
       if (e == cudaSuccess)
@@ -721,7 +724,7 @@ cudaError_t launch_variant(const TcScanParams& p, int grid, cudaStream_t st) {
     set(tc_scan_kernel<false, false, BKT, RES>); set(tc_scan_kernel<true, false, BKT, RES>);
     set(tc_scan_kernel<false, true, BKT, RES>); set(tc_scan_kernel<true, true, BKT, RES>);
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   if (p.dump) {
     if (p.l2) tc_scan_kernel<true, true, BKT, RES><<<grid, THREADS, smem, st>>>(p);

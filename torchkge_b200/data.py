@@ -26,6 +26,13 @@ class FilterIndex:
     def __init__(self, heads, tails, relations, n_ent, n_rel):
         heads, tails, relations = (x.long().cpu() for x in (heads, tails, relations))
         self.n_ent, self.n_rel = int(n_ent), int(n_rel)
+        if self.n_ent * self.n_rel * self.n_ent >= 2 ** 63:
+            raise ValueError("FilterIndex packs (entity, relation, entity) into one int64 key: "
+                             "n_ent^2 * n_rel = %d * %d * %d does not fit" % (self.n_ent, self.n_rel, self.n_ent))
+        for name, x, hi in (("heads", heads, self.n_ent), ("tails", tails, self.n_ent),
+                            ("relations", relations, self.n_rel)):
+            if x.numel() and (int(x.min()) < 0 or int(x.max()) >= hi):
+                raise ValueError("FilterIndex: %s outside [0, %d)" % (name, hi))
         # one sorted, deduplicated int64 array per side: (key1 * n_rel + rel) * n_ent + value
         self.kv = {
             "tail": torch.unique((heads * self.n_rel + relations) * self.n_ent + tails),

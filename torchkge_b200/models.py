@@ -14,7 +14,7 @@ from torch import nn
 from torch.nn.functional import normalize
 
 from . import _lib
-from .engine import ModelSpec, default_engine
+from .engine import ModelSpec, _device_guard, default_engine
 
 
 def init_embedding(n_vectors, dim):
@@ -26,13 +26,18 @@ def init_embedding(n_vectors, dim):
 
 
 def l1_dissimilarity(a, b):
-    """Selector for the L1 translational kernels (torchkge/utils/dissimilarities.py:11)."""
-    raise RuntimeError("dissimilarity functions are kernel selectors here, not callables")
+    """torchkge/utils/dissimilarities.py:11-16.  The models use the function's IDENTITY to select
+    the L1 kernels (interfaces.py:205-208 does the same); calling it evaluates the reference's
+    expression with tensor ops on the tensors' device, for user code that does
+    ``model.dissimilarity(x, y)``."""
+    assert len(a.shape) == len(b.shape)
+    return (a - b).norm(p=1, dim=-1)
 
 
 def l2_dissimilarity(a, b):
-    """Selector for the L2 translational kernels (torchkge/utils/dissimilarities.py:19)."""
-    raise RuntimeError("dissimilarity functions are kernel selectors here, not callables")
+    """torchkge/utils/dissimilarities.py:19-25 (2-norm first, then squared); see l1_dissimilarity."""
+    assert len(a.shape) == len(b.shape)
+    return (a - b).norm(p=2, dim=-1) ** 2
 
 
 class Model(nn.Module):
@@ -42,7 +47,6 @@ class Model(nn.Module):
         super().__init__()
         self.n_ent = n_entities
         self.n_rel = n_relations
-        self._packed_cache = None  # (key, packed tensor) of the last table packed for inference
 
     # ---- training-side API -------------------------------------------------------------
     def forward(self, heads, tails, relations, negative_heads, negative_tails,
@@ -135,12 +139,13 @@ def _dense_scores(model, h, t, r):
     spec = ModelSpec(code, d, n_cand, b, tables[0], tables[1] if len(tables) > 1 else None,
                      rel[0], rel[1] if len(rel) > 1 else None)
     eng = default_engine()
-    key = tuple((tb.data_ptr(), tb._version, tuple(tb.shape)) for tb in tables) + (code,)
-    if model._packed_cache is None or model._packed_cache[0] != key:
-        model._packed_cache = (key, eng.pack(spec))
-    packed = model._packed_cache[1]
     rows = torch.stack([x.detach().contiguous() for x in ent], dim=1).contiguous()  # (b, planes, d)
-    return eng.score_all(spec, packed, side, rows, rows, None)
+    with _device_guard(rows.device):
+        # the scan layout is rebuilt on every call (2 x table bytes of traffic, small next to the
+        # b x n_cand scan): a cache keyed on data_ptr / _version would go stale under in-place
+        # updates through ``.data`` (optimizer steps on .data, ``weight.data.frac_()``)
+        packed = eng.pack(spec)
+        return eng.score_all(spec, packed, side, rows, rows, None)
 
 
 def _dense_relation_scores(model, hp, tp, rp):
@@ -162,13 +167,11 @@ def _dense_relation_scores(model, hp, tp, rp):
     rspec = relation_spec(ModelSpec(code, d, model.n_ent, n_rel, tables[0], None, tables[0],
                                     tables[1] if len(tables) > 1 else None))
     eng = default_engine()
-    key = tuple((tb.data_ptr(), tb._version, tuple(tb.shape)) for tb in tables) + (code, "rel")
-    if model._packed_cache is None or model._packed_cache[0] != key:
-        model._packed_cache = (key, eng.pack(rspec))
-    packed = model._packed_cache[1]
     hrows = torch.stack([x.detach().contiguous() for x in hp], dim=1).contiguous()  # (b, planes, d)
     trows = torch.stack([x.detach().contiguous() for x in tp], dim=1).contiguous()
-    return eng.score_all(rspec, packed, _lib.SIDE_REL, hrows, trows, None)
+    with _device_guard(hrows.device):
+        packed = eng.pack(rspec)       # rebuilt per call, see _dense_scores
+        return eng.score_all(rspec, packed, _lib.SIDE_REL, hrows, trows, None)
 
 
 def l1_torus_dissimilarity(a, b):
