@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 5
+#define KGE_ABI_VERSION 6
 
 /* error codes */
 #define KGE_OK 0
@@ -108,21 +108,32 @@ int kge_schedule_depth(int model, int dim);
  * (translation.py:105-125, bilinear.py:123-143, 247-267, 530-556). */
 /* ---- tensor-core operand image of a table shard (optional, see kge_rank_args_t.flags) ----
  * For models whose score is a dot product or a squared L2 distance (DistMult, RESCAL, ComplEx,
- * TransE-L2) the dense scan can run as a bf16x3 split GEMM on the tensor cores that decides
+ * TransE-L2) the dense scan can run as a split GEMM (x = hi + lo in bf16 or fp16, three MMAs per
+ * fp32 product) on the tensor cores that decides
  * every (query, candidate) pair whose approximate score differs from the true score by more
  * than a rigorous error bound, the remaining near-ties being re-scored exactly -- ranks are
  * unchanged.  kge_tc_pack_table writes the operand image that path streams:
- * [hi/lo bf16 planes in swizzled shared-memory order (64-byte swizzle spans by default, see
- * kge_tc_configure) | per-row norm bounds and squared norms].
+ * [hi/lo half-precision planes in swizzled shared-memory order (64-byte swizzle spans by default,
+ * see kge_tc_configure) | per-row norm bounds and squared norms | 256 bytes of per-image facts
+ * (scale, maxima) established on the device].
  * kge_tc_packed_bytes returns 0 for models without such a path (TransE-L1, RotatE). */
 size_t kge_tc_packed_bytes(int model, int64_t n_rows, int dim);
 /* Tuning / test hook of the tensor-core scan (process-wide; defaults also settable through the
  * environment: KGE_TC_BK, KGE_TC_RESIDENT, KGE_TC_GROUP, KGE_TC_MAX_CTAS).  bk = bf16 per k-block
  * (32: 64-byte swizzle, query-tile image resident in shared memory when k <= 224; 64: 128-byte
  * swizzle, both operands streamed); ct_group = candidate tiles per work unit (0 = automatic);
- * max_ctas = grid limit (0 = one CTA per SM).  Negative arguments keep the current value.
- * Images packed under one bk must be scanned under the same bk.  Results never depend on it. */
-int kge_tc_configure(int bk, int resident, int ct_group, int max_ctas);
+ * max_ctas = grid limit (0 = one CTA per SM); fp16 = operand format of the split (0: bf16, residual
+ * 2^-16 |x|; 1: fp16 with a per-image power-of-two pre-scale, residual 2^-22 |x|, i.e. a narrower
+ * near-tie band; KGE_TC_FP16).  Negative arguments keep the current value.
+ * Images packed under one (bk, fp16) must be scanned under the same.  Results never depend on it. */
+int kge_tc_configure(int bk, int resident, int ct_group, int max_ctas, int fp16);
+/* (host only) The constants of the rigorous error bound the tensor-core scan uses for `model` at
+ * `dim` under the current operand format (csrc/tc.h: tc_gamma, tc_gamma2):
+ *   dot models : |s_tc - s_ref| <= gamma |a| |b|
+ *   TransE-L2  : |s_tc - s_ref| <= 2 gamma |a| |b| + gamma2 (|a| + |b|)^2
+ * (|a|, |b| the per-row norm bounds, inflated by TcMeta::kappa under fp16).  Exposed so that the
+ * tests check the measured error against exactly what the kernel assumes. */
+int kge_tc_bound_constants(int model, int dim, float* gamma, float* gamma2, int* fp16);
 int kge_tc_pack_table(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
                       void* tc_packed, void* stream);
 

@@ -49,13 +49,14 @@ def test_size_queries():
                                            _lib.FLAG_TENSOR_CORE)
     assert with_tc > small + (64 * 100000 // 128) * 8  # near-tie list (1/128 of the pairs) + operand image
     # tensor-core operand image per 256-row tile: k-blocks x (hi, lo) x 256 rows x row bytes, + norms
+    # + 256 bytes of per-image facts (scale, maxima)
     try:
-        lib.kge_tc_configure(32, -1, -1, -1)   # 64-byte swizzle: 7 k-blocks of 32 for k = 200
-        assert lib.kge_tc_packed_bytes(_lib.DISTMULT, 1000, 200) == 4 * (7 * 2 * 256 * 64) + 2 * 1024 * 4
-        lib.kge_tc_configure(64, -1, -1, -1)   # 128-byte swizzle: 4 k-blocks of 64
-        assert lib.kge_tc_packed_bytes(_lib.DISTMULT, 1000, 200) == 4 * (4 * 2 * 256 * 128) + 2 * 1024 * 4
+        lib.kge_tc_configure(32, -1, -1, -1, -1)   # 64-byte swizzle: 7 k-blocks of 32 for k = 200
+        assert lib.kge_tc_packed_bytes(_lib.DISTMULT, 1000, 200) == 4 * (7 * 2 * 256 * 64) + 2 * 1024 * 4 + 256
+        lib.kge_tc_configure(64, -1, -1, -1, -1)   # 128-byte swizzle: 4 k-blocks of 64
+        assert lib.kge_tc_packed_bytes(_lib.DISTMULT, 1000, 200) == 4 * (4 * 2 * 256 * 128) + 2 * 1024 * 4 + 256
     finally:
-        lib.kge_tc_configure(32, -1, -1, -1)
+        lib.kge_tc_configure(32, -1, -1, -1, -1)
     assert lib.kge_tc_packed_bytes(_lib.TRANSE_L1, 1000, 200) == 0   # no tensor-core path
     assert lib.kge_tc_packed_bytes(_lib.ROTATE, 1000, 200) == 0
 

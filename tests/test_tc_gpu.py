@@ -31,9 +31,35 @@ def _approx_scores(eng, spec, side, h, t, r):
     return dump.cpu()
 
 
+@pytest.fixture(params=[0, 1], ids=["bf16", "fp16"])
+def operand_format(request):
+    """Both operand formats of the split (csrc/tc.h): restored to the environment's default afterwards."""
+    default = _lib.tc_bound_constants(_lib.DISTMULT, 16)[2]
+    _lib.tc_configure(fp16=request.param)
+    yield request.param
+    _lib.tc_configure(fp16=int(default))
+
+
+def _kernel_bound(code, d, k_total, na, nb, max_a, max_b, max_norm2_b, l2):
+    """The bound E(q, c) the scan's threshold test uses (csrc/tc.cu epilogue, csrc/tc.h), from the
+    library's own constants: na (nq, 1), nb (1, nc) row norms."""
+    gamma, gamma2, fp16 = _lib.tc_bound_constants(code, d)
+    e_abs = 0.0
+    if fp16:
+        na = na + max_a * 2.0 ** -11 * (k_total ** 0.5) * 1.01 / 3.0
+        nb = nb + max_b * 2.0 ** -11 * (k_total ** 0.5) * 1.01 / 3.0
+        if l2 and max_norm2_b > 0:
+            import math
+            phi = 2.0 ** (14 - math.frexp(0.5 * max_norm2_b)[1])
+            e_abs = 2.0 ** -22 / phi
+    if l2:
+        return 2 * gamma * na * nb + gamma2 * (na + nb) ** 2 + e_abs
+    return gamma * na * nb
+
+
 @pytest.mark.parametrize("kind", TC_KINDS)
 @pytest.mark.parametrize("d", [13, 50, 64, 200])
-def test_approximate_scores_within_half_the_bound(kind, d, cuda_device):
+def test_approximate_scores_within_half_the_bound(kind, d, cuda_device, operand_format):
     if kind == "rescal" and d > 64:
         pytest.skip("rescal d^2 tables: small dims only")
     n_ent, n_rel, b = 1300, 7, 150
@@ -53,13 +79,8 @@ def test_approximate_scores_within_half_the_bound(kind, d, cuda_device):
         got = _approx_scores(eng, spec, side, h.to(cuda_device), t.to(cuda_device), r.to(cuda_device))
         want = oracle.scores_all(kind, P, h, t, r, name).double()
         assert not torch.isnan(got).any()
-        # the bound the kernel uses: gamma * |a| |b|  (dot) or gamma * (|a| + |b|)^2  (L2)
         l2 = kind == "transe_l2"
         k_total = 2 * d if kind == "complex" else (d + 3 if l2 else d)  # csrc/api.cu: tc_k_total
-        depth = _lib.load().kge_schedule_depth(spec.code, d)           # depth of the ATen reduction tree
-        gamma = (3.0 * 2.0 ** -16 + 2.0 * (3.0 * ((k_total + 15) // 16) + 2.0) * 2.0 ** -22
-                 + (0.0 if l2 else (depth + 4.0) * 2.0 ** -24))        # csrc/tc.h: tc_gamma
-        gamma2 = (depth + 42.0) * 2.0 ** -24                           # csrc/tc.h: tc_gamma2
         # operand norms
         if kind == "complex":
             cand = torch.cat([P["re_ent"], P["im_ent"]], 1).double()
@@ -81,14 +102,89 @@ def test_approximate_scores_within_half_the_bound(kind, d, cuda_device):
         na, nb = q.norm(dim=1).view(-1, 1), cand.norm(dim=1).view(1, -1)
         if l2 and side == 1:   # head side: the kernel bounds |t - r| by |t| + |r| (see tc.cu)
             na = (P["ent"][t].double().norm(dim=1) + P["rel"][r].double().norm(dim=1)).view(-1, 1)
-        bound = (2 * gamma * na * nb + gamma2 * (na + nb) ** 2) if l2 else gamma * na * nb
+        bound = _kernel_bound(spec.code, d, k_total, na, nb, q.abs().max().item(), cand.abs().max().item(),
+                              (cand ** 2).sum(1).max().item(), l2)
         ratio = ((got.double() - want).abs() / bound).max().item()
         assert ratio < 0.5, "%s %s d=%d: error / bound = %.3f" % (kind, name, d, ratio)
 
 
+def _operands(shape, n_q, n_c, d, g):
+    """Adversarial operand families for the error bound (the CPU twin is tests/test_tc_bound_cpu.py)."""
+    a = torch.randn(n_q, d, generator=g)
+    b = torch.randn(n_c, d, generator=g)
+    if shape == "cancelling":        # large products of alternating sign: running sums far below sum |terms|
+        sign = torch.where(torch.arange(d) % 2 == 0, 1.0, -1.0)
+        a, b = a.abs(), b.abs() * sign
+    elif shape == "same_sign":       # every product positive: the accumulator grows monotonically (truncation bias)
+        a, b = a.abs(), b.abs()
+    elif shape == "wide":            # 2^-10 .. 2^10 per element
+        a = a * torch.exp2(torch.randint(-10, 11, (n_q, d), generator=g).float())
+        b = b * torch.exp2(torch.randint(-10, 11, (n_c, d), generator=g).float())
+    elif shape == "one_big":         # one dominant product per 16-term instruction, 15 small ones below its ulp
+        a, b = a.abs() * 2.0 ** -13, b.abs() * 2.0 ** -13
+        a[:, ::16] = 1.0 + a[:, ::16]
+        b[:, ::16] = 1.0 + b[:, ::16]
+    elif shape == "normalised":
+        a = torch.nn.functional.normalize(a, dim=1)
+        b = torch.nn.functional.normalize(b, dim=1)
+    return a.contiguous(), b.contiguous()
+
+
+@pytest.mark.parametrize("shape", ["normalised", "cancelling", "same_sign", "wide", "one_big"])
+@pytest.mark.parametrize("kind,d", [("distmult", 203), ("distmult", 800), ("distmult", 1024),
+                                    ("transe_l2", 200), ("transe_l2", 797), ("complex", 400)])
+def test_error_bound_holds_on_adversarial_operands(shape, kind, d, cuda_device, operand_format):
+    """|tensor-core score - reference fp32 score| <= the kernel's bound, pair by pair, on operand
+    families built to stress each term of the bound: K = 203, 800, 1024 (13, 50, 64 MMA k-steps x 3
+    instructions).  Queries are table rows with an identity relation, so the operands are exactly
+    the generated vectors."""
+    g = torch.Generator().manual_seed(1000 + d)
+    n_q, n_c = 96, 1100
+    dev = cuda_device
+    code = {"distmult": _lib.DISTMULT, "transe_l2": _lib.TRANSE_L2, "complex": _lib.COMPLEX}[kind]
+    l2 = kind == "transe_l2"
+    if kind == "complex":
+        a0, b0 = _operands(shape, n_q, n_c, d, g)
+        a1, b1 = _operands(shape, n_q, n_c, d, g)
+        ent0, ent1 = torch.cat([b0, a0]), torch.cat([b1, a1])
+        P = {"re_ent": ent0, "im_ent": ent1, "re_rel": torch.ones(1, d), "im_rel": torch.zeros(1, d)}
+        spec = ModelSpec(code, d, n_c, 1, ent0[:n_c].contiguous().to(dev), ent1[:n_c].contiguous().to(dev),
+                         P["re_rel"].to(dev), P["im_rel"].to(dev))
+        hrows = torch.stack([a0, a1], 1).contiguous().to(dev)        # (n_q, 2, d); q = h o (1 + 0i) = h
+        qv, cv = torch.cat([a0, a1], 1).double(), torch.cat([b0, b1], 1).double()
+        k_total = 2 * d
+    else:
+        a, b = _operands(shape, n_q, n_c, d, g)
+        rel = torch.ones(1, d) if kind == "distmult" else torch.zeros(1, d)   # h * 1 = h ; h + 0 = h
+        ent = torch.cat([b, a])
+        P = {"ent": ent, "rel": rel}
+        spec = ModelSpec(code, d, n_c, 1, ent[:n_c].contiguous().to(dev), None, rel.to(dev), None)
+        hrows = a.view(n_q, 1, d).contiguous().to(dev)
+        qv, cv = a.double(), b.double()
+        k_total = d + 3 if l2 else d
+    h_idx = torch.arange(n_c, n_c + n_q)
+    r_idx = torch.zeros(n_q, dtype=torch.int64)
+    want = oracle.scores_all(kind, P, h_idx, h_idx, r_idx, "tail")[:, :n_c].double()
+    eng = CudaEngine(tensor_core=True)
+    tcp = eng.pack_tc(spec)
+    dump = torch.full((n_q, n_c), float("nan"), device=dev)
+    raw = torch.zeros(n_q, dtype=torch.int32, device=dev)
+    eng.rank_side(spec, None, _lib.SIDE_TAIL, hrows, hrows, r_idx.to(dev), r_idx.to(dev), None, raw,
+                  torch.zeros_like(raw), tc_packed=tcp, tc_dump=dump)
+    torch.cuda.synchronize()
+    got = dump.cpu().double()
+    assert torch.isfinite(got).all()
+    na, nb = qv.norm(dim=1).view(-1, 1), cv.norm(dim=1).view(1, -1)
+    bound = _kernel_bound(code, d, k_total, na, nb, qv.abs().max().item(), cv.abs().max().item(),
+                          (cv ** 2).sum(1).max().item(), l2)
+    ratio = ((got - want).abs() / bound).max().item()
+    assert ratio <= 1.0, "%s %s d=%d: error / bound = %.3f" % (kind, shape, d, ratio)
+    print("tc bound %s %s d=%d fp16=%d: max error / bound = %.3f" % (kind, shape, d, operand_format, ratio))
+
+
 @pytest.mark.parametrize("kind", TC_KINDS)
 @pytest.mark.parametrize("d", [13, 50, 100])
-def test_ranks_equal_oracle_with_tensor_cores(kind, d, cuda_device):
+def test_ranks_equal_oracle_with_tensor_cores(kind, d, cuda_device, operand_format):
     if kind == "rescal" and not helpers.rescal_order_matches_here(d):
         pytest.skip("oneMKL on this CPU sums RESCAL's batched matmul in another order than the authoring machine")
     n_ent, n_rel = 1500, 9

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libkge_b200.so")
 TRANSE_L1, TRANSE_L2, DISTMULT, RESCAL, COMPLEX, ROTATE, TORUSE_L1, TORUSE_L2 = range(8)
 SIDE_TAIL, SIDE_HEAD, SIDE_REL = 0, 1, 2
 TILE_C, TILE_Q = 128, 64
-ABI_VERSION = 5
+ABI_VERSION = 6
 FLAG_TENSOR_CORE = 1
 FLAG_APPROX_SCAN = 2
 LOSS_LOGISTIC, LOSS_BCE = 1, 2
@@ -96,7 +96,9 @@ SIGNATURES = {
                                                _c.c_int]),
     "kge_schedule_depth": (_c.c_int, [_c.c_int, _c.c_int]),
     "kge_tc_packed_bytes": (_c.c_size_t, [_c.c_int, _c.c_int64, _c.c_int]),
-    "kge_tc_configure": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    "kge_tc_configure": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    "kge_tc_bound_constants": (_c.c_int, [_c.c_int, _c.c_int, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float),
+                                          _c.POINTER(_c.c_int)]),
     "kge_tc_pack_table": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _c.c_int, _p, _p]),
     "kge_rank_side": (_c.c_int, [_c.POINTER(RankArgs)]),
     "kge_filter_side": (_c.c_int, [_c.POINTER(RankArgs)]),
@@ -167,9 +169,17 @@ def build_schedule(model, dim):
     return perm, code
 
 
-def tc_configure(bk=-1, resident=-1, ct_group=-1, max_ctas=-1):
+def tc_configure(bk=-1, resident=-1, ct_group=-1, max_ctas=-1, fp16=-1):
     """Tuning / test hook of the tensor-core scan (include/kge_b200.h: kge_tc_configure)."""
-    check(load().kge_tc_configure(bk, resident, ct_group, max_ctas), "kge_tc_configure")
+    check(load().kge_tc_configure(bk, resident, ct_group, max_ctas, fp16), "kge_tc_configure")
+
+
+def tc_bound_constants(model, dim):
+    """(gamma, gamma2, fp16) of the tensor-core scan's error bound for (model, dim) -- host only."""
+    g, g2, f = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int(0)
+    check(load().kge_tc_bound_constants(model, dim, ctypes.byref(g), ctypes.byref(g2), ctypes.byref(f)),
+          "kge_tc_bound_constants")
+    return g.value, g2.value, bool(f.value)
 
 
 def scan_timing_enable(on=True):

@@ -21,6 +21,7 @@
 // Warps 2-9: epilogue -- tcgen05.ld the accumulator (one query row per thread, two warps per TMEM
 // lane quadrant), compare with two per-thread thresholds, count, append near-ties.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -111,9 +112,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= G::LAYOUT << 61;
   return d;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, K-major both, N = 256, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                           ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32 (bits [4,6) = 1), A / B format in bits [7,10) / [10,13)
+// (0 = fp16, 1 = bf16), K-major both, N = 256 (bits [17,23) = N >> 3), M = 128 (bits [24,29) = M >> 4)
+constexpr uint32_t IDESC_BASE = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t IDESC_BF16 = IDESC_BASE | (1u << 7) | (1u << 10);
+constexpr uint32_t IDESC_FP16 = IDESC_BASE;
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -243,9 +246,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
           const int k16s = min(G::K16, (p.k_total - kb * BKT + 15) / 16);
           for (int k = 0; k < k16s; ++k) {
             const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16-B units
-            umma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kb | k) ? 1u : 0u);
-            umma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1u);
-            umma_bf16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+            umma_bf16(d_tmem, a_hi + adv, b_hi + adv, p.idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(d_tmem, a_lo + adv, b_hi + adv, p.idesc, 1u);
+            umma_bf16(d_tmem, a_hi + adv, b_lo + adv, p.idesc, 1u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -280,6 +283,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
     int amb_n = 0;                              // entries in it (warp-uniform)
     float k1 = 0.f, k0 = 0.f, tbase = 0.f;
     constexpr float INFL = 1.f + 0x1p-19f;      // covers the fp32 rounding of E's evaluation
+    // the accumulator holds S * (a.b [- |b|^2/2]), S = scale_a * scale_b (a power of two; NaN when an
+    // operand could not be represented: both threshold tests then fail and every pair is rechecked)
+    const float S = p.meta_a->acc_scale;
+    const float inv_S = 1.f / S;
+    const float e_abs = p.meta_a->e_abs;
+    const float kappa_a = p.meta_a->kappa, kappa_b = p.meta_b->kappa;
     for (long long u = blockIdx.x; u < units.n_units; u += gridDim.x) {
      long long qt, ct_lo, ct_hi; units.decode(u, &qt, &ct_lo, &ct_hi);
      for (long long ct = ct_lo; ct < ct_hi; ++ct) {
@@ -305,7 +314,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
         cnt = 0; cur_qt = qt;
         const bool vq = q < p.n_q;
         st = vq ? p.s_true[q] : INFINITY;
-        qb = vq ? p.qbound[q] : 0.f;
+        qb = vq ? __fadd_ru(p.qbound[q], kappa_a) : 0.f;
         qn = vq ? p.qnorm2[q] : 0.f;
         if constexpr (L2) {
           // E = 2 gamma qb cb + gamma2 (qb + cb)^2 = cb (k1 + gamma2 cb) + k0
@@ -325,7 +334,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
       for (int b = 0; b < 4; ++b) {
         const long long c = ct * BN + c_begin + 32 * b + lane;
         const float x = c < p.n_rows ? p.cbound[c] : 0.f;
-        cbm[b] = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(x)));  // x >= 0
+        cbm[b] = __fadd_ru(__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(x))), kappa_b);  // x >= 0
       }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       fence_after();
@@ -345,9 +354,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
           float e;
           if constexpr (L2) e = fmaf(cb, fmaf(p.gamma2 * INFL, cb, k1), k0) * INFL;
           else e = k1 * cb;
+          e = __fadd_ru(e, e_abs);
           t_hi = __fadd_ru(tbase, e);
           t_lo = __fadd_rd(tbase, -e);
           if constexpr (L2) { t_hi = __fmul_ru(t_hi, 0.5f); t_lo = __fmul_rd(t_lo, 0.5f); }
+          t_hi = __fmul_ru(t_hi, S);   // exact (power of two) unless it overflows, then still on the safe side
+          t_lo = __fmul_rd(t_lo, S);
         }
         // 32 independent threshold tests -> two bit masks per thread (no per-element branches)
         // (NaN / inf anywhere -- accumulator, thresholds, norm bounds -- fails both tests and lands
@@ -358,7 +370,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
           const float f = __uint_as_float(v[j]);
           if constexpr (DUMP) {
             if (j < lim && q < p.n_q)
-              p.dump[(size_t)q * p.n_rows + ct * BN + c0 + j] = L2 ? fmaf(2.f, f, -qn) : f;
+              p.dump[(size_t)q * p.n_rows + ct * BN + c0 + j] = L2 ? fmaf(2.f, f * inv_S, -qn) : f * inv_S;
           } else {
             gt_mask |= (f > t_hi ? 1u : 0u) << j;
             lt_mask |= (f < t_lo ? 1u : 0u) << j;
@@ -461,24 +473,42 @@ __device__ __forceinline__ float operand_value(const float* __restrict__ p0,
   return k < dim ? p0[k] : p1[k - dim];
 }
 
-template <int ROWS, int BKT>
+// Half-precision formats of the split: bf16 (8 significant bits) or fp16 (11; operands pre-scaled)
+template <bool FP16> struct HalfT;
+template <> struct HalfT<false> {
+  using T = __nv_bfloat16;
+  static __device__ __forceinline__ T from(float x) { return __float2bfloat16_rn(x); }
+  static __device__ __forceinline__ float to(T h) { return __bfloat162float(h); }
+};
+template <> struct HalfT<true> {
+  using T = __half;
+  static __device__ __forceinline__ T from(float x) { return __float2half_rn(x); }
+  static __device__ __forceinline__ float to(T h) { return __half2float(h); }
+};
+
+template <int ROWS, int BKT, bool FP16>
 __global__ void pack_operand_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
                                     long long row_stride, long long plane1_offset, long long n_rows,
                                     int dim, int k_total, int n_kb, int sub_mode, int fold,
-                                    const float* __restrict__ norm2,
+                                    const float* __restrict__ norm2, const TcMeta* __restrict__ meta,
                                     unsigned char* __restrict__ out) {
   // src0 + row*row_stride = first plane of the row; second plane at +plane1_offset (same row)
   // or in src1 (separate table).  sub_mode = 1: value = plane1[k] - plane0[k]  (t - r, L2 head)
+  // Every value is multiplied by meta->scale (a power of two: exact) before it is split.
   // fold (L2 only; k_total = dim + 3): the three k slots after the data carry, on the candidate
-  // side (fold = 2), -|b|^2/2 split exactly into three bf16 pieces (hi plane; lo plane 0) and, on
-  // the query side (fold = 1), 1.0 -- so the hi*hi product adds -|b|^2/2 to every accumulator
-  // and the epilogue compares the accumulator with thresholds directly.
+  // side (fold = 2), -|b|^2/2 * phi split exactly into three half-precision pieces (hi plane; lo
+  // plane 0) and, on the query side (fold = 1), alpha = scale_a * scale_b / phi -- so the hi*hi
+  // product adds -S |b|^2/2 to every accumulator and the epilogue compares the accumulator with
+  // thresholds directly.
+  using H = HalfT<FP16>;
+  using HT = typename H::T;
   constexpr int CH = BKT / 8;        // 16-byte chunks per row
   constexpr int ROWB = 2 * BKT;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n_tiles = (n_rows + ROWS - 1) / ROWS;
   const long long total = n_tiles * n_kb * ROWS * CH;
   if (gid >= total) return;
+  const float scale = meta->scale, fold_c = meta->fold;
   const int j = (int)(gid % CH);
   long long rest = gid / CH;
   const int r = (int)(rest % ROWS);
@@ -486,7 +516,7 @@ __global__ void pack_operand_kernel(const float* __restrict__ src0, const float*
   const int kb = (int)(rest % n_kb);
   const long long tile = rest / n_kb;
   const long long row = tile * ROWS + r;
-  __nv_bfloat16 hi[8], lo[8];
+  HT hi[8], lo[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int k = kb * BKT + j * 8 + e;
@@ -495,17 +525,17 @@ __global__ void pack_operand_kernel(const float* __restrict__ src0, const float*
       if (fold && k >= dim) {
         if (k < dim + 3) {
           if (fold == 1) {
-            hi[e] = __float2bfloat16_rn(1.0f);
+            hi[e] = H::from(fold_c);                 // alpha: a power of two inside the format's range
           } else {
-            float rest = -0.5f * norm2[row];
-            __nv_bfloat16 piece = __float2bfloat16_rn(rest);
+            float rem = -0.5f * norm2[row] * fold_c;  // phi: a power of two (exact)
+            HT piece = H::from(rem);
             for (int i = 0; i < k - dim; ++i) {
-              rest -= __bfloat162float(piece);  // exact: piece holds the leading bits of rest
-              piece = __float2bfloat16_rn(rest);
+              rem -= H::to(piece);  // exact: piece holds the leading bits of rem
+              piece = H::from(rem);
             }
             hi[e] = piece;
           }
-          lo[e] = __float2bfloat16_rn(0.f);
+          lo[e] = H::from(0.f);
           continue;
         }
       } else {
@@ -515,9 +545,10 @@ __global__ void pack_operand_kernel(const float* __restrict__ src0, const float*
         else x = operand_value(a, b, dim, k, k_total);
       }
     }
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    x *= scale;
+    const HT h = H::from(x);
     hi[e] = h;
-    lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
+    lo[e] = H::from(x - H::to(h));
   }
   const size_t plane = (size_t)ROWS * ROWB;
   const size_t base = ((size_t)tile * n_kb + kb) * (2 * plane);
@@ -527,17 +558,20 @@ __global__ void pack_operand_kernel(const float* __restrict__ src0, const float*
   *reinterpret_cast<uint4*>(out + base + plane + off) = *reinterpret_cast<const uint4*>(lo);
 }
 
-// per-row |x|_2 (rounded up a little) and |x|_2^2 of the operand vector, one warp per row
+// per-row |x|_2 (rounded up a little) and |x|_2^2 of the operand vector, one warp per row; the
+// operand's largest |x| and largest |x|_2^2 are folded into meta (bit-pattern maxima of non-negative
+// floats: a NaN or inf anywhere wins, which invalidates the image -- see tc_meta_kernel)
 __global__ void row_norms_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
                                  long long row_stride, long long plane1_offset, long long n_rows,
                                  int dim, int k_total, int sub_mode, float* __restrict__ bound,
-                                 float* __restrict__ norm2) {
+                                 float* __restrict__ norm2, TcMeta* __restrict__ meta) {
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n_rows) return;
   const float* a = src0 + (size_t)w * row_stride;
   const float* b = src1 ? src1 + (size_t)w * row_stride : a + plane1_offset;
   double s = 0.0, sa = 0.0, sb = 0.0;
+  unsigned mx = 0u;
   for (int k = lane; k < k_total; k += 32) {
     float x;
     if (sub_mode) {
@@ -547,6 +581,7 @@ __global__ void row_norms_kernel(const float* __restrict__ src0, const float* __
       x = operand_value(a, b, dim, k, k_total);
     }
     s += (double)x * (double)x;
+    mx = max(mx, __float_as_uint(fabsf(x)));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -554,13 +589,70 @@ __global__ void row_norms_kernel(const float* __restrict__ src0, const float* __
     sa += __shfl_xor_sync(0xffffffffu, sa, o);
     sb += __shfl_xor_sync(0xffffffffu, sb, o);
   }
+  mx = __reduce_max_sync(0xffffffffu, mx);
   if (lane == 0) {
-    norm2[w] = (float)s;
+    const float n2 = (float)s;
+    norm2[w] = n2;
     // L2 head side: the reference rounds c + r before subtracting t, an error that scales with
     // |r| and |t| separately, so the bound uses |t| + |r| (>= |t - r|) for this operand
     const double nb = sub_mode ? sqrt(sa) + sqrt(sb) : sqrt(s);
     bound[w] = (float)(nb * (1.0 + 1e-6)) + 1e-30f;
+    atomicMax(reinterpret_cast<unsigned*>(&meta->max_abs), mx);
+    atomicMax(reinterpret_cast<unsigned*>(&meta->max_norm2), __float_as_uint(fabsf(n2)));
   }
+}
+
+// Scales of one operand image, decided on the device from the maxima row_norms_kernel gathered.
+//   bf16: scale = 1, phi = alpha = 1, S = 1, nothing else.
+//   fp16: scale = 2^e with max|x| * scale in [2^8, 2^9): hi never overflows (65504), the lo part of
+//         every element >= 2^-12 max|x| is a normal fp16 number (residual 2^-22 |x|); smaller elements
+//         are off by <= 2^-25 in scaled units = 2^-33 max|x|, which sum_k |y_k| <= sqrt(K) |y| turns into
+//         <= 2^-33 sqrt(K) max|x| |y| per pair: covered by adding kappa = 2^-11 sqrt(K) max|x| / 3 (+1 %)
+//         to the row bounds (gamma >= 3 2^-22 multiplies them).
+//         phi (candidate side, L2 fold): max_rows(|b|^2/2) * phi in [2^13, 2^14): the three pieces of
+//         -|b|^2/2 * phi fit fp16 and are exact to 33 bits for every row within 2^-13 of the largest;
+//         beyond, the absolute error 3 * 2^-25 / phi (|b|^2/2 units) goes into e_abs.
+//         alpha (query side) = scale_a * scale_b / phi must itself be an fp16 normal power of two.
+//   An operand with a NaN / inf entry, or whose alpha falls outside fp16, gets scale = NaN: its image,
+//   S and hence both thresholds are NaN, every pair fails both tests and is rechecked exactly.
+__global__ void tc_meta_kernel(TcMeta* __restrict__ m, const TcMeta* __restrict__ other, int k_total,
+                               int is_query, int l2, int fp16) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float mx = m->max_abs, n2 = m->max_norm2;
+  const bool finite = mx <= 3.0e38f && n2 <= 3.0e38f;   // false for NaN and inf
+  float scale = 1.f, fold = 1.f, kappa = 0.f, acc = 1.f, e_abs = 0.f;
+  bool ok = finite;
+  if (fp16 && finite) {
+    if (mx > 0.f) {
+      int ex; frexpf(mx, &ex);                 // mx = f * 2^ex, f in [0.5, 1)
+      int e = 9 - ex;
+      e = max(-120, min(120, e));
+      scale = ldexpf(1.f, e);
+      kappa = mx * 0x1p-11f * sqrtf((float)k_total) * (1.01f / 3.f);
+    }
+    if (!is_query && l2 && n2 > 0.f) {
+      int ex; frexpf(0.5f * n2, &ex);
+      fold = ldexpf(1.f, max(-120, min(120, 14 - ex)));   // phi
+    }
+  }
+  if (is_query) {
+    const float sb = other->scale, phi = other->fold;
+    acc = scale * sb;                                      // NaN if the table image is invalid
+    if (l2) {
+      fold = acc / phi;                                    // alpha
+      if (fp16) {
+        if (!(fold >= 0x1p-14f && fold <= 0x1p15f)) ok = false;
+        e_abs = 0x1p-22f / phi;                            // 8 * 2^-25 / phi: fold pieces, score = 2 f - |a|^2
+      }
+    }
+    if (!(acc >= 0x1p-60f && acc <= 0x1p60f)) ok = false;
+  }
+  const float nanv = __uint_as_float(0x7fc00000u);
+  m->scale = ok ? scale : nanv;
+  m->fold = ok ? fold : nanv;
+  m->acc_scale = ok ? acc : nanv;
+  m->e_abs = e_abs;
+  m->kappa = kappa;
 }
 
 template <int EL>
@@ -632,10 +724,11 @@ int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 struct Config {
-  int bk, resident, group, max_ctas;
+  int bk, resident, group, max_ctas, fp16;
   Config()
       : bk(env_int("KGE_TC_BK", 32) == 64 ? 64 : 32), resident(env_int("KGE_TC_RESIDENT", 1) != 0),
-        group(env_int("KGE_TC_GROUP", 0)), max_ctas(env_int("KGE_TC_MAX_CTAS", 0)) {}
+        group(env_int("KGE_TC_GROUP", 0)), max_ctas(env_int("KGE_TC_MAX_CTAS", 0)),
+        fp16(env_int("KGE_TC_FP16", 0) != 0) {}
 };
 Config& config() {
   static Config c;
@@ -643,13 +736,15 @@ Config& config() {
 }
 }  // namespace
 
-void configure(int bk_, int resident_, int group_, int max_ctas_) {
+void configure(int bk_, int resident_, int group_, int max_ctas_, int fp16_) {
   Config& c = config();
   if (bk_ == 32 || bk_ == 64) c.bk = bk_;
   if (resident_ >= 0) c.resident = resident_ != 0;
   if (group_ >= 0) c.group = group_;
   if (max_ctas_ >= 0) c.max_ctas = max_ctas_;
+  if (fp16_ >= 0) c.fp16 = fp16_ != 0;
 }
+bool fp16() { return config().fp16 != 0; }
 int bk() { return config().bk; }
 int n_kblocks(int k_total) { return (k_total + bk() - 1) / bk(); }
 bool resident(int n_kb) {
@@ -669,40 +764,51 @@ size_t b_image_bytes(long long n_rows, int n_kb) {
   return (size_t)n_ct * n_kb * 2 * BN * 2 * bk();
 }
 
+namespace {
+template <int ROWS>
+void launch_pack_operand(const float* src0, const float* src1, long long row_stride, long long plane1_offset,
+                         long long n_rows, int dim, int k_total, int n_kb, int sub_mode, int fold,
+                         const float* norm2, const TcMeta* meta, unsigned char* out, cudaStream_t st) {
+  const long long n_tiles = (n_rows + ROWS - 1) / ROWS;
+  const long long total = n_tiles * n_kb * ROWS * (bk() / 8);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+#define KGE_PACK(BKT, F16)                                                                              \
+  pack_operand_kernel<ROWS, BKT, F16><<<blocks, 256, 0, st>>>(src0, src1, row_stride, plane1_offset, n_rows, dim, \
+                                                              k_total, n_kb, sub_mode, fold, norm2, meta, out)
+  if (bk() == 64) { if (fp16()) KGE_PACK(64, true); else KGE_PACK(64, false); }
+  else { if (fp16()) KGE_PACK(32, true); else KGE_PACK(32, false); }
+#undef KGE_PACK
+}
+}  // namespace
+
+uint32_t instruction_descriptor() { return fp16() ? IDESC_FP16 : IDESC_BF16; }
+
 cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows, int dim, int k_total,
                           int n_kb, bool fold, unsigned char* bpack, float* cbound, float* cnorm2,
-                          cudaStream_t st) {
+                          TcMeta* meta_b, cudaStream_t st) {
   if (n_rows <= 0) return cudaSuccess;
-  const long long n_ct = (n_rows + BN - 1) / BN;
-  const long long total = n_ct * n_kb * BN * (bk() / 8);
+  cudaError_t e = cudaMemsetAsync(meta_b, 0, TC_META_BYTES, st);
+  if (e != cudaSuccess) return e;
   // norms first: with fold the image carries -|b|^2/2 (the SAME fp32 value the bound uses)
   row_norms_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, st>>>(
-      ent0, ent1, dim, 0, n_rows, dim, fold ? dim : k_total, 0, cbound, cnorm2);
-  const int f = fold ? 2 : 0;
-  if (bk() == 64)
-    pack_operand_kernel<BN, 64><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        ent0, ent1, dim, 0, n_rows, dim, k_total, n_kb, 0, f, cnorm2, bpack);
-  else
-    pack_operand_kernel<BN, 32><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        ent0, ent1, dim, 0, n_rows, dim, k_total, n_kb, 0, f, cnorm2, bpack);
+      ent0, ent1, dim, 0, n_rows, dim, fold ? dim : k_total, 0, cbound, cnorm2, meta_b);
+  tc_meta_kernel<<<1, 32, 0, st>>>(meta_b, nullptr, k_total, 0, fold ? 1 : 0, fp16() ? 1 : 0);
+  launch_pack_operand<BN>(ent0, ent1, dim, 0, n_rows, dim, k_total, n_kb, 0, fold ? 2 : 0, cnorm2, meta_b, bpack, st);
   return cudaGetLastError();
 }
 
 cudaError_t launch_pack_a(const float* qplain, int qw, long long n_q, int dim, int k_total, int n_kb,
                           int sub_mode, bool fold, unsigned char* apack, float* qbound, float* qnorm2,
-                          cudaStream_t st) {
+                          TcMeta* meta_a, const TcMeta* meta_b, cudaStream_t st) {
   if (n_q <= 0) return cudaSuccess;
-  const long long n_qt = (n_q + BM - 1) / BM;
-  const long long total = n_qt * n_kb * BM * (bk() / 8);
+  cudaError_t e = cudaMemsetAsync(meta_a, 0, TC_META_BYTES, st);
+  if (e != cudaSuccess) return e;
   // qplain rows are [qw][dim]: plane 1 (if any) follows plane 0 inside the row
-  if (bk() == 64)
-    pack_operand_kernel<BM, 64><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        qplain, nullptr, (long long)qw * dim, dim, n_q, dim, k_total, n_kb, sub_mode, fold ? 1 : 0, nullptr, apack);
-  else
-    pack_operand_kernel<BM, 32><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        qplain, nullptr, (long long)qw * dim, dim, n_q, dim, k_total, n_kb, sub_mode, fold ? 1 : 0, nullptr, apack);
   row_norms_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, st>>>(
-      qplain, nullptr, (long long)qw * dim, dim, n_q, dim, fold ? dim : k_total, sub_mode, qbound, qnorm2);
+      qplain, nullptr, (long long)qw * dim, dim, n_q, dim, fold ? dim : k_total, sub_mode, qbound, qnorm2, meta_a);
+  tc_meta_kernel<<<1, 32, 0, st>>>(meta_a, meta_b, k_total, 1, fold ? 1 : 0, fp16() ? 1 : 0);
+  launch_pack_operand<BM>(qplain, nullptr, (long long)qw * dim, dim, n_q, dim, k_total, n_kb, sub_mode,
+                          fold ? 1 : 0, nullptr, meta_a, apack, st);
   return cudaGetLastError();
 }
 
@@ -740,6 +846,7 @@ cudaError_t launch_variant(const TcScanParams& p, int grid, cudaStream_t st) {
 cudaError_t launch_tc_scan(const TcScanParams& p_in, cudaStream_t st) {
   TcScanParams p = p_in;
   p.ct_group = ct_group(p.n_kb);
+  p.idesc = instruction_descriptor();
   const int grid = scan_grid_size(p.n_q, p.n_rows, p.n_kb);
   if (grid <= 0) return cudaSuccess;
   if (bk() == 64) return launch_variant<64, false>(p, grid, st);

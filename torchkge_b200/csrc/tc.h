@@ -13,9 +13,28 @@ constexpr int TC_BN = 256;       // candidates per MMA tile (TMEM columns, fp32)
 int bk();
 int n_kblocks(int k_total);
 // Tuning / test hook (kge_tc_configure): bk 32|64, resident 0|1, ct_group (0 = automatic),
-// max_ctas (0 = one per SM); negative values keep the current setting.  Operand images packed
-// under one bk must be scanned under the same bk.
-void configure(int bk, int resident, int ct_group, int max_ctas);
+// max_ctas (0 = one per SM), fp16 0|1 (operand format of the split, see below); negative values
+// keep the current setting.  Operand images packed under one (bk, fp16) must be scanned under the same.
+void configure(int bk, int resident, int ct_group, int max_ctas, int fp16);
+// Operand format of the split x = hi + lo: bf16 (8 significant bits each, residual 2^-16 |x|) or
+// fp16 (11 bits each, residual 2^-22 |x|, operands pre-scaled by a power of two per table so that
+// the lo parts stay in fp16's normal range).  KGE_TC_FP16=0|1.
+bool fp16();
+
+// Per-operand facts the pack kernels establish ON THE DEVICE (no host round trip) and the scan
+// reads: 32 bytes at the end of the candidate image (B) / in the call's workspace (A).
+struct TcMeta {
+  float scale;      // power of two the operand was multiplied by (1 for bf16); NaN: operand has non-finite
+                    // entries or its range cannot be represented -> every pair goes to the exact recheck
+  float max_abs;    // max |x| over the operand        (bit pattern maximum: NaN / inf win)
+  float max_norm2;  // max row |x|^2
+  float fold;       // B: phi (the fold slots hold -|b|^2/2 * phi);  A: alpha (its fold slots hold alpha)
+  float acc_scale;  // A only: S = scale_a * scale_b = alpha * phi; the accumulator holds S * (a.b - |b|^2/2)
+  float e_abs;      // A only: absolute error (score units) of the scaled representation
+  float kappa;      // added to every row's norm bound (covers the absolute residual of subnormal lo parts)
+  float reserved;
+};
+constexpr size_t TC_META_BYTES = 256;
 
 struct TcScanParams {
   const unsigned char* apack;  // [n_qt][n_kb][hi,lo][128 rows x 2*bk() B, swizzled]
@@ -30,6 +49,9 @@ struct TcScanParams {
   int2* amb_pairs;                // [n_qt][amb_cap]
   unsigned long long amb_cap;     // capacity of ONE region
   float* dump;                 // debug: write approximate scores [n_q][n_rows] instead of counting
+  const TcMeta* meta_a;        // device: facts of the query image (this call)
+  const TcMeta* meta_b;        // device: facts of the candidate image
+  uint32_t idesc;              // tcgen05 instruction descriptor (operand format bf16 / fp16)
   float gamma;                 // tc_gamma(k)
   float gamma2;                // tc_gamma2(k) (L2 only)
   int l2;                      // 1: score = -(|a|^2 + |b|^2 - 2 a.b)
@@ -43,10 +65,16 @@ struct TcScanParams {
 //   dot models : eps = gamma  * |a| |b|
 //   L2         : eps = gamma  * 2 |a| |b|  +  gamma2 * (|a| + |b|)^2
 // gamma collects everything proportional to sum_k |a_k b_k| <= |a| |b|:
-//   bf16 splitting x = hi + lo + r, |r| <= 2^-16 |x| (two roundings to 8 significant bits):
-//     dropped lo*lo, a*r_b, r_a*b                                   -> 3 * 2^-16       (exact bound)
-//   fp32 accumulation inside the tensor core: assumed <= 2 ulp of the running magnitude per
-//     MMA instruction, 3 instructions per 16 terms, doubled for safety -> 2 (3 ceil(k/16) + 2) 2^-22
+//   splitting x = hi + lo + r into two half-precision numbers (two roundings to p significant bits:
+//     p = 8 for bf16, 11 for fp16), |r| <= 2^-2p |x|; dropped lo*lo, a*r_b, r_a*b
+//                                                                   -> 3 * 2^-2p (1 + 2^-p)  (exact bound)
+//     (fp16 only: a lo part below fp16's normal range is off by <= 2^-25 in scaled units instead;
+//      that absolute residual is carried by TcMeta::kappa, an additive inflation of the row bounds)
+//   fp32 accumulation inside the tensor core: every tcgen05.mma adds 16 exact products to the
+//     accumulator; MEASURED on B200 (scripts/tc_numerics_probe.py, profiles/r02_tc_numerics_probe.md):
+//     |result - exact| <= TC_ACC_ULPS * 2^-24 * (|acc_in| + sum |products|) per instruction.
+//     All 3 ceil(k/16) instructions see a running magnitude <= sum_k |a_k b_k| (1 + 2^-p)^2
+//                                                       -> TC_ACC_ULPS (3 ceil(k/16) + 2) 2^-24
 //   dot models only: the reference's own fp32 evaluation -- every product rounded once (ComplEx:
 //     two products and their sum), then summed in ATen's cascade order, whose tree depth
 //     `ref_depth` (schedule.h: schedule_depth, computed from the very schedule the exact kernels
@@ -56,29 +84,32 @@ struct TcScanParams {
 //   by |c| + |r| + |t| -- the head-side query bound is |t| + |r| for that reason), squares it,
 //   sums in the 8-lane norm order (depth ref_depth), takes an exactly rounded sqrt and squares it:
 //     relative (ref_depth + 10) u on sum x^2;
-//   this side: |a|^2 and |b|^2 rounded to fp32 (2u), |b|^2/2 carried as three bf16 pieces (u),
-//   the <= 6 MMA instructions that accumulate it (6 * 2^-21 * |b|^2 / 2 = 24 u |b|^2), threshold
-//   arithmetic is directed-rounded                                    -> (ref_depth + 42) * 2^-24
-// tests/test_tc_gpu.py measures the actual error on every model and requires it to stay below
-// half of the bound.
-inline float tc_gamma(int k_total, int ref_depth, bool l2) {
-  const double split = 3.0 * 0x1p-16;
-  const double accum = 2.0 * (3.0 * ((k_total + 15) / 16) + 2.0) * 0x1p-22;
+//   this side: |a|^2 and |b|^2 rounded to fp32 (2u), |b|^2/2 carried as three half-precision pieces
+//   (u), the <= 6 MMA instructions that accumulate it (6 TC_ACC_ULPS u |b|^2 / 2), threshold
+//   arithmetic is directed-rounded                     -> (ref_depth + 18 + 3 TC_ACC_ULPS) * 2^-24
+// tests/test_tc_gpu.py measures the actual error on random AND adversarial operands (cancelling,
+// wide dynamic range, same sign) and requires error <= bound.
+constexpr double TC_ACC_ULPS = 8.0;   // per-instruction accumulation error in units of 2^-24 * running magnitude
+inline float tc_gamma(int k_total, int ref_depth, bool l2, bool fp16 = false) {
+  const double split = fp16 ? 3.0 * 0x1p-22 * (1.0 + 0x1p-11) : 3.0 * 0x1p-16 * (1.0 + 0x1p-8);
+  const double accum = TC_ACC_ULPS * (3.0 * ((k_total + 15) / 16) + 2.0) * 0x1p-24;
   const double ref = l2 ? 0.0 : (ref_depth + 4.0) * 0x1p-24;
   return (float)(split + accum + ref);
 }
-inline float tc_gamma2(int ref_depth) { return (float)((ref_depth + 42.0) * 0x1p-24); }
+inline float tc_gamma2(int ref_depth) { return (float)((ref_depth + 18.0 + 3.0 * TC_ACC_ULPS) * 0x1p-24); }
 
 size_t a_image_bytes(long long n_q, int n_kb);
 size_t b_image_bytes(long long n_rows, int n_kb);
 // fold = true (L2 models, k_total = dim + 3): the images carry -|b|^2/2 resp. 1.0 in the three k
 // slots after the data, so the accumulator already holds  a.b - |b|^2/2.
+// meta_b / meta_a: TC_META_BYTES of device memory each (written here, read by the scan)
 cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows, int dim, int k_total,
                           int n_kb, bool fold, unsigned char* bpack, float* cbound, float* cnorm2,
-                          cudaStream_t st);
+                          TcMeta* meta_b, cudaStream_t st);
 cudaError_t launch_pack_a(const float* qplain, int qw, long long n_q, int dim, int k_total, int n_kb,
                           int sub_mode, bool fold, unsigned char* apack, float* qbound, float* qnorm2,
-                          cudaStream_t st);
+                          TcMeta* meta_a, const TcMeta* meta_b, cudaStream_t st);
+uint32_t instruction_descriptor();
 cudaError_t launch_tc_scan(const TcScanParams& p, cudaStream_t st);
 // The near-tie list is split into one region per QUERY TILE (regions = n_qt): region_counts[regions]
 // (zeroed by the caller), pairs[regions][region_cap].  A region's pairs all belong to the same 128
