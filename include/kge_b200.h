@@ -127,6 +127,16 @@ size_t kge_tc_packed_bytes(int model, int64_t n_rows, int dim);
  * near-tie band; KGE_TC_FP16).  Negative arguments keep the current value.
  * Images packed under one (bk, fp16) must be scanned under the same.  Results never depend on it. */
 int kge_tc_configure(int bk, int resident, int ct_group, int max_ctas, int fp16);
+/* (host only) identifies the operand-image layout kge_tc_configure currently selects (k-block width
+ * and operand format): an image may only be scanned under the layout it was packed under. */
+int kge_tc_layout_id(void);
+/* kge_tc_pack_table for callers that KEEP the image between evaluations: `guard` = 4 device uint64
+ * (zero-initialised once, owned by the caller together with tc_packed).  The call computes a 128-bit
+ * content checksum of the table (one read of the table at HBM speed) and rebuilds the image only
+ * when it differs from the checksum recorded at the last rebuild -- in-place weight updates of any
+ * kind (optimizer steps, `.data` edits) are therefore always picked up.  guard = NULL: always rebuild. */
+int kge_tc_pack_table_cached(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
+                             void* tc_packed, uint64_t* guard, void* stream);
 /* (host only) The constants of the rigorous error bound the tensor-core scan uses for `model` at
  * `dim` under the current operand format (csrc/tc.h: tc_gamma, tc_gamma2):
  *   dot models : |s_tc - s_ref| <= gamma |a| |b|
@@ -246,6 +256,35 @@ typedef struct {
   void* stream;
 } kge_score_all_args_t;
 int kge_score_all(const kge_score_all_args_t* args);
+
+/* ---- top-k inference (EntityInference / RelationInference, torchkge/inference.py:78-250) ------
+ * pred[i][0..k) / scores[i][0..k): the k best candidates of query i and their exact (ATen-order)
+ * scores, best first -- what the reference obtains from inference_scoring_function, filter_scores
+ * (true_idx = None: every listed candidate masked with -inf, utils/modeling.py:91-102) and
+ * sort(descending=True)[:, :k] -- without an (n, n_rows) score matrix: the dense scan runs in a
+ * collect mode that writes out only candidates not below the query's current k-th best, a chunk of
+ * candidate rows at a time, merged into a per-query sorted list after every chunk.  NaN ranks above
+ * everything (as in torch's sort); exact ties are ordered by ascending candidate id. */
+typedef struct {
+  int32_t model, side, dim, k;   /* 1 <= k <= 1024, k <= n_rows */
+  int64_t n;                     /* queries */
+  int64_t n_rows;                /* candidates (rows of the packed table) */
+  const float* packed;           /* kge_pack_table output of the candidate table */
+  const float* rel0;
+  const float* rel1;
+  const float* hrows;
+  const float* trows;
+  const int64_t* r_idx;          /* as in kge_score_all_args_t */
+  const int64_t* mask_offs;      /* [n+1] CSR of candidates to mask with -inf, or NULL */
+  const int64_t* mask_ids;       /* candidate ids, ASCENDING within each row */
+  int64_t* pred;                 /* [n][k] out */
+  float* scores;                 /* [n][k] out */
+  void* workspace;               /* kge_topk_workspace_bytes() bytes, 256-B aligned */
+  size_t workspace_bytes;
+  void* stream;
+} kge_topk_args_t;
+size_t kge_topk_workspace_bytes(int model, int side, int dim, int64_t n, int64_t n_rows, int k);
+int kge_topk_side(const kge_topk_args_t* args);
 
 /* ---- training side ----------------------------------------------------------------------
  * Tables as in ModelSpec order: ent0/ent1 entity planes (n_ent, dim), rel0/rel1 relation

@@ -284,3 +284,36 @@ def test_rotate_bound_and_refine_gives_oracle_ranks(d, refine, cuda_device):
         assert 2 * n_test <= found < 0.05 * 2 * n_test * n_ent     # at least the true entities themselves
     else:
         assert len(eng.tc_stats) == 0
+
+
+def test_cached_operand_image_follows_in_place_weight_updates(cuda_device):
+    """The engine keeps the tensor-core operand image between evaluations, guarded by a device-side
+    content checksum of the table: in-place updates that leave data_ptr and _version untouched
+    (``weight.data.mul_``, an optimizer step on ``.data``) must be picked up, an unchanged table must
+    not be rebuilt (same ranks either way)."""
+    import torchkge_b200.engine as engine_mod
+    n_ent, n_rel, d = 900, 6, 48
+    kg, dh, dt = helpers.make_kg(n_ent, n_rel, n_facts=5000, n_test=260, seed=77)
+    model = helpers.make_model("complex", d, n_ent, n_rel, seed=7).to(cuda_device)
+    eng = CudaEngine(tensor_core=True)
+    assert eng.tc_cache_entries > 0
+    old = engine_mod._default_engine
+    engine_mod._default_engine = eng
+    try:
+        for step in range(3):
+            if step == 1:
+                pass                                            # unchanged table: served from the cache
+            if step == 2:
+                with torch.no_grad():
+                    model.re_ent_emb.weight.data[::3] *= -1.5   # same storage, same _version
+                    model.im_ent_emb.weight.data[5] = 0.25
+            ev = tk.LinkPredictionEvaluator(model, kg)
+            ev.evaluate(b_size=64, verbose=False)
+            P = helpers.oracle_params("complex", model)
+            ref = oracle.link_prediction("complex", P, kg.head_idx, kg.tail_idx, kg.relations, dh, dt, 64)
+            for a, b in zip((ev.rank_true_heads, ev.rank_true_tails, ev.filt_rank_true_heads,
+                             ev.filt_rank_true_tails), ref):
+                assert torch.equal(a, b), "step %d" % step
+            assert len(eng._tc_cache) == 1
+    finally:
+        engine_mod._default_engine = old

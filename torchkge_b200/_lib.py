@@ -58,6 +58,17 @@ class ScoreAllArgs(ctypes.Structure):
     ]
 
 
+class TopkArgs(ctypes.Structure):
+    """kge_topk_args_t"""
+    _fields_ = [
+        ("model", _c.c_int32), ("side", _c.c_int32), ("dim", _c.c_int32), ("k", _c.c_int32),
+        ("n", _c.c_int64), ("n_rows", _c.c_int64),
+        ("packed", _p), ("rel0", _p), ("rel1", _p), ("hrows", _p), ("trows", _p), ("r_idx", _p),
+        ("mask_offs", _p), ("mask_ids", _p), ("pred", _p), ("scores", _p),
+        ("workspace", _p), ("workspace_bytes", _c.c_size_t), ("stream", _p),
+    ]
+
+
 class Tables(ctypes.Structure):
     """kge_tables_t"""
     _fields_ = [("model", _c.c_int32), ("dim", _c.c_int32),
@@ -99,11 +110,15 @@ SIGNATURES = {
     "kge_tc_configure": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     "kge_tc_bound_constants": (_c.c_int, [_c.c_int, _c.c_int, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float),
                                           _c.POINTER(_c.c_int)]),
+    "kge_tc_layout_id": (_c.c_int, []),
     "kge_tc_pack_table": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _c.c_int, _p, _p]),
+    "kge_tc_pack_table_cached": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _c.c_int, _p, _p, _p]),
     "kge_rank_side": (_c.c_int, [_c.POINTER(RankArgs)]),
     "kge_filter_side": (_c.c_int, [_c.POINTER(RankArgs)]),
     "kge_finalize_ranks": (_c.c_int, [_p, _p, _c.c_int64, _p, _p, _p]),
     "kge_score_all": (_c.c_int, [_c.POINTER(ScoreAllArgs)]),
+    "kge_topk_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64, _c.c_int]),
+    "kge_topk_side": (_c.c_int, [_c.POINTER(TopkArgs)]),
     "kge_score_triples_fwd": (_c.c_int, [_c.POINTER(Tables), _p, _p, _p, _c.c_int64, _p, _p]),
     "kge_score_triples_bwd": (_c.c_int, [_c.POINTER(Tables), _c.POINTER(Grads), _p, _p, _p,
                                          _c.c_int64, _p, _p]),

@@ -306,6 +306,8 @@ int kge_tc_configure(int bk, int resident, int ct_group, int max_ctas, int fp16)
   return KGE_OK;
 }
 
+int kge_tc_layout_id(void) { return kge::tc::bk() * 2 + (kge::tc::fp16() ? 1 : 0); }
+
 int kge_tc_bound_constants(int model, int dim, float* gamma, float* gamma2, int* fp16) {
   const int el = kge::elem_kind_for(model, KGE_SIDE_TAIL);
   if (el < 0 || !tc_supported(el)) return fail(KGE_ERR_UNSUPPORTED, "kge_tc_bound_constants: model has no tensor-core path");
@@ -320,6 +322,11 @@ int kge_tc_bound_constants(int model, int dim, float* gamma, float* gamma2, int*
 
 int kge_tc_pack_table(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
                       void* tc_packed, void* stream) {
+  return kge_tc_pack_table_cached(model, ent0, ent1, n_rows, dim, tc_packed, nullptr, stream);
+}
+
+int kge_tc_pack_table_cached(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
+                             void* tc_packed, uint64_t* guard, void* stream) {
   const int el = kge::elem_kind_for(model, KGE_SIDE_TAIL);
   if (el < 0 || !tc_supported(el)) return fail(KGE_ERR_UNSUPPORTED, "kge_tc_pack_table: model has no tensor-core path");
   if (n_rows <= 0) return KGE_OK;
@@ -333,7 +340,9 @@ int kge_tc_pack_table(int model, const float* ent0, const float* ent1, int64_t n
   float* cbound = reinterpret_cast<float*>(bpack + kge::tc::b_image_bytes(n_rows, n_kb));
   float* cnorm2 = cbound + (size_t)n_ct * kge::tc::TC_BN;
   KGE_CUDA_TRY(kge::tc::launch_pack_b(ent0, ent1, n_rows, dim, k_total, n_kb, tc_is_l2(el), bpack, cbound, cnorm2,
-                                      tc_meta_of(bpack, n_rows, n_kb), static_cast<cudaStream_t>(stream)),
+                                      tc_meta_of(bpack, n_rows, n_kb),
+                                      reinterpret_cast<unsigned long long*>(guard),
+                                      static_cast<cudaStream_t>(stream)),
                "tc pack table");
   return KGE_OK;
 }
@@ -449,6 +458,7 @@ int kge_rank_side(const kge_rank_args_t* a) {
     p.n_ct = (a->n_rows + kge::TILE_C - 1) / kge::TILE_C;
     p.n_qt = n_qt;
     p.amb_count = nullptr; p.amb_pairs = nullptr; p.amb_cap = 0; p.rel_eps = 0.f; p.abs_eps = 0.f;
+    p.col_buf = nullptr; p.col_count = nullptr; p.col_cap = 0; p.col_id_base = 0; p.col_dense = 0;
     if (use_approx) {
       // RotatE bound-and-refine: |s~ - s_ATen| <= rel_eps |s~| (all terms >= 0).  Per element the
       // exact path is within 4 u and the approximate one within 3 u + 2^-21 (sqrt.approx) of the
@@ -542,6 +552,7 @@ int kge_score_all(const kge_score_all_args_t* a) {
   p.code_host = hs->s.code.data();
   p.counts = nullptr;
   p.amb_count = nullptr; p.amb_pairs = nullptr; p.amb_cap = 0; p.rel_eps = 0.f; p.abs_eps = 0.f;
+  p.col_buf = nullptr; p.col_count = nullptr; p.col_cap = 0; p.col_id_base = 0; p.col_dense = 0;
   p.scores = a->scores;
   p.dim = a->dim;
   p.n_q = a->n;
@@ -549,6 +560,103 @@ int kge_score_all(const kge_score_all_args_t* a) {
   p.n_ct = (a->n_rows + kge::TILE_C - 1) / kge::TILE_C;
   p.n_qt = n_qt;
   KGE_CUDA_TRY(timed_scan(el, hs->s.has_cascade, p, st), "score scan");
+  return KGE_OK;
+}
+
+// ------------------------------------ top-k inference ------------------------------------
+namespace {
+// candidate rows scanned per collect pass: the per-query lists of one pass hold at most this many
+// entries each (8 bytes), bounded to 256 MB in total, a multiple of the scan's candidate tile
+int64_t topk_chunk_rows(int64_t n, int64_t n_rows) {
+  const int64_t budget = (int64_t)256 << 20;
+  int64_t rows = budget / (8 * (n > 0 ? n : 1));
+  rows = rows / kge::TILE_C * kge::TILE_C;
+  if (rows < kge::TILE_C) rows = kge::TILE_C;
+  const int64_t all = (n_rows + kge::TILE_C - 1) / kge::TILE_C * kge::TILE_C;
+  return rows < all ? rows : all;
+}
+struct TopkWorkspace {
+  Workspace w;
+  float* thr;
+  unsigned* col_count;
+  int2* col_buf;
+  unsigned long long* best;
+  int64_t chunk_rows;
+  size_t bytes;
+};
+TopkWorkspace carve_topk(void* base, int qw, int dim, int64_t n, int64_t n_rows, int k) {
+  TopkWorkspace t;
+  t.w = carve(base, qw, dim, n);
+  size_t off = align_up(t.w.bytes, 256);
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const int64_t n_qt = (n + kge::TILE_Q - 1) / kge::TILE_Q;
+  t.chunk_rows = topk_chunk_rows(n, n_rows);
+  t.thr = static_cast<float*>(take((size_t)n_qt * kge::TILE_Q * sizeof(float)));
+  t.col_count = static_cast<unsigned*>(take((size_t)n * sizeof(unsigned)));
+  t.col_buf = static_cast<int2*>(take((size_t)n * t.chunk_rows * sizeof(int2)));
+  t.best = static_cast<unsigned long long*>(take((size_t)n * k * sizeof(unsigned long long)));
+  t.bytes = off;
+  return t;
+}
+}  // namespace
+
+size_t kge_topk_workspace_bytes(int model, int side, int dim, int64_t n, int64_t n_rows, int k) {
+  const int el = kge::elem_kind_for(model, side);
+  if (el < 0 || dim < 1 || n < 0 || n_rows < 0 || k < 1 || k > kge::TOPK_MAX_K) return 0;
+  return carve_topk(nullptr, kge::elem_qw(el), dim, n, n_rows, k).bytes;
+}
+
+int kge_topk_side(const kge_topk_args_t* a) {
+  if (!a) return fail(KGE_ERR_ARG, "kge_topk_side: null args");
+  const int el = kge::elem_kind_for(a->model, a->side);
+  if (el < 0) return fail(KGE_ERR_ARG, "kge_topk_side: unknown model/side");
+  if (a->k < 1 || a->k > kge::TOPK_MAX_K) return fail(KGE_ERR_ARG, "kge_topk_side: k must be in [1, 1024]");
+  if (a->n < 0 || a->n_rows < 0 || a->dim < 1) return fail(KGE_ERR_ARG, "kge_topk_side: bad sizes");
+  if ((int64_t)a->k > a->n_rows) return fail(KGE_ERR_ARG, "kge_topk_side: k exceeds the number of candidates");
+  if (a->n == 0) return KGE_OK;
+  const bool rel_side = a->side == KGE_SIDE_REL;
+  if (!a->packed || (!a->rel0 && !rel_side) || !a->hrows || !a->trows || !a->pred || !a->scores || !a->workspace)
+    return fail(KGE_ERR_ARG, "kge_topk_side: null pointer");
+  if (!rel_side && model_needs_rel1(a->model) && !a->rel1) return fail(KGE_ERR_ARG, "kge_topk_side: rel1 required");
+  if (a->mask_offs && !a->mask_ids) return fail(KGE_ERR_ARG, "kge_topk_side: mask arrays incomplete");
+  const HostSchedule* hs = get_schedule(a->model, a->dim);
+  if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_topk_side: unsupported dim");
+  DeviceScope device_scope(a->packed);
+  const int qw = kge::elem_qw(el), cw = kge::elem_cw(el);
+  TopkWorkspace t = carve_topk(a->workspace, qw, a->dim, a->n, a->n_rows, a->k);
+  if (t.bytes > a->workspace_bytes) return fail(KGE_ERR_ARG, "kge_topk_side: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  int rc = prepare_queries(a->model, a->side, a->dim, a->n, a->hrows, a->trows, a->rel0, a->rel1, a->r_idx, hs,
+                           t.w, el, st);
+  if (rc != KGE_OK) return rc;
+  const int64_t n_qt = (a->n + kge::TILE_Q - 1) / kge::TILE_Q;
+  KGE_CUDA_TRY(kge::launch_fill_f32(t.thr, -__builtin_inff(), n_qt * kge::TILE_Q, st), "topk: thresholds");
+  KGE_CUDA_TRY(cudaMemsetAsync(t.best, 0, (size_t)a->n * a->k * sizeof(unsigned long long), st), "topk: reset lists");
+  for (int64_t c0 = 0; c0 < a->n_rows; c0 += t.chunk_rows) {
+    const int64_t rows = a->n_rows - c0 < t.chunk_rows ? a->n_rows - c0 : t.chunk_rows;
+    const bool first = c0 == 0;   // thresholds are -inf: every candidate is collected, slot = row
+    if (!first) KGE_CUDA_TRY(cudaMemsetAsync(t.col_count, 0, (size_t)a->n * sizeof(unsigned), st), "topk: reset counts");
+    kge::ScanParams p;
+    p.packed = a->packed + (size_t)(c0 / kge::TILE_C) * a->dim * cw * kge::TILE_C;
+    p.qpacked = t.w.qpacked;
+    p.s_true = t.thr;
+    p.code_host = hs->s.code.data();
+    p.counts = nullptr; p.scores = nullptr;
+    p.amb_count = nullptr; p.amb_pairs = nullptr; p.amb_cap = 0; p.rel_eps = 0.f; p.abs_eps = 0.f;
+    p.col_buf = t.col_buf; p.col_count = t.col_count; p.col_cap = (unsigned long long)t.chunk_rows;
+    p.col_id_base = c0; p.col_dense = first ? 1 : 0;
+    p.dim = a->dim; p.n_q = a->n; p.n_rows = rows;
+    p.n_ct = (rows + kge::TILE_C - 1) / kge::TILE_C; p.n_qt = n_qt;
+    KGE_CUDA_TRY(timed_scan(el, hs->s.has_cascade, p, st), "topk: collect scan");
+    KGE_CUDA_TRY(kge::launch_topk_merge(t.best, a->k, t.col_buf, t.col_count, (unsigned long long)t.chunk_rows,
+                                        first ? rows : -1, a->mask_offs, a->mask_ids, t.thr, a->n, st),
+                 "topk: merge");
+  }
+  KGE_CUDA_TRY(kge::launch_topk_finish(t.best, a->k, a->n, a->pred, a->scores, st), "topk: finish");
   return KGE_OK;
 }
 

@@ -36,6 +36,13 @@ struct ScanParams {
   unsigned long long amb_cap;
   float rel_eps;
   float abs_eps;   // flushed subnormal terms: dim * 1.1e-19
+  // top-k collect form (kge_topk_side): s_true holds a per-query THRESHOLD; every candidate whose
+  // exact score is not below it is appended to the query's list as (score bits, global id)
+  int2* col_buf;                  // [n_q][col_cap] or nullptr
+  unsigned* col_count;            // [n_q] fill counts (unused when col_dense)
+  unsigned long long col_cap;
+  long long col_id_base;          // global id of candidate row 0 of this launch
+  int col_dense;                  // 1: slot = row index (first chunk: everything is collected)
   int dim;
   int64_t n_q;
   int64_t n_rows;
@@ -86,5 +93,19 @@ cudaError_t launch_filter(int el, bool cascade, int dim, int64_t n, int64_t n_fi
 
 cudaError_t launch_finalize(const int32_t* raw, const int32_t* sub, int64_t n, int64_t* ranks,
                             int64_t* filt_ranks, cudaStream_t stream);
+
+// ---- top-k selection over collected candidates (topk.cu) ----
+// best[q][k] sorted 64-bit keys (score order, then smaller id first; 0 = empty slot).
+// Merges the `count[q]` (or `dense_count`) entries of col_buf[q] into best[q], masking ids listed in
+// the query's sorted CSR row with -inf (filter_scores with true_idx = None, utils/modeling.py:91-102),
+// and writes the new threshold thr[q] (the k-th best score, -inf while fewer than k are held).
+cudaError_t launch_topk_merge(unsigned long long* best, int k, const int2* col_buf,
+                              const unsigned* col_count, unsigned long long col_cap, long long dense_count,
+                              const int64_t* mask_offs, const int64_t* mask_ids, float* thr, int64_t n_q,
+                              cudaStream_t stream);
+// pred[q][j], scores[q][j] from the keys
+cudaError_t launch_topk_finish(const unsigned long long* best, int k, int64_t n_q, int64_t* pred,
+                               float* scores, cudaStream_t stream);
+constexpr int TOPK_MAX_K = 1024;
 
 }  // namespace kge

@@ -254,7 +254,27 @@ __global__ void __launch_bounds__(Cfg<EL, G>::THREADS, 1)
 
     // ---- epilogue: finish the scores, count or store ----
     const long long c_base = ct * TILE_C + c_off;
-    if (p.scores != nullptr) {
+    if (p.col_buf != nullptr) {
+      // top-k collect: keep what is not below the query's current k-th best (NaN kept: torch.topk
+      // ranks NaN above everything)
+#pragma unroll
+      for (int i = 0; i < TQ; ++i) {
+        const long long q = qt * TILE_Q + q_off + i;
+        if (q >= p.n_q) continue;
+        int2* list = p.col_buf + (size_t)q * p.col_cap;
+#pragma unroll
+        for (int j = 0; j < TC; ++j) {
+          const long long c = c_base + 32 * (j / 4) + (j % 4);
+          if (c >= p.n_rows) continue;
+          const float s = acc_finish<EL>(acc[i][j]);
+          if (!(s < st[i])) {
+            const unsigned long long slot = p.col_dense ? (unsigned long long)c
+                                                        : (unsigned long long)atomicAdd(&p.col_count[q], 1u);
+            if (slot < p.col_cap) list[slot] = make_int2(__float_as_int(s), (int)(p.col_id_base + c));
+          }
+        }
+      }
+    } else if (p.scores != nullptr) {
 #pragma unroll
       for (int i = 0; i < TQ; ++i) {
         const long long q = qt * TILE_Q + q_off + i;

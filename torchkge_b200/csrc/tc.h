@@ -102,10 +102,13 @@ size_t a_image_bytes(long long n_q, int n_kb);
 size_t b_image_bytes(long long n_rows, int n_kb);
 // fold = true (L2 models, k_total = dim + 3): the images carry -|b|^2/2 resp. 1.0 in the three k
 // slots after the data, so the accumulator already holds  a.b - |b|^2/2.
-// meta_b / meta_a: TC_META_BYTES of device memory each (written here, read by the scan)
+// meta_b / meta_a: TC_META_BYTES of device memory each (written here, read by the scan).
+// guard (launch_pack_b, optional): 4 device uint64 kept by the caller NEXT TO a cached image: the
+// table's content checksum is recomputed (one read of the table) and the packing kernels run only
+// if it differs from the checksum the image was built from -- a cache that cannot go stale.
 cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows, int dim, int k_total,
                           int n_kb, bool fold, unsigned char* bpack, float* cbound, float* cnorm2,
-                          TcMeta* meta_b, cudaStream_t st);
+                          TcMeta* meta_b, unsigned long long* guard, cudaStream_t st);
 cudaError_t launch_pack_a(const float* qplain, int qw, long long n_q, int dim, int k_total, int n_kb,
                           int sub_mode, bool fold, unsigned char* apack, float* qbound, float* qnorm2,
                           TcMeta* meta_a, const TcMeta* meta_b, cudaStream_t st);

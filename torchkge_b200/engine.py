@@ -136,6 +136,12 @@ class CudaEngine:
         #: use the tcgen05 bound-and-refine scan for models that have one (ranks unchanged)
         self.tensor_core = bool(tensor_core)
         self.tc_stats = []  # (device tensor [found, capacity]) per tensor-core call, for checks
+        #: tensor-core operand images kept between evaluations, each with a device-side content
+        #: checksum of the table it was built from (kge_tc_pack_table_cached): an unchanged table
+        #: costs one read instead of a rebuild, a changed one is always rebuilt.  KGE_TC_CACHE=0 or
+        #: ``tc_cache_entries = 0`` disables it; ``clear_cache()`` frees the images.
+        self.tc_cache_entries = 0 if os.environ.get("KGE_TC_CACHE", "1") == "0" else 2
+        self._tc_cache = {}
         #: KGE_TRACE=1: rank_link_prediction appends (label, host seconds, CUDA event) marks here
         self.trace = [] if os.environ.get("KGE_TRACE") else None
 
@@ -170,6 +176,9 @@ class CudaEngine:
             self.launches += 1
         return packed
 
+    def clear_cache(self):
+        self._tc_cache.clear()
+
     def pack_tc(self, spec):
         """Tensor-core operand image of the shard, or None when the model has no such path."""
         if not self.tensor_core:
@@ -177,10 +186,29 @@ class CudaEngine:
         nbytes = self.lib.kge_tc_packed_bytes(spec.code, spec.n_rows, spec.dim)
         if nbytes == 0:
             return None
-        out = torch.empty(nbytes, dtype=torch.uint8, device=spec.ent0.device)
-        _lib.check(self.lib.kge_tc_pack_table(spec.code, _ptr(spec.ent0), _ptr(spec.ent1), spec.n_rows,
-                                              spec.dim, _ptr(out), _stream(out.device)), "kge_tc_pack_table")
-        self.launches += 2
+        dev = spec.ent0.device
+        if self.tc_cache_entries <= 0:
+            out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.check(self.lib.kge_tc_pack_table(spec.code, _ptr(spec.ent0), _ptr(spec.ent1), spec.n_rows,
+                                                  spec.dim, _ptr(out), _stream(dev)), "kge_tc_pack_table")
+            self.launches += 4
+            return out
+        key = (spec.code, spec.ent0.data_ptr(), None if spec.ent1 is None else spec.ent1.data_ptr(),
+               spec.n_rows, spec.dim, self.lib.kge_tc_layout_id(), str(dev))
+        hit = self._tc_cache.pop(key, None)
+        if hit is None:
+            while len(self._tc_cache) >= self.tc_cache_entries:
+                self._tc_cache.pop(next(iter(self._tc_cache)))
+            # the table tensors are kept too: their storage cannot be freed and re-used at the same
+            # address by another table while the entry lives
+            hit = (torch.empty(nbytes, dtype=torch.uint8, device=dev),
+                   torch.zeros(4, dtype=torch.int64, device=dev), spec.ent0, spec.ent1)
+        self._tc_cache[key] = hit        # most recently used last
+        out, guard = hit[0], hit[1]
+        _lib.check(self.lib.kge_tc_pack_table_cached(spec.code, _ptr(spec.ent0), _ptr(spec.ent1), spec.n_rows,
+                                                     spec.dim, _ptr(out), _ptr(guard), _stream(dev)),
+                   "kge_tc_pack_table_cached")
+        self.launches += 8 if spec.ent1 is None else 9
         return out
 
     def gather_rows(self, spec, idx):
@@ -262,6 +290,31 @@ class CudaEngine:
         _lib.check(self.lib.kge_score_all(ctypes.byref(a)), "kge_score_all")
         self.launches += 4
         return scores
+
+    def topk_side(self, spec, packed, side, hrows, trows, r_idx, k, mask=None):
+        """(pred int64 (n, k), scores float32 (n, k)) of the k best candidates per query, exact
+        scores, best first; ``mask`` = device CSR (offs, ids ascending per row) of candidates to set to
+        -inf.  No (n, n_rows) matrix is allocated (include/kge_b200.h: kge_topk_side)."""
+        n = hrows.shape[0]
+        dev = hrows.device
+        pred = torch.empty((n, k), dtype=torch.int64, device=dev)
+        scores = torch.empty((n, k), dtype=torch.float32, device=dev)
+        ws_bytes = self.lib.kge_topk_workspace_bytes(spec.code, side, spec.dim, n, spec.n_rows, k)
+        if ws_bytes == 0:
+            raise _lib.KgeLibraryError("kge_topk_workspace_bytes: unsupported arguments (k must be in [1, 1024])")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        a = _lib.TopkArgs()
+        a.model, a.side, a.dim, a.k = spec.code, side, spec.dim, k
+        a.n, a.n_rows = n, spec.n_rows
+        a.packed, a.rel0, a.rel1 = _ptr(packed), _ptr(spec.rel0), _ptr(spec.rel1)
+        a.hrows, a.trows, a.r_idx = _ptr(hrows), _ptr(trows), _ptr(r_idx)
+        if mask is not None:
+            a.mask_offs, a.mask_ids = _ptr(mask[0]), _ptr(mask[1])
+        a.pred, a.scores = _ptr(pred), _ptr(scores)
+        a.workspace, a.workspace_bytes, a.stream = _ptr(ws), ws_bytes, _stream(dev)
+        _lib.check(self.lib.kge_topk_side(ctypes.byref(a)), "kge_topk_side")
+        self.launches += 7   # prep, pack, fill, finish + at least one collect scan / merge pair
+        return pred, scores
 
     def finalize(self, raw_count, filt_sub):
         n = raw_count.shape[0]

@@ -2,12 +2,13 @@
 attributes (torchkge/inference.py:78-250): the top-k candidates that complete (h, r, ?),
 (?, r, t) or (h, ?, t), optionally with the known facts of a dictionary masked out.
 
-Scores come from ``kge_score_all`` (the exact, ATen-order dense scorer of the scan kernels), in
-chunks sized so that a chunk's (rows x candidates) score matrix stays under 1 GiB; known facts
-are masked with -inf exactly as ``filter_scores(..., true_idx=None)`` does (utils/modeling.py:
-76-102) and the k best per row are selected on the device with ``torch.topk`` (sorted,
-descending, as the reference's ``sort(descending=True)[:, :k]``; the ORDER among exactly tied
-scores is unspecified there and here).
+The selection runs inside the scan (``kge_topk_side``, csrc/topk.cu): the dense scan's "collect"
+epilogue writes out only the candidates whose exact, ATen-order score is not below the query's
+current k-th best, one chunk of candidate rows at a time, and a merge kernel keeps a sorted list of
+k (score, id) pairs per query -- no (rows x candidates) score matrix exists.  Known facts are masked
+with -inf exactly as ``filter_scores(..., true_idx=None)`` does (utils/modeling.py:76-102); results
+are sorted descending as the reference's ``sort(descending=True)[:, :k]`` (the ORDER among exactly
+tied scores is unspecified there; here: ascending candidate id).
 
 Deviation, on purpose: the reference stores the scores with ``self.scores[i * b_size, (i + 1) *
 b_size] = ...`` (inference.py:151, 246) -- an index pair instead of a slice, which raises
@@ -19,41 +20,36 @@ from . import _lib
 from .engine import ModelSpec, default_engine, relation_spec
 from .exceptions import WrongArgumentsError
 
-_MAX_SCORE_BYTES = 1 << 30
+_MAX_QUERIES_PER_CALL = 16384
 
 
 def _mask_csr(dictionary, key1, key2):
-    """CSR of dictionary[(key1[i], key2[i])] for every row (whole sets: true_idx is None)."""
+    """CSR of dictionary[(key1[i], key2[i])] for every row (whole sets: true_idx is None), the ids
+    of a row in ascending order (the merge kernel looks them up by bisection)."""
     offs, ids = [0], []
     get = dictionary.get if hasattr(dictionary, "get") else None
     for a, b in zip(key1.tolist(), key2.tolist()):
         s = get((a, b)) if get else dictionary[a, b]
         if s:
-            ids.extend(s)
+            ids.extend(sorted(s))
         offs.append(len(ids))
     return torch.tensor(offs, dtype=torch.int64), torch.tensor(ids, dtype=torch.int64)
 
 
-def _topk_chunks(n, n_cand, top_k, score_chunk, mask_csr, device):
-    """Runs score_chunk(lo, hi) -> (hi - lo, n_cand) fp32 over chunks, masks, selects."""
+def _topk_chunks(n, n_cand, top_k, topk_chunk, mask_csr, device):
+    """Runs topk_chunk(lo, hi, mask) -> (pred, vals) over chunks of queries."""
     if top_k > n_cand:
         raise WrongArgumentsError("top_k = %d exceeds the %d candidates" % (top_k, n_cand))
     pred = torch.empty((n, top_k), dtype=torch.int64, device=device)
     vals = torch.empty((n, top_k), dtype=torch.float32, device=device)
-    rows = max(1, min(n, _MAX_SCORE_BYTES // (4 * max(1, n_cand))))
-    for lo in range(0, n, rows):
-        hi = min(n, lo + rows)
-        scores = score_chunk(lo, hi)
+    for lo in range(0, n, _MAX_QUERIES_PER_CALL):
+        hi = min(n, lo + _MAX_QUERIES_PER_CALL)
+        mask = None
         if mask_csr is not None:
             offs, ids = mask_csr
             a, b = int(offs[lo]), int(offs[hi])
-            if b > a:
-                cnt = (offs[lo + 1:hi + 1] - offs[lo:hi]).to(device)
-                row = torch.repeat_interleave(torch.arange(hi - lo, device=device), cnt)
-                scores[row, ids[a:b].to(device)] = -float("inf")
-        v, i = torch.topk(scores, top_k, dim=1, largest=True, sorted=True)
-        pred[lo:hi], vals[lo:hi] = i, v
-        del scores
+            mask = ((offs[lo:hi + 1] - a).to(device), ids[a:b].to(device))
+        pred[lo:hi], vals[lo:hi] = topk_chunk(lo, hi, mask)
     return pred, vals
 
 
@@ -99,14 +95,14 @@ class EntityInference(object):
         rels = self.known_relations.long().to(dev)
         side = _lib.SIDE_TAIL if self.missing == 'tails' else _lib.SIDE_HEAD
 
-        def score_chunk(lo, hi):
+        def topk_chunk(lo, hi, mask):
             rows = engine.gather_rows(spec, ents[lo:hi])
-            return engine.score_all(spec, packed, side, rows, rows, rels[lo:hi])
+            return engine.topk_side(spec, packed, side, rows, rows, rels[lo:hi].contiguous(), self.top_k, mask)
 
         mask = None
         if self.dictionary is not None:
             mask = _mask_csr(self.dictionary, self.known_entities, self.known_relations)
-        pred, vals = _topk_chunks(ents.shape[0], spec.n_rows, self.top_k, score_chunk, mask, dev)
+        pred, vals = _topk_chunks(ents.shape[0], spec.n_rows, self.top_k, topk_chunk, mask, dev)
         self.predictions, self.scores = pred.cpu(), vals.cpu()
 
 
@@ -138,12 +134,12 @@ class RelationInference(object):
         packed = engine.pack(rspec)
         e1, e2 = self.entities1.long().to(dev), self.entities2.long().to(dev)
 
-        def score_chunk(lo, hi):
+        def topk_chunk(lo, hi, mask):
             hrows, trows = engine.gather_rows(spec, e1[lo:hi]), engine.gather_rows(spec, e2[lo:hi])
-            return engine.score_all(rspec, packed, _lib.SIDE_REL, hrows, trows, None)
+            return engine.topk_side(rspec, packed, _lib.SIDE_REL, hrows, trows, None, self.topk, mask)
 
         mask = None
         if self.dictionary is not None:
             mask = _mask_csr(self.dictionary, self.entities1, self.entities2)
-        pred, vals = _topk_chunks(e1.shape[0], rspec.n_rows, self.topk, score_chunk, mask, dev)
+        pred, vals = _topk_chunks(e1.shape[0], rspec.n_rows, self.topk, topk_chunk, mask, dev)
         self.predictions, self.scores = pred.cpu(), vals.cpu()
