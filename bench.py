@@ -709,8 +709,14 @@ def run_ours(args, rank, local, world):
                                     "peak_telem": mufu_peak / 1e12,
                                     "frac": elems / (scan_ms_per_launch / 1000.0) / mufu_peak}
                 roofline["kernel"] = "scan_kernel<EL_ROT, APPROX> (approximate-sqrt bound-and-refine, fp32 pipes + MUFU)"
+        import hashlib
+        flat = torch.cat([x.view(-1) for x in ranks_dev]).cpu()
+        digest = hashlib.sha256(flat.numpy().tobytes()).hexdigest()[:16]
         rec = {
             "value": value, "unit": "triples/s", "ms_per_step": dev_ms / args.steps,
+            # identical across GPU counts and decompositions iff the rank vectors are (same test set)
+            "ranks_sha256_16": digest,
+            "ranks_first8": [x[:8].tolist() for x in ranks_dev],
             "parallelism": parallelism_text(mode, world),
             "e2e": {"value": e2e_value, "unit": "triples/s",
                     "h2d_bytes_per_step": evaluator.last_stats.get("h2d_bytes"),
@@ -793,6 +799,7 @@ def run_ours(args, rank, local, world):
         "config": workload_config(args.workload, wl, world, primary, n_test),
         "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": clock_rec,
         "roofline": head["roofline"], "parity_full": head["parity_full"], "cpu_baseline": cpu,
+        "ranks_sha256_16": head["ranks_sha256_16"], "ranks_first8": head["ranks_first8"],
         "filter_csr_build_s": csr_build_s, "filter_index_build_s": head["filter_index_build_s"],
         "mean_filter_set": float(csr_t[1].numel() + csr_h[1].numel()) / (2 * n_test),
     }

@@ -286,6 +286,28 @@ typedef struct {
 size_t kge_topk_workspace_bytes(int model, int side, int dim, int64_t n, int64_t n_rows, int k);
 int kge_topk_side(const kge_topk_args_t* args);
 
+/* ---- dense side paths -----------------------------------------------------------------------
+ * RESCAL relation prediction (models/bilinear.py:115-121): the candidates are the relation matrices,
+ * scores[i][c] = ((h_i^T M_c) * t_i).sum() -- batched matmul in the reference's (oneMKL) summation
+ * order, then the ATen cascade sum.  hrows / trows: [n][dim] rows of the heads / tails, rel_mat:
+ * [n_rel][dim*dim], scores: [n][n_rel] out.  The matrix is small (n_rel columns) and is what
+ * kge_rank_dense / kge_topk_dense consume. */
+int kge_rescal_rel_scores(const float* hrows, const float* trows, const float* rel_mat, int dim, int64_t n,
+                          int64_t n_rel, float* scores, void* stream);
+/* get_rank + filter_scores (utils/operations.py:37-61, utils/modeling.py:91-102) on a dense (n, n_cand)
+ * score matrix, counters ADDED INTO as by kge_rank_side: raw_count[i] += #{c : s >= s_true};
+ * filt_sub[i] += listed candidates with s >= s_true (minus the -inf quirk).  s_true = true_score_in[i]
+ * if given (undirected second pass) else scores[i][true_idx[i]]; true_score (optional) receives it. */
+int kge_rank_dense(const float* scores, int64_t n, int64_t n_cand, const int64_t* true_idx,
+                   const float* true_score_in, const int64_t* filt_offs, const int64_t* filt_ids,
+                   int32_t* raw_count, int32_t* filt_sub, float* true_score, void* stream);
+/* the k best columns of every row of a dense matrix, masked candidates set to -inf (same ordering
+ * rules as kge_topk_side) */
+size_t kge_topk_dense_workspace_bytes(int64_t n, int64_t n_cand, int k);
+int kge_topk_dense(const float* scores, int64_t n, int64_t n_cand, int k, const int64_t* mask_offs,
+                   const int64_t* mask_ids, int64_t* pred, float* out_scores, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* ---- training side ----------------------------------------------------------------------
  * Tables as in ModelSpec order: ent0/ent1 entity planes (n_ent, dim), rel0/rel1 relation
  * planes (n_rel, dim) -- RESCAL: rel0 = rel_mat (n_rel, dim*dim); RotatE: (cos, sin) of the

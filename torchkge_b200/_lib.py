@@ -119,6 +119,10 @@ SIGNATURES = {
     "kge_score_all": (_c.c_int, [_c.POINTER(ScoreAllArgs)]),
     "kge_topk_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int64, _c.c_int64, _c.c_int]),
     "kge_topk_side": (_c.c_int, [_c.POINTER(TopkArgs)]),
+    "kge_rescal_rel_scores": (_c.c_int, [_p, _p, _p, _c.c_int, _c.c_int64, _c.c_int64, _p, _p]),
+    "kge_rank_dense": (_c.c_int, [_p, _c.c_int64, _c.c_int64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "kge_topk_dense_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int64, _c.c_int]),
+    "kge_topk_dense": (_c.c_int, [_p, _c.c_int64, _c.c_int64, _c.c_int, _p, _p, _p, _p, _p, _c.c_size_t, _p]),
     "kge_score_triples_fwd": (_c.c_int, [_c.POINTER(Tables), _p, _p, _p, _c.c_int64, _p, _p]),
     "kge_score_triples_bwd": (_c.c_int, [_c.POINTER(Tables), _c.POINTER(Grads), _p, _p, _p,
                                          _c.c_int64, _p, _p]),

@@ -660,6 +660,62 @@ int kge_topk_side(const kge_topk_args_t* a) {
   return KGE_OK;
 }
 
+// ------------------------------------ dense side paths ------------------------------------
+int kge_rescal_rel_scores(const float* hrows, const float* trows, const float* rel_mat, int dim, int64_t n,
+                          int64_t n_rel, float* scores, void* stream) {
+  if (n == 0 || n_rel == 0) return KGE_OK;
+  if (n < 0 || n_rel < 0 || dim < 1 || !hrows || !trows || !rel_mat || !scores)
+    return fail(KGE_ERR_ARG, "kge_rescal_rel_scores: bad argument");
+  if (dim > 2048) return fail(KGE_ERR_UNSUPPORTED, "kge_rescal_rel_scores: dim > 2048");
+  DeviceScope device_scope(scores);
+  KGE_CUDA_TRY(kge::launch_rescal_rel_scores(hrows, trows, rel_mat, dim, n, n_rel, scores,
+                                             static_cast<cudaStream_t>(stream)),
+               "rescal_rel_scores");
+  return KGE_OK;
+}
+
+int kge_rank_dense(const float* scores, int64_t n, int64_t n_cand, const int64_t* true_idx,
+                   const float* true_score_in, const int64_t* filt_offs, const int64_t* filt_ids,
+                   int32_t* raw_count, int32_t* filt_sub, float* true_score, void* stream) {
+  if (n == 0) return KGE_OK;
+  if (n < 0 || n_cand < 1 || !scores || !raw_count || (!true_idx && !true_score_in) || (filt_offs && (!filt_ids || !filt_sub)))
+    return fail(KGE_ERR_ARG, "kge_rank_dense: bad argument");
+  DeviceScope device_scope(scores);
+  KGE_CUDA_TRY(kge::launch_rank_dense(scores, n, n_cand, true_idx, true_score_in, filt_offs, filt_ids, raw_count,
+                                      filt_sub, true_score, static_cast<cudaStream_t>(stream)),
+               "rank_dense");
+  return KGE_OK;
+}
+
+size_t kge_topk_dense_workspace_bytes(int64_t n, int64_t n_cand, int k) {
+  if (n < 0 || n_cand < 1 || k < 1 || k > kge::TOPK_MAX_K) return 0;
+  return align_up((size_t)n * n_cand * sizeof(int2), 256) + align_up((size_t)n * k * sizeof(unsigned long long), 256) +
+         align_up((size_t)n * sizeof(float), 256);
+}
+
+int kge_topk_dense(const float* scores, int64_t n, int64_t n_cand, int k, const int64_t* mask_offs,
+                   const int64_t* mask_ids, int64_t* pred, float* out_scores, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  if (n == 0) return KGE_OK;
+  if (n < 0 || n_cand < 1 || k < 1 || k > kge::TOPK_MAX_K || k > n_cand || !scores || !pred || !out_scores || !workspace)
+    return fail(KGE_ERR_ARG, "kge_topk_dense: bad argument");
+  if (kge_topk_dense_workspace_bytes(n, n_cand, k) > workspace_bytes)
+    return fail(KGE_ERR_ARG, "kge_topk_dense: workspace too small");
+  DeviceScope device_scope(scores);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(workspace);
+  int2* pairs = reinterpret_cast<int2*>(base);
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(base + align_up((size_t)n * n_cand * sizeof(int2), 256));
+  float* thr = reinterpret_cast<float*>(reinterpret_cast<char*>(best) + align_up((size_t)n * k * sizeof(unsigned long long), 256));
+  KGE_CUDA_TRY(cudaMemsetAsync(best, 0, (size_t)n * k * sizeof(unsigned long long), st), "topk_dense: reset");
+  KGE_CUDA_TRY(kge::launch_dense_to_pairs(scores, n, n_cand, pairs, st), "topk_dense: pairs");
+  KGE_CUDA_TRY(kge::launch_topk_merge(best, k, pairs, nullptr, (unsigned long long)n_cand, n_cand, mask_offs, mask_ids,
+                                      thr, n, st),
+               "topk_dense: merge");
+  KGE_CUDA_TRY(kge::launch_topk_finish(best, k, n, pred, out_scores, st), "topk_dense: finish");
+  return KGE_OK;
+}
+
 // ------------------------------------ training side ------------------------------------
 namespace {
 bool tables_ok(const kge_tables_t* tb) {

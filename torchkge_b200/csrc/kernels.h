@@ -108,4 +108,13 @@ cudaError_t launch_topk_finish(const unsigned long long* best, int k, int64_t n_
                                float* scores, cudaStream_t stream);
 constexpr int TOPK_MAX_K = 1024;
 
+// ---- dense side paths (dense.cu) ----
+// scores[i][c] = ((h_i^T M_c) * t_i).sum()   RESCAL relation case, bilinear.py:115-121
+cudaError_t launch_rescal_rel_scores(const float* hrows, const float* trows, const float* rel_mat, int dim,
+                                     int64_t n, int64_t n_rel, float* scores, cudaStream_t stream);
+cudaError_t launch_rank_dense(const float* scores, int64_t n, int64_t n_c, const int64_t* true_idx,
+                              const float* true_score_in, const int64_t* offs, const int64_t* ids,
+                              int32_t* raw_count, int32_t* filt_sub, float* true_score_out, cudaStream_t stream);
+cudaError_t launch_dense_to_pairs(const float* scores, int64_t n, int64_t n_c, int2* pairs, cudaStream_t stream);
+
 }  // namespace kge

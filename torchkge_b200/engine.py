@@ -316,6 +316,39 @@ class CudaEngine:
         self.launches += 7   # prep, pack, fill, finish + at least one collect scan / merge pair
         return pred, scores
 
+    def rescal_rel_scores(self, spec, hrows, trows):
+        """(n, n_rel) scores ((h^T M_c) * t).sum() of every relation matrix c: RESCAL's relation case
+        (bilinear.py:115-121), dense (the candidates are per-fact vectors, nothing to scan)."""
+        n, dev = hrows.shape[0], hrows.device
+        scores = torch.empty((n, spec.n_rel), dtype=torch.float32, device=dev)
+        _lib.check(self.lib.kge_rescal_rel_scores(_ptr(hrows), _ptr(trows), _ptr(spec.rel0), spec.dim, n,
+                                                  spec.n_rel, _ptr(scores), _stream(dev)), "kge_rescal_rel_scores")
+        self.launches += 1
+        return scores
+
+    def rank_dense(self, scores, true_idx, filt, raw_count, filt_sub, true_score=None, true_score_in=None):
+        """get_rank + filter_scores on a dense (n, n_cand) matrix, counters added into."""
+        n, n_c = scores.shape
+        offs, ids = filt if filt is not None else (None, None)
+        _lib.check(self.lib.kge_rank_dense(_ptr(scores), n, n_c, _ptr(true_idx), _ptr(true_score_in), _ptr(offs),
+                                           _ptr(ids), _ptr(raw_count), _ptr(filt_sub), _ptr(true_score),
+                                           _stream(scores.device)), "kge_rank_dense")
+        self.launches += 1
+
+    def topk_dense(self, scores, k, mask=None):
+        """(pred, scores) of the k best columns per row of a dense matrix (kge_topk_dense)."""
+        n, n_c = scores.shape
+        dev = scores.device
+        pred = torch.empty((n, k), dtype=torch.int64, device=dev)
+        vals = torch.empty((n, k), dtype=torch.float32, device=dev)
+        ws_bytes = self.lib.kge_topk_dense_workspace_bytes(n, n_c, k)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        offs, ids = mask if mask is not None else (None, None)
+        _lib.check(self.lib.kge_topk_dense(_ptr(scores), n, n_c, k, _ptr(offs), _ptr(ids), _ptr(pred), _ptr(vals),
+                                           _ptr(ws), ws_bytes, _stream(dev)), "kge_topk_dense")
+        self.launches += 3
+        return pred, vals
+
     def finalize(self, raw_count, filt_sub):
         n = raw_count.shape[0]
         ranks = torch.empty(n, dtype=torch.int64, device=raw_count.device)
@@ -545,8 +578,8 @@ def relation_spec(spec):
         cand0, cand1 = spec.rel0, spec.rel1
     else:
         raise NotImplementedError(
-            "%s has no CUDA relation-prediction path (supported: TransE L1/L2, DistMult, ComplEx)"
-            % _lib.MODEL_NAMES.get(spec.code, spec.code))
+            "%s has no scan-based relation-prediction path (TransE L1/L2, DistMult, ComplEx have; RESCAL "
+            "goes through the dense kge_rescal_rel_scores)" % _lib.MODEL_NAMES.get(spec.code, spec.code))
     return ModelSpec(spec.code, spec.dim, spec.n_rel, spec.n_rel, cand0, cand1, None, None)
 
 
@@ -562,11 +595,27 @@ def rank_relation_prediction(spec, h_idx, t_idx, r_idx, filt, directed=True, eng
     Returns (rank_true_rels, filt_rank_true_rels), int64 device tensors.
     """
     engine = engine or default_engine()
-    rspec = relation_spec(spec)
     n = h_idx.shape[0]
     dev = spec.ent0.device
-    packed = engine.pack(rspec)
     counters = torch.zeros((2, n), dtype=torch.int32, device=dev)
+    if spec.code == _lib.RESCAL:
+        # the candidates are the relation MATRICES: per-fact vectors h^T M_c, a dense (n, n_rel)
+        # score matrix (bilinear.py:115-121) ranked by kge_rank_dense
+        for lo in range(0, n, min(chunk, 4096)):
+            hi = min(n, lo + min(chunk, 4096))
+            h, t, r = h_idx[lo:hi], t_idx[lo:hi], r_idx[lo:hi].contiguous()
+            hrows = engine.gather_rows(spec, h).view(hi - lo, spec.dim)
+            trows = engine.gather_rows(spec, t).view(hi - lo, spec.dim)
+            f = None if filt is None else _csr_slice(filt, lo, hi, n)
+            s_true = torch.empty(hi - lo, dtype=torch.float32, device=dev)
+            scores = engine.rescal_rel_scores(spec, hrows, trows)
+            engine.rank_dense(scores, r, f, counters[0][lo:hi], counters[1][lo:hi], true_score=s_true)
+            if not directed:
+                scores2 = engine.rescal_rel_scores(spec, trows, hrows)
+                engine.rank_dense(scores2, r, f, counters[0][lo:hi], counters[1][lo:hi], true_score_in=s_true)
+        return engine.finalize(counters[0], counters[1])
+    rspec = relation_spec(spec)
+    packed = engine.pack(rspec)
     keep = []
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)

@@ -130,9 +130,22 @@ class RelationInference(object):
                                        "this package has no CPU execution path")
         dev = spec.ent0.device
         engine = default_engine()
+        e1, e2 = self.entities1.long().to(dev), self.entities2.long().to(dev)
+        if spec.code == _lib.RESCAL:
+            # candidates are relation matrices: dense (n, n_rel) scores, then the same selection kernels
+            def topk_chunk(lo, hi, mask):
+                hrows = engine.gather_rows(spec, e1[lo:hi]).view(hi - lo, spec.dim)
+                trows = engine.gather_rows(spec, e2[lo:hi]).view(hi - lo, spec.dim)
+                return engine.topk_dense(engine.rescal_rel_scores(spec, hrows, trows), self.topk, mask)
+
+            mask = None
+            if self.dictionary is not None:
+                mask = _mask_csr(self.dictionary, self.entities1, self.entities2)
+            pred, vals = _topk_chunks(e1.shape[0], spec.n_rel, self.topk, topk_chunk, mask, dev)
+            self.predictions, self.scores = pred.cpu(), vals.cpu()
+            return
         rspec = relation_spec(spec)
         packed = engine.pack(rspec)
-        e1, e2 = self.entities1.long().to(dev), self.entities2.long().to(dev)
 
         def topk_chunk(lo, hi, mask):
             hrows, trows = engine.gather_rows(spec, e1[lo:hi]), engine.gather_rows(spec, e2[lo:hi])

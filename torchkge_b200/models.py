@@ -113,6 +113,8 @@ def _dense_scores(model, h, t, r):
     if (rp[0].dim() == 3 and hp[0].dim() == 2 and tp[0].dim() == 2
             and type(model).__name__ != "RESCALModel"):
         return _dense_relation_scores(model, hp, tp, rp)
+    if type(model).__name__ == "RESCALModel" and rp[0].dim() == 4 and hp[0].dim() == 2 and tp[0].dim() == 2:
+        return _rescal_relation_scores(model, hp[0], tp[0], rp[0])
     if rp[0].dim() != 2 and not (type(model).__name__ == "RESCALModel" and rp[0].dim() == 3):
         raise NotImplementedError("relation-prediction scoring (candidate relations) is not on "
                                   "the CUDA path for this model")
@@ -172,6 +174,22 @@ def _dense_relation_scores(model, hp, tp, rp):
     with _device_guard(hrows.device):
         packed = eng.pack(rspec)       # rebuilt per call, see _dense_scores
         return eng.score_all(rspec, packed, _lib.SIDE_REL, hrows, trows, None)
+
+
+def _rescal_relation_scores(model, h, t, cands):
+    """RESCAL's relation case of ``inference_scoring_function`` (bilinear.py:115-121): ``cands`` is
+    the (b, n_rel, d, d) expansion of ``rel_mat`` returned by ``inference_prepare_candidates(...,
+    entities=False)``; scores ((h^T M_c) * t).sum() for every relation c (kge_rescal_rel_scores)."""
+    if cands.shape[0] > 1 and cands.stride(0) != 0:
+        raise NotImplementedError("per-row candidate tensors are not supported: pass the tensor returned by "
+                                  "inference_prepare_candidates")
+    if not h.is_cuda:
+        raise _lib.KgeLibraryError("inference_scoring_function needs CUDA tensors; there is no CPU fallback")
+    b, n_rel, d, _ = cands.shape
+    mats = cands[0].detach().contiguous().view(n_rel, d * d)
+    spec = ModelSpec(_lib.RESCAL, d, model.n_ent, n_rel, h.detach(), None, mats, None)
+    with _device_guard(h.device):
+        return default_engine().rescal_rel_scores(spec, h.detach().contiguous(), t.detach().contiguous())
 
 
 def l1_torus_dissimilarity(a, b):
