@@ -777,7 +777,7 @@ struct Config {
   Config()
       : bk(env_int("KGE_TC_BK", 32) == 64 ? 64 : 32), resident(env_int("KGE_TC_RESIDENT", 1) != 0),
         group(env_int("KGE_TC_GROUP", 0)), max_ctas(env_int("KGE_TC_MAX_CTAS", 0)),
-        fp16(env_int("KGE_TC_FP16", 0) != 0) {}
+        fp16(env_int("KGE_TC_FP16", 1) != 0) {}
 };
 Config& config() {
   static Config c;

@@ -18,7 +18,8 @@ int n_kblocks(int k_total);
 void configure(int bk, int resident, int ct_group, int max_ctas, int fp16);
 // Operand format of the split x = hi + lo: bf16 (8 significant bits each, residual 2^-16 |x|) or
 // fp16 (11 bits each, residual 2^-22 |x|, operands pre-scaled by a power of two per table so that
-// the lo parts stay in fp16's normal range).  KGE_TC_FP16=0|1.
+// the lo parts stay in fp16's normal range; the default: on c2 / c3 the near-tie band is 2.3x / 1.3x
+// narrower than with bf16 -- profiles/r02_fp16_vs_bf16.md).  KGE_TC_FP16=0|1.
 bool fp16();
 
 // Per-operand facts the pack kernels establish ON THE DEVICE (no host round trip) and the scan

@@ -15,7 +15,10 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
 #include "../../include/kge_b200.h"
+#include "ptx.cuh"
 #include "train.h"
 
 namespace kge {
@@ -598,6 +601,255 @@ margin_step_fast_kernel(MarginStepParams a, TrainGrads gr, const float* __restri
   vec_atomic_add(gr.rel0 + (size_t)ri * dim, dim, lane, Gr);
 }
 
+// ------------------------------------------------------------------------------------------
+// Ring variant of the fast fused step: the corrupted entities' rows travel through a per-warp
+// shared-memory ring filled by 1-D bulk async copies (cp.async.bulk, completion on an mbarrier per
+// slot) instead of through registers.  The register form keeps PF = 4 (2 backward) rows in flight
+// per warp and stalls on them before every reduction -- measured 0.53 of the HBM copy bandwidth
+// with 16 resident warps per SM (ncu: warps active 24 %).  Here a warp keeps RING rows in flight
+// at all times (8 x 800 B = 6.4 KB), independently of its register budget, the Philox draws of all
+// negatives are made up front into shared memory, and row j + RING is requested the moment row j
+// has been consumed.  Arithmetic per negative is exactly that of margin_step_fast_kernel.
+// Shared memory per warp: RING * row_bytes + 4 * n_neg (codes) + RING barriers.
+// ------------------------------------------------------------------------------------------
+constexpr int RING = 8;
+constexpr unsigned CODE_BOTH = 0xFFFFFFFFu;   // caller-supplied negative with both ends replaced
+
+__device__ __forceinline__ Vec vec_load_smem(const float* row, int dim, int lane) {
+  Vec v;
+#pragma unroll
+  for (int i = 0; i < FAST_NCH; ++i) {
+    const int k = 4 * (lane + 32 * i);
+    v.c[i] = k < dim ? *reinterpret_cast<const float4*>(row + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  return v;
+}
+
+template <int MODEL, bool BWD>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+margin_step_ring_kernel(MarginStepParams a, TrainGrads gr, const float* __restrict__ gloss) {
+  extern __shared__ __align__(128) unsigned char ring_smem[];
+  const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * WARPS_PER_BLOCK + warp_in_block;
+  const int dim = a.dim;
+  const unsigned row_bytes = (unsigned)dim * 4u;                 // dim % 4 == 0: a multiple of 16
+  const int n_codes = (a.n_neg + 3) & ~3;
+  const size_t per_warp = (size_t)RING * row_bytes + (size_t)n_codes * 4 + RING * sizeof(uint64_t);
+  unsigned char* base = ring_smem + (size_t)warp_in_block * ((per_warp + 127) & ~(size_t)127);
+  float* ring = reinterpret_cast<float*>(base);
+  unsigned* codes = reinterpret_cast<unsigned*>(base + (size_t)RING * row_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)RING * row_bytes + (size_t)n_codes * 4);
+  if (w >= a.b) return;          // whole warps only: no block-wide barrier below
+  if (lane == 0) {
+#pragma unroll
+    for (int s_ = 0; s_ < RING; ++s_) ptx::mbar_init(&bars[s_], 1);
+    ptx::fence_mbar_init();
+  }
+  const float* __restrict__ ent = a.tb.ent0;
+  const long long hi = a.h[w], ti = a.t[w], ri = a.r[w];
+  const float p_head = a.nh ? 0.f : a.probs[ri];
+  // ---- all corruptions of this positive, up front: code = entity | head flag ----
+  for (int j0 = 0; j0 < a.n_neg; j0 += 32) {
+    const int j = j0 + lane;
+    if (j < a.n_neg) {
+      const long long idx = (long long)j * a.b + w;
+      long long nh = hi, nt = ti;
+      if (a.nh) { nh = a.nh[idx]; nt = a.nt[idx]; }
+      else corrupt_one(a.seed, a.offset, (uint64_t)idx, p_head, a.n_ent, hi, ti, &nh, &nt);
+      if (!BWD && a.nh_out) { a.nh_out[idx] = nh; a.nt_out[idx] = nt; }
+      const bool head = nh != hi;
+      codes[j] = (nh != hi && nt != ti) ? CODE_BOTH : ((unsigned)(head ? nh : nt) | (head ? 0x80000000u : 0u));
+    }
+  }
+  __syncwarp();
+  auto request = [&](int j) {      // lane 0: start the copy of negative j's row into its slot
+    const unsigned code = codes[j];
+    if (code == CODE_BOTH) return;
+    const int slot = j % RING;
+    ptx::mbar_arrive_expect_tx(&bars[slot], row_bytes);
+    ptx::bulk_g2s(ring + (size_t)slot * dim, ent + (size_t)(code & 0x7FFFFFFFu) * dim, row_bytes, &bars[slot]);
+  };
+  if (lane == 0) {
+    const int first = a.n_neg < RING ? a.n_neg : RING;
+    for (int j = 0; j < first; ++j) request(j);
+  }
+  // ---- the positive (its three rows come straight from global memory, once) ----
+  const Vec h = vec_load(ent + (size_t)hi * dim, dim, lane);
+  const Vec t = vec_load(ent + (size_t)ti * dim, dim, lane);
+  const Vec r = vec_load(a.tb.rel0 + (size_t)ri * dim, dim, lane);
+  float sh = vec_dot(h, h), stt = vec_dot(t, t);
+  warp_sum2(sh, stt);
+  const float inv_h = 1.0f / fmaxf(sqrtf(sh), NORM_EPS), inv_t = 1.0f / fmaxf(sqrtf(stt), NORM_EPS);
+  const Vec hn = vec_scale(h, inv_h), tn = vec_scale(t, inv_t);
+  Vec A, Bv;
+  if constexpr (MODEL == KGE_DISTMULT) {
+    A = vec_map(hn, r, [](float x, float y) { return x * y; });
+    Bv = vec_map(r, tn, [](float x, float y) { return x * y; });
+  } else {
+    A = vec_map(hn, r, [](float x, float y) { return x + y; });
+    Bv = vec_map(tn, r, [](float x, float y) { return x - y; });
+  }
+  float sA = 0.f, sB = 0.f, pos;
+  if constexpr (MODEL == KGE_DISTMULT) {
+    pos = warp_sum(vec_dot(A, tn));
+  } else if constexpr (MODEL == KGE_TRANSE_L2) {
+    sA = vec_dot(A, A); sB = vec_dot(Bv, Bv);
+    warp_sum2(sA, sB);
+    const Vec x = vec_map(A, tn, [](float p, float q) { return p - q; });
+    pos = -warp_sum(vec_dot(x, x));
+  } else {
+    pos = -warp_sum(vec_l1_diff(A, tn));
+  }
+  if (lane == 0 && a.pos_out && !BWD) a.pos_out[w] = pos;
+  const float g = BWD ? *gloss : 0.f;
+  float loss = 0.f;
+  Vec Vt, Vh;
+#pragma unroll
+  for (int i = 0; i < FAST_NCH; ++i) Vt.c[i] = Vh.c[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int n_t = 0, n_h = 0;
+  unsigned phases = 0u;   // bit s = parity of the next completion of slot s (a skipped use does not advance it)
+  for (int j = 0; j < a.n_neg; ++j) {
+    const unsigned code = codes[j];
+    const long long idx = (long long)j * a.b + w;
+    if (code == CODE_BOTH) {
+      // both ends replaced (possible with caller-supplied negatives only): generic path, no ring slot
+      const long long nh = a.nh[idx], nt = a.nt[idx];
+      const RowPtrs pn = make_rows(MODEL, dim, a.tb, nh, nt, ri);
+      const float neg = triple_score(MODEL, dim, pn, lane, nullptr, nullptr);
+      const float v = a.margin - pos + neg;
+      if (lane == 0) {
+        if (!BWD && a.neg_out) a.neg_out[idx] = neg;
+        loss += fmaxf(0.f, v);
+      }
+      if (BWD && v > 0.f) {
+        triple_backward(MODEL, dim, pn, gr, nh, nt, ri, g, lane);
+        const RowPtrs pp = make_rows(MODEL, dim, a.tb, hi, ti, ri);
+        triple_backward(MODEL, dim, pp, gr, hi, ti, ri, -g, lane);
+      }
+      if (lane == 0 && j + RING < a.n_neg) request(j + RING);
+      continue;
+    }
+    const int slot = j % RING;
+    ptx::mbar_wait(&bars[slot], (phases >> slot) & 1u);
+    phases ^= 1u << slot;
+    const Vec ev = vec_load_smem(ring + (size_t)slot * dim, dim, lane);
+    __syncwarp();                        // every lane has its copy: the slot may be refilled
+    if (lane == 0 && j + RING < a.n_neg) {
+      ptx::fence_proxy_async();          // generic-proxy reads above, async-proxy write below
+      request(j + RING);
+    }
+    const bool head = (code & 0x80000000u) != 0u;   // warp-uniform
+    const long long e = (long long)(code & 0x7FFFFFFFu);
+    const Vec& P = head ? Bv : A;
+    float se = vec_dot(ev, ev), sp = vec_dot(ev, P);
+    warp_sum2(se, sp);
+    const float inv_e = 1.0f / fmaxf(sqrtf(se), NORM_EPS);
+    float neg, en_dot_G = 0.f;
+    Vec en;
+    if constexpr (MODEL == KGE_DISTMULT) {
+      neg = sp * inv_e;
+      en_dot_G = neg;
+    } else if constexpr (MODEL == KGE_TRANSE_L2) {
+      const float sP = head ? sB : sA;
+      const float ee = inv_e * inv_e * se, pe = inv_e * sp;
+      neg = -(sP - 2.f * pe + ee);
+      en_dot_G = 2.f * (pe - ee);
+    } else {
+      en = vec_scale(ev, inv_e);
+      float l1 = vec_l1_diff(P, en), eg = 0.f;
+      if (BWD) {
+        const Vec sg = vec_map(P, en, [](float p, float q) { return sgn(p - q); });
+        eg = vec_dot(en, sg);
+      }
+      warp_sum2(l1, eg);
+      neg = -l1;
+      en_dot_G = eg;
+    }
+    const float v = a.margin - pos + neg;
+    if (lane == 0) {
+      if (!BWD && a.neg_out) a.neg_out[idx] = neg;
+      loss += fmaxf(0.f, v);
+    }
+    if (BWD && v > 0.f) {
+      if constexpr (MODEL != KGE_TRANSE_L1) en = vec_scale(ev, inv_e);
+      Vec ge, V;
+      const float c = g * inv_e;
+      if constexpr (MODEL == KGE_DISTMULT) {
+        ge = vec_map(P, en, [=](float p, float q) { return c * (p - q * en_dot_G); });
+        V = en;
+      } else if constexpr (MODEL == KGE_TRANSE_L2) {
+        ge = vec_map(P, en, [=](float p, float q) { return c * (2.f * (p - q) - q * en_dot_G); });
+        V = en;
+      } else {
+        V = vec_map(P, en, [](float p, float q) { return sgn(p - q); });
+        ge = vec_map(V, en, [=](float s_, float q) { return c * (s_ - q * en_dot_G); });
+      }
+      vec_atomic_add(gr.ent0 + (size_t)e * dim, dim, lane, ge);
+      if (head) { Vh = vec_map(Vh, V, [](float x, float y) { return x + y; }); ++n_h; }
+      else { Vt = vec_map(Vt, V, [](float x, float y) { return x + y; }); ++n_t; }
+    }
+  }
+  if (!BWD) {
+    if (lane == 0) atomicAdd(a.loss, loss);
+    return;
+  }
+  if (n_t + n_h == 0) return;
+  const float fn_t = (float)n_t, fn_h = (float)n_h, fn = (float)(n_t + n_h);
+  Vec Gh, Gt, Gr;
+  if constexpr (MODEL == KGE_DISTMULT) {
+    Gh = vec_map3(r, Vt, tn, [=](float rr, float vt, float tt) { return g * rr * (vt - fn * tt); });
+    Gt = vec_map3(r, Vh, hn, [=](float rr, float vh, float hh) { return g * rr * (vh - fn * hh); });
+    const Vec tmp = vec_map3(hn, Vt, tn, [=](float hh, float vt, float tt) { return hh * (vt - fn * tt); });
+    Gr = vec_map3(tmp, tn, Vh, [=](float x, float tt, float vh) { return g * (x + tt * vh); });
+  } else if constexpr (MODEL == KGE_TRANSE_L2) {
+    const Vec x = vec_map(A, tn, [](float p, float q) { return p - q; });
+    const Vec dt = vec_map3(A, Vt, x, [=](float aa, float vt, float xx) { return fn_t * aa - vt - fn * xx; });
+    const Vec dh = vec_map(Vh, Bv, [=](float vh, float bb) { return vh - fn_h * bb; });
+    Gh = vec_scale(dt, -2.f * g);
+    Gt = vec_map3(dh, x, x, [=](float d, float xx, float) { return 2.f * g * (d - fn * xx); });
+    Gr = vec_map(dt, dh, [=](float p, float q) { return -2.f * g * (p + q); });
+  } else {
+    const Vec sx = vec_map(A, tn, [](float p, float q) { return sgn(p - q); });
+    Gh = vec_map(Vt, sx, [=](float vt, float s_) { return g * (fn * s_ - vt); });
+    Gt = vec_map(Vh, sx, [=](float vh, float s_) { return g * (-vh - fn * s_); });
+    Gr = vec_map3(Vt, Vh, sx, [=](float vt, float vh, float s_) { return g * (vh - vt + fn * s_); });
+  }
+  float ph = vec_dot(hn, Gh), pt = vec_dot(tn, Gt);
+  warp_sum2(ph, pt);
+  const Vec gh = vec_map(Gh, hn, [=](float gg, float q) { return (gg - q * ph) * inv_h; });
+  const Vec gt = vec_map(Gt, tn, [=](float gg, float q) { return (gg - q * pt) * inv_t; });
+  vec_atomic_add(gr.ent0 + (size_t)hi * dim, dim, lane, gh);
+  vec_atomic_add(gr.ent0 + (size_t)ti * dim, dim, lane, gt);
+  vec_atomic_add(gr.rel0 + (size_t)ri * dim, dim, lane, Gr);
+}
+
+__host__ inline size_t ring_smem_bytes(const MarginStepParams& a) {
+  const size_t per_warp = (size_t)RING * a.dim * 4 + (size_t)((a.n_neg + 3) & ~3) * 4 + RING * sizeof(uint64_t);
+  return WARPS_PER_BLOCK * ((per_warp + 127) & ~(size_t)127);
+}
+// KGE_TRAIN_RING=0 selects the register-resident form (margin_step_fast_kernel)
+__host__ inline bool ring_step_ok(const MarginStepParams& a) {
+  static const bool enabled = [] { const char* v = getenv("KGE_TRAIN_RING"); return !(v && v[0] == '0'); }();
+  return enabled && a.n_neg <= 8192 && a.n_ent < 0x7FFFFFFFll && ring_smem_bytes(a) <= 96 * 1024;
+}
+
+template <int MODEL, bool BWD>
+cudaError_t launch_ring(const MarginStepParams& a, const TrainGrads& gr, const float* gloss, cudaStream_t st) {
+  const size_t smem = ring_smem_bytes(a);
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (smem > 48 * 1024 && (dev < 0 || dev >= 64 || !configured[dev])) {
+    e = cudaFuncSetAttribute(margin_step_ring_kernel<MODEL, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  const unsigned blocks = (unsigned)((a.b + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  margin_step_ring_kernel<MODEL, BWD><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(a, gr, gloss);
+  return cudaGetLastError();
+}
+
 __host__ inline bool fast_step_ok(const MarginStepParams& a) {
   return (a.model == KGE_TRANSE_L1 || a.model == KGE_TRANSE_L2 || a.model == KGE_DISTMULT) &&
          a.dim % 4 == 0 && a.dim <= FAST_MAX_DIM;
@@ -698,6 +950,14 @@ cudaError_t launch_corrupt_batch(const int64_t* h, const int64_t* t, const int64
 
 cudaError_t launch_margin_step_fwd(const MarginStepParams& a, cudaStream_t st) {
   if (a.b <= 0) return cudaSuccess;
+  if (fast_step_ok(a) && ring_step_ok(a)) {
+    const TrainGrads none{nullptr, nullptr, nullptr, nullptr};
+    switch (a.model) {
+      case KGE_TRANSE_L1: return launch_ring<KGE_TRANSE_L1, false>(a, none, nullptr, st);
+      case KGE_TRANSE_L2: return launch_ring<KGE_TRANSE_L2, false>(a, none, nullptr, st);
+      default: return launch_ring<KGE_DISTMULT, false>(a, none, nullptr, st);
+    }
+  }
   if (fast_step_ok(a)) {
     const TrainGrads none{nullptr, nullptr, nullptr, nullptr};
     const unsigned blocks = blocks_for_warps(a.b);
@@ -715,6 +975,13 @@ cudaError_t launch_margin_step_fwd(const MarginStepParams& a, cudaStream_t st) {
 cudaError_t launch_margin_step_bwd(const MarginStepParams& a, const TrainGrads& gr, const float* gloss,
                                    cudaStream_t st) {
   if (a.b <= 0) return cudaSuccess;
+  if (fast_step_ok(a) && ring_step_ok(a)) {
+    switch (a.model) {
+      case KGE_TRANSE_L1: return launch_ring<KGE_TRANSE_L1, true>(a, gr, gloss, st);
+      case KGE_TRANSE_L2: return launch_ring<KGE_TRANSE_L2, true>(a, gr, gloss, st);
+      default: return launch_ring<KGE_DISTMULT, true>(a, gr, gloss, st);
+    }
+  }
   if (fast_step_ok(a)) {
     const unsigned blocks = blocks_for_warps(a.b);
     switch (a.model) {

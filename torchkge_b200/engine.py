@@ -308,7 +308,7 @@ class CudaEngine:
         a.n, a.n_rows = n, spec.n_rows
         a.packed, a.rel0, a.rel1 = _ptr(packed), _ptr(spec.rel0), _ptr(spec.rel1)
         a.hrows, a.trows, a.r_idx = _ptr(hrows), _ptr(trows), _ptr(r_idx)
-        if mask is not None:
+        if mask is not None and mask[1].numel() > 0:
             a.mask_offs, a.mask_ids = _ptr(mask[0]), _ptr(mask[1])
         a.pred, a.scores = _ptr(pred), _ptr(scores)
         a.workspace, a.workspace_bytes, a.stream = _ptr(ws), ws_bytes, _stream(dev)
@@ -329,6 +329,8 @@ class CudaEngine:
     def rank_dense(self, scores, true_idx, filt, raw_count, filt_sub, true_score=None, true_score_in=None):
         """get_rank + filter_scores on a dense (n, n_cand) matrix, counters added into."""
         n, n_c = scores.shape
+        if filt is not None and filt[1].numel() == 0:
+            filt = None      # nothing to discount (an empty tensor has no device pointer)
         offs, ids = filt if filt is not None else (None, None)
         _lib.check(self.lib.kge_rank_dense(_ptr(scores), n, n_c, _ptr(true_idx), _ptr(true_score_in), _ptr(offs),
                                            _ptr(ids), _ptr(raw_count), _ptr(filt_sub), _ptr(true_score),
@@ -343,6 +345,8 @@ class CudaEngine:
         vals = torch.empty((n, k), dtype=torch.float32, device=dev)
         ws_bytes = self.lib.kge_topk_dense_workspace_bytes(n, n_c, k)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        if mask is not None and mask[1].numel() == 0:
+            mask = None
         offs, ids = mask if mask is not None else (None, None)
         _lib.check(self.lib.kge_topk_dense(_ptr(scores), n, n_c, k, _ptr(offs), _ptr(ids), _ptr(pred), _ptr(vals),
                                            _ptr(ws), ws_bytes, _stream(dev)), "kge_topk_dense")
