@@ -138,12 +138,13 @@ int kge_tc_layout_id(void);
 int kge_tc_pack_table_cached(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
                              void* tc_packed, uint64_t* guard, void* stream);
 /* (host only) The constants of the rigorous error bound the tensor-core scan uses for `model` at
- * `dim` under the current operand format (csrc/tc.h: tc_gamma, tc_gamma2):
- *   dot models : |s_tc - s_ref| <= gamma |a| |b|
- *   TransE-L2  : |s_tc - s_ref| <= 2 gamma |a| |b| + gamma2 (|a| + |b|)^2
- * (|a|, |b| the per-row norm bounds, inflated by TcMeta::kappa under fp16).  Exposed so that the
- * tests check the measured error against exactly what the kernel assumes. */
-int kge_tc_bound_constants(int model, int dim, float* gamma, float* gamma2, int* fp16);
+ * `dim` under the current operand format (csrc/tc.h: tc_gamma, tc_gamma2, tc_gamma_p):
+ *   dot models : |s_tc - s_ref| <= gamma |a| |b| + gamma_p P(a) P(b)
+ *   TransE-L2  : |s_tc - s_ref| <= 2 gamma |a| |b| + 2 gamma_p P(a) P(b) + gamma2 (|a| + |b|)^2
+ * |a|, |b|: per-row norm bounds (inflated by TcMeta::kappa under fp16); P(x) = sqrt(sum_i |x_{<=16 i}|^2),
+ * the running-magnitude factor of the accumulation inside the tensor core.  Exposed so that the tests
+ * check the measured error against exactly what the kernel assumes. */
+int kge_tc_bound_constants(int model, int dim, float* gamma, float* gamma2, float* gamma_p, int* fp16);
 int kge_tc_pack_table(int model, const float* ent0, const float* ent1, int64_t n_rows, int dim,
                       void* tc_packed, void* stream);
 

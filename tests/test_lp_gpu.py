@@ -243,3 +243,22 @@ def test_non_finite_embeddings_rank_like_the_reference(n_test, cuda_device):
     P = helpers.oracle_params("distmult", model)
     ref = oracle.link_prediction("distmult", P, kg.head_idx, kg.tail_idx, kg.relations, dh, dt, 64)
     _assert_ranks_equal(_ranks_gpu(model, kg), ref, "distmult")
+
+
+def test_model_on_a_non_current_device(cuda_device):
+    """A model on cuda:1 while cuda:0 is the current device: every launching entry point of the
+    library switches to the device that owns its buffers (csrc/api.cu: DeviceScope), and kernel
+    attributes are set per device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    other = torch.device("cuda", 1)
+    assert torch.cuda.current_device() == 0
+    n_ent, n_rel, d = 600, 5, 40
+    kg, dh, dt = helpers.make_kg(n_ent, n_rel, n_facts=3000, n_test=150, seed=4)
+    for kind in ("transe_l2", "transe_l1", "complex"):
+        model = helpers.make_model(kind, d, n_ent, n_rel, seed=4).to(other)
+        P = helpers.oracle_params(kind, model)
+        ref = oracle.link_prediction(kind, P, kg.head_idx, kg.tail_idx, kg.relations, dh, dt, b_size=64)
+        ev = _ranks_gpu(model, kg)
+        _assert_ranks_equal(ev, ref, kind)
+        assert torch.cuda.current_device() == 0

@@ -34,16 +34,28 @@ def _approx_scores(eng, spec, side, h, t, r):
 @pytest.fixture(params=[0, 1], ids=["bf16", "fp16"])
 def operand_format(request):
     """Both operand formats of the split (csrc/tc.h): restored to the environment's default afterwards."""
-    default = _lib.tc_bound_constants(_lib.DISTMULT, 16)[2]
+    default = _lib.tc_bound_constants(_lib.DISTMULT, 16)[3]
     _lib.tc_configure(fp16=request.param)
     yield request.param
     _lib.tc_configure(fp16=int(default))
 
 
-def _kernel_bound(code, d, k_total, na, nb, max_a, max_b, max_norm2_b, l2):
+def _prefix_factor(x, k_total=None):
+    """P(x) = sqrt(sum_i |x_{<= 16 i}|^2) per row over the ceil(k_total / 16) MMA k-steps
+    (csrc/tc.h: tc_gamma_p), x (n, k) float64; k_total > k: trailing k-steps see the whole |x|^2."""
+    k = x.shape[1]
+    pad = (-k) % 16
+    sq = torch.nn.functional.pad(x * x, (0, pad)).view(x.shape[0], -1, 16).sum(2)
+    pre = torch.cumsum(sq, 1)
+    extra = 0 if k_total is None else (k_total + 15) // 16 - (k + 15) // 16
+    return (pre.sum(1) + extra * pre[:, -1]).sqrt()
+
+
+def _kernel_bound(code, d, k_total, na, nb, max_a, max_b, max_norm2_b, l2, pa, pb):
     """The bound E(q, c) the scan's threshold test uses (csrc/tc.cu epilogue, csrc/tc.h), from the
-    library's own constants: na (nq, 1), nb (1, nc) row norms."""
-    gamma, gamma2, fp16 = _lib.tc_bound_constants(code, d)
+    library's own constants: na (nq, 1), nb (1, nc) row norms; pa (nq, 1), pb (1, nc) the
+    running-magnitude factors of the operands."""
+    gamma, gamma2, gamma_p, fp16 = _lib.tc_bound_constants(code, d)
     e_abs = 0.0
     if fp16:
         na = na + max_a * 2.0 ** -11 * (k_total ** 0.5) * 1.01 / 3.0
@@ -53,8 +65,8 @@ def _kernel_bound(code, d, k_total, na, nb, max_a, max_b, max_norm2_b, l2):
             phi = 2.0 ** (14 - math.frexp(0.5 * max_norm2_b)[1])
             e_abs = 2.0 ** -22 / phi
     if l2:
-        return 2 * gamma * na * nb + gamma2 * (na + nb) ** 2 + e_abs
-    return gamma * na * nb
+        return 2 * gamma * na * nb + 2 * gamma_p * pa * pb + gamma2 * (na + nb) ** 2 + e_abs
+    return gamma * na * nb + gamma_p * pa * pb
 
 
 @pytest.mark.parametrize("kind", TC_KINDS)
@@ -100,10 +112,13 @@ def test_approximate_scores_within_half_the_bound(kind, d, cuda_device, operand_
             cand = P["ent"].double()
             q = ((P["ent"][h] + P["rel"][r]) if side == 0 else (P["ent"][t] - P["rel"][r])).double()
         na, nb = q.norm(dim=1).view(-1, 1), cand.norm(dim=1).view(1, -1)
+        pa, pb = _prefix_factor(q, k_total).view(-1, 1), _prefix_factor(cand, k_total).view(1, -1)
         if l2 and side == 1:   # head side: the kernel bounds |t - r| by |t| + |r| (see tc.cu)
-            na = (P["ent"][t].double().norm(dim=1) + P["rel"][r].double().norm(dim=1)).view(-1, 1)
+            nt = (P["ent"][t].double().norm(dim=1) + P["rel"][r].double().norm(dim=1)).view(-1, 1)
+            pa = pa * nt / na.clamp_min(1e-300)
+            na = nt
         bound = _kernel_bound(spec.code, d, k_total, na, nb, q.abs().max().item(), cand.abs().max().item(),
-                              (cand ** 2).sum(1).max().item(), l2)
+                              (cand ** 2).sum(1).max().item(), l2, pa, pb)
         ratio = ((got.double() - want).abs() / bound).max().item()
         assert ratio < 0.5, "%s %s d=%d: error / bound = %.3f" % (kind, name, d, ratio)
 
@@ -176,7 +191,8 @@ def test_error_bound_holds_on_adversarial_operands(shape, kind, d, cuda_device, 
     assert torch.isfinite(got).all()
     na, nb = qv.norm(dim=1).view(-1, 1), cv.norm(dim=1).view(1, -1)
     bound = _kernel_bound(code, d, k_total, na, nb, qv.abs().max().item(), cv.abs().max().item(),
-                          (cv ** 2).sum(1).max().item(), l2)
+                          (cv ** 2).sum(1).max().item(), l2, _prefix_factor(qv, k_total).view(-1, 1),
+                          _prefix_factor(cv, k_total).view(1, -1))
     ratio = ((got - want).abs() / bound).max().item()
     assert ratio <= 1.0, "%s %s d=%d: error / bound = %.3f" % (kind, shape, d, ratio)
     print("tc bound %s %s d=%d fp16=%d: max error / bound = %.3f" % (kind, shape, d, operand_format, ratio))

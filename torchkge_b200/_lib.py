@@ -109,7 +109,7 @@ SIGNATURES = {
     "kge_tc_packed_bytes": (_c.c_size_t, [_c.c_int, _c.c_int64, _c.c_int]),
     "kge_tc_configure": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     "kge_tc_bound_constants": (_c.c_int, [_c.c_int, _c.c_int, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float),
-                                          _c.POINTER(_c.c_int)]),
+                                          _c.POINTER(_c.c_float), _c.POINTER(_c.c_int)]),
     "kge_tc_layout_id": (_c.c_int, []),
     "kge_tc_pack_table": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _c.c_int, _p, _p]),
     "kge_tc_pack_table_cached": (_c.c_int, [_c.c_int, _p, _p, _c.c_int64, _c.c_int, _p, _p, _p]),
@@ -194,11 +194,11 @@ def tc_configure(bk=-1, resident=-1, ct_group=-1, max_ctas=-1, fp16=-1):
 
 
 def tc_bound_constants(model, dim):
-    """(gamma, gamma2, fp16) of the tensor-core scan's error bound for (model, dim) -- host only."""
-    g, g2, f = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int(0)
-    check(load().kge_tc_bound_constants(model, dim, ctypes.byref(g), ctypes.byref(g2), ctypes.byref(f)),
-          "kge_tc_bound_constants")
-    return g.value, g2.value, bool(f.value)
+    """(gamma, gamma2, gamma_p, fp16) of the tensor-core scan's error bound for (model, dim) -- host only."""
+    g, g2, gp, f = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(0), ctypes.c_int(0)
+    check(load().kge_tc_bound_constants(model, dim, ctypes.byref(g), ctypes.byref(g2), ctypes.byref(gp),
+                                        ctypes.byref(f)), "kge_tc_bound_constants")
+    return g.value, g2.value, gp.value, bool(f.value)
 
 
 def scan_timing_enable(on=True):

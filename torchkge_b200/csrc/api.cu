@@ -89,6 +89,7 @@ struct Workspace {
   unsigned char* apack;
   float* qbound;
   float* qnorm2;
+  float* qprefix;
   kge::tc::TcMeta* meta_a;
   unsigned long long* amb_count;
   int2* amb_pairs;
@@ -107,7 +108,7 @@ bool approx_supported(int el) { return el == kge::EL_ROT; }
 // the candidate image ends with its TcMeta record (kge_tc_packed_bytes)
 kge::tc::TcMeta* tc_meta_of(const unsigned char* bpack, int64_t n_rows, int n_kb) {
   const int64_t n_ct = (n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
-  const size_t off = align_up(kge::tc::b_image_bytes(n_rows, n_kb) + 2 * (size_t)n_ct * kge::tc::TC_BN * sizeof(float), 256);
+  const size_t off = align_up(kge::tc::b_image_bytes(n_rows, n_kb) + 3 * (size_t)n_ct * kge::tc::TC_BN * sizeof(float), 256);
   return reinterpret_cast<kge::tc::TcMeta*>(const_cast<unsigned char*>(bpack) + off);
 }
 int tc_k_total(int el, int dim) { return el == kge::EL_DOT2 ? 2 * dim : (tc_is_l2(el) ? dim + 3 : dim); }
@@ -127,7 +128,7 @@ Workspace carve(void* base, int qw, int dim, int64_t n, int el = -1, int64_t n_r
   w.s_true = static_cast<float*>(take((size_t)n_qt * kge::TILE_Q * sizeof(float)));
   w.perm = static_cast<int32_t*>(take((size_t)dim * sizeof(int32_t)));
   w.code = static_cast<uint8_t*>(take((size_t)dim));
-  w.apack = nullptr; w.qbound = w.qnorm2 = nullptr; w.amb_count = nullptr; w.amb_pairs = nullptr;
+  w.apack = nullptr; w.qbound = w.qnorm2 = w.qprefix = nullptr; w.amb_count = nullptr; w.amb_pairs = nullptr;
   w.meta_a = nullptr;
   w.amb_cap = 0;
   const bool want_tc = (flags & KGE_FLAG_TENSOR_CORE) && el >= 0 && tc_supported(el) && n_rows > 0;
@@ -137,6 +138,7 @@ Workspace carve(void* base, int qw, int dim, int64_t n, int el = -1, int64_t n_r
     w.apack = static_cast<unsigned char*>(take(kge::tc::a_image_bytes(n, n_kb)));
     w.qbound = static_cast<float*>(take((size_t)n * sizeof(float)));
     w.qnorm2 = static_cast<float*>(take((size_t)n * sizeof(float)));
+    w.qprefix = static_cast<float*>(take((size_t)n * sizeof(float)));
     w.meta_a = static_cast<kge::tc::TcMeta*>(take(kge::tc::TC_META_BYTES));
   }
   if (want_tc || want_approx) {
@@ -297,7 +299,7 @@ size_t kge_tc_packed_bytes(int model, int64_t n_rows, int dim) {
   if (el < 0 || !tc_supported(el) || n_rows <= 0 || dim < 1) return 0;
   const int n_kb = kge::tc::n_kblocks(tc_k_total(el, dim));
   const int64_t n_ct = (n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
-  return align_up(kge::tc::b_image_bytes(n_rows, n_kb) + 2 * (size_t)n_ct * kge::tc::TC_BN * sizeof(float), 256) +
+  return align_up(kge::tc::b_image_bytes(n_rows, n_kb) + 3 * (size_t)n_ct * kge::tc::TC_BN * sizeof(float), 256) +
          kge::tc::TC_META_BYTES;
 }
 
@@ -308,7 +310,7 @@ int kge_tc_configure(int bk, int resident, int ct_group, int max_ctas, int fp16)
 
 int kge_tc_layout_id(void) { return kge::tc::bk() * 2 + (kge::tc::fp16() ? 1 : 0); }
 
-int kge_tc_bound_constants(int model, int dim, float* gamma, float* gamma2, int* fp16) {
+int kge_tc_bound_constants(int model, int dim, float* gamma, float* gamma2, float* gamma_p, int* fp16) {
   const int el = kge::elem_kind_for(model, KGE_SIDE_TAIL);
   if (el < 0 || !tc_supported(el)) return fail(KGE_ERR_UNSUPPORTED, "kge_tc_bound_constants: model has no tensor-core path");
   const HostSchedule* hs = get_schedule(model, dim);
@@ -316,6 +318,7 @@ int kge_tc_bound_constants(int model, int dim, float* gamma, float* gamma2, int*
   const int depth = kge::schedule_depth(hs->s);
   if (gamma) *gamma = kge::tc::tc_gamma(tc_k_total(el, dim), depth, tc_is_l2(el), kge::tc::fp16());
   if (gamma2) *gamma2 = kge::tc::tc_gamma2(depth);
+  if (gamma_p) *gamma_p = kge::tc::tc_gamma_p();
   if (fp16) *fp16 = kge::tc::fp16() ? 1 : 0;
   return KGE_OK;
 }
@@ -339,8 +342,9 @@ int kge_tc_pack_table_cached(int model, const float* ent0, const float* ent1, in
   unsigned char* bpack = static_cast<unsigned char*>(tc_packed);
   float* cbound = reinterpret_cast<float*>(bpack + kge::tc::b_image_bytes(n_rows, n_kb));
   float* cnorm2 = cbound + (size_t)n_ct * kge::tc::TC_BN;
+  float* cprefix = cnorm2 + (size_t)n_ct * kge::tc::TC_BN;
   KGE_CUDA_TRY(kge::tc::launch_pack_b(ent0, ent1, n_rows, dim, k_total, n_kb, tc_is_l2(el), bpack, cbound, cnorm2,
-                                      tc_meta_of(bpack, n_rows, n_kb),
+                                      cprefix, tc_meta_of(bpack, n_rows, n_kb),
                                       reinterpret_cast<unsigned long long*>(guard),
                                       static_cast<cudaStream_t>(stream)),
                "tc pack table");
@@ -410,7 +414,7 @@ int kge_rank_side(const kge_rank_args_t* a) {
     const unsigned char* bpack = static_cast<const unsigned char*>(a->tc_packed);
     const kge::tc::TcMeta* meta_b = tc_meta_of(bpack, a->n_rows, n_kb);
     KGE_CUDA_TRY(kge::tc::launch_pack_a(w.qplain, qw, a->n, a->dim, k_total, n_kb,
-                                        el == kge::EL_L2_HEAD ? 1 : 0, l2, w.apack, w.qbound, w.qnorm2,
+                                        el == kge::EL_L2_HEAD ? 1 : 0, l2, w.apack, w.qbound, w.qnorm2, w.qprefix,
                                         w.meta_a, meta_b, st),
                  "tc pack queries");
     if (kge::tc::scan_grid_size(a->n, a->n_rows, n_kb) <= 0)
@@ -424,6 +428,8 @@ int kge_rank_side(const kge_rank_args_t* a) {
     tp.apack = w.apack; tp.bpack = bpack; tp.s_true = w.s_true;
     tp.qbound = w.qbound; tp.qnorm2 = w.qnorm2;
     tp.cbound = cbound; tp.cnorm2 = cbound + (size_t)n_ct * kge::tc::TC_BN;
+    tp.cprefix = cbound + 2 * (size_t)n_ct * kge::tc::TC_BN; tp.qprefix = w.qprefix;
+    tp.gamma_p = kge::tc::tc_gamma_p();
     tp.counts = a->raw_count; tp.amb_count = w.amb_count; tp.amb_pairs = w.amb_pairs;
     tp.amb_cap = region_cap; tp.dump = a->tc_dump;
     const int ref_depth = kge::schedule_depth(hs->s);

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
     const int col_half = (warp - 2) >> 2;     // which 128 columns of the tile this warp handles
     int acc = 0; uint32_t acc_phase = 0;
     long long cur_qt = -1;
-    float st = 0.f, qb = 0.f, qn = 0.f;
+    float st = 0.f, qb = 0.f, qn = 0.f, kp = 0.f;
     int cnt = 0;
     int2* wbuf = s_amb + (warp - 2) * AMB_BUF;  // this warp's near-tie buffer
     int amb_n = 0;                              // entries in it (warp-uniform)
@@ -316,6 +316,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
         st = vq ? p.s_true[q] : INFINITY;
         qb = vq ? __fadd_ru(p.qbound[q], kappa_a) : 0.f;
         qn = vq ? p.qnorm2[q] : 0.f;
+        // accumulation term: gamma_p P(a) P(b) (x2 for L2, whose score is 2 f - |a|^2)
+        kp = vq ? (L2 ? 2.f : 1.f) * p.gamma_p * p.qprefix[q] * INFL : 0.f;
         if constexpr (L2) {
           // E = 2 gamma qb cb + gamma2 (qb + cb)^2 = cb (k1 + gamma2 cb) + k0
           k1 = 2.f * (p.gamma + p.gamma2) * qb * INFL;
@@ -329,12 +331,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
       // largest candidate norm bound of each of this warp's four 32-column blocks (one coalesced
       // load + one redux each, issued before waiting for the accumulator)
       const int c_begin = col_half * (BN / 2);
-      float cbm[4];
+      float cbm[4], cpm[4];
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const long long c = ct * BN + c_begin + 32 * b + lane;
         const float x = c < p.n_rows ? p.cbound[c] : 0.f;
+        const float y = c < p.n_rows ? p.cprefix[c] : 0.f;
         cbm[b] = __fadd_ru(__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(x))), kappa_b);  // x >= 0
+        cpm[b] = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(y)));
       }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       fence_after();
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
           float e;
           if constexpr (L2) e = fmaf(cb, fmaf(p.gamma2 * INFL, cb, k1), k0) * INFL;
           else e = k1 * cb;
-          e = __fadd_ru(e, e_abs);
+          e = __fadd_ru(__fmaf_ru(kp, cpm[b], e), e_abs);
           t_hi = __fadd_ru(tbase, e);
           t_lo = __fadd_rd(tbase, -e);
           if constexpr (L2) { t_hi = __fmul_ru(t_hi, 0.5f); t_lo = __fmul_rd(t_lo, 0.5f); }
@@ -567,39 +571,56 @@ __global__ void pack_operand_kernel(const float* __restrict__ src0, const float*
   *reinterpret_cast<uint4*>(out + base + plane + off) = *reinterpret_cast<const uint4*>(lo);
 }
 
-// per-row |x|_2 (rounded up a little) and |x|_2^2 of the operand vector, one warp per row; the
-// operand's largest |x| and largest |x|_2^2 are folded into meta (bit-pattern maxima of non-negative
-// floats: a NaN or inf anywhere wins, which invalidates the image -- see tc_meta_kernel)
+// per-row |x|_2 (rounded up a little), |x|_2^2 and the running-magnitude factor
+//   P(x) = sqrt( sum_{i=1..ceil(k/16)} |x_{<= 16 i}|^2 )     (tc.h: tc_gamma_p)
+// of the operand vector, one warp per row: 32 consecutive k per iteration, lanes 0-15 / 16-31 are the
+// two MMA k-steps of the iteration.  The operand's largest |x| and largest |x|_2^2 are folded into
+// meta (bit-pattern maxima of non-negative floats: a NaN or inf anywhere wins, which invalidates the
+// image -- see tc_meta_kernel).
 __global__ void row_norms_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
                                  long long row_stride, long long plane1_offset, long long n_rows,
-                                 int dim, int k_total, int sub_mode, float* __restrict__ bound,
-                                 float* __restrict__ norm2, TcMeta* __restrict__ meta,
+                                 int dim, int k_total, int extra_steps, int sub_mode, float* __restrict__ bound,
+                                 float* __restrict__ norm2, float* __restrict__ prefix, TcMeta* __restrict__ meta,
                                  const unsigned long long* __restrict__ guard) {
+  // extra_steps: MMA k-steps beyond ceil(k_total / 16) (the L2 fold slots spilling into a k-step of
+  // their own): their incoming accumulator is bounded by the full |x|^2
   if (guard_unchanged(guard)) return;
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n_rows) return;
   const float* a = src0 + (size_t)w * row_stride;
   const float* b = src1 ? src1 + (size_t)w * row_stride : a + plane1_offset;
-  double s = 0.0, sa = 0.0, sb = 0.0;
+  double s = 0.0, sa = 0.0, sb = 0.0;   // s: running |x_{<= ...}|^2 (all lanes hold the same value)
+  double p2 = 0.0;                      // sum of the squared prefix norms at the 16-element boundaries
   unsigned mx = 0u;
-  for (int k = lane; k < k_total; k += 32) {
-    float x;
-    if (sub_mode) {
-      x = k < dim ? __fsub_rn(b[k], a[k]) : 0.f;
-      if (k < dim) { sa += (double)a[k] * (double)a[k]; sb += (double)b[k] * (double)b[k]; }
-    } else {
-      x = operand_value(a, b, dim, k, k_total);
+  for (int k0 = 0; k0 < k_total; k0 += 32) {
+    const int k = k0 + lane;
+    float x = 0.f;
+    double xa = 0.0, xb = 0.0;
+    if (k < k_total) {
+      if (sub_mode) {
+        x = k < dim ? __fsub_rn(b[k], a[k]) : 0.f;
+        if (k < dim) { xa = (double)a[k] * (double)a[k]; xb = (double)b[k] * (double)b[k]; }
+      } else {
+        x = operand_value(a, b, dim, k, k_total);
+      }
     }
-    s += (double)x * (double)x;
     mx = max(mx, __float_as_uint(fabsf(x)));
-  }
+    double h = (double)x * (double)x;   // -> sum over this lane's half-warp (one k-step)
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    sa += __shfl_xor_sync(0xffffffffu, sa, o);
-    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    for (int o = 8; o > 0; o >>= 1) {
+      h += __shfl_xor_sync(0xffffffffu, h, o);
+      xa += __shfl_xor_sync(0xffffffffu, xa, o);
+      xb += __shfl_xor_sync(0xffffffffu, xb, o);
+    }
+    const double h_lo = __shfl_sync(0xffffffffu, h, 0), h_hi = __shfl_sync(0xffffffffu, h, 16);
+    sa += xa + __shfl_xor_sync(0xffffffffu, xa, 16);
+    sb += xb + __shfl_xor_sync(0xffffffffu, xb, 16);
+    s += h_lo;
+    p2 += s;                                           // |x_{<= 16 i}|^2 after k-step i = 2 g + 1
+    if (k0 + 16 < k_total) { s += h_hi; p2 += s; }     // ... and after k-step 2 g + 2
   }
+  p2 += (double)extra_steps * s;
   mx = __reduce_max_sync(0xffffffffu, mx);
   if (lane == 0) {
     const float n2 = (float)s;
@@ -608,6 +629,9 @@ __global__ void row_norms_kernel(const float* __restrict__ src0, const float* __
     // |r| and |t| separately, so the bound uses |t| + |r| (>= |t - r|) for this operand
     const double nb = sub_mode ? sqrt(sa) + sqrt(sb) : sqrt(s);
     bound[w] = (float)(nb * (1.0 + 1e-6)) + 1e-30f;
+    // the head-side operand t - r is bounded by |t| + |r| the same way: scale P by that ratio
+    const double pr = sqrt(p2) * (s > 0.0 ? nb / sqrt(s) : 1.0);
+    prefix[w] = (float)(pr * (1.0 + 1e-6)) + 1e-30f;
     atomicMax(reinterpret_cast<unsigned*>(&meta->max_abs), mx);
     atomicMax(reinterpret_cast<unsigned*>(&meta->max_norm2), __float_as_uint(fabsf(n2)));
   }
@@ -834,7 +858,7 @@ void launch_pack_operand(const float* src0, const float* src1, long long row_str
 uint32_t instruction_descriptor() { return fp16() ? IDESC_FP16 : IDESC_BF16; }
 
 cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows, int dim, int k_total,
-                          int n_kb, bool fold, unsigned char* bpack, float* cbound, float* cnorm2,
+                          int n_kb, bool fold, unsigned char* bpack, float* cbound, float* cnorm2, float* cprefix,
                           TcMeta* meta_b, unsigned long long* guard, cudaStream_t st) {
   if (n_rows <= 0) return cudaSuccess;
   if (guard) {
@@ -853,7 +877,8 @@ cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows
   tc_meta_reset_kernel<<<1, 32, 0, st>>>(meta_b, guard);
   // norms first: with fold the image carries -|b|^2/2 (the SAME fp32 value the bound uses)
   row_norms_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, st>>>(
-      ent0, ent1, dim, 0, n_rows, dim, fold ? dim : k_total, 0, cbound, cnorm2, meta_b, guard);
+      ent0, ent1, dim, 0, n_rows, dim, fold ? dim : k_total, fold ? (k_total + 15) / 16 - (dim + 15) / 16 : 0, 0,
+      cbound, cnorm2, cprefix, meta_b, guard);
   tc_meta_kernel<<<1, 32, 0, st>>>(meta_b, nullptr, k_total, 0, fold ? 1 : 0, fp16() ? 1 : 0, guard);
   launch_pack_operand<BN>(ent0, ent1, dim, 0, n_rows, dim, k_total, n_kb, 0, fold ? 2 : 0, cnorm2, meta_b, guard,
                           bpack, st);
@@ -862,14 +887,14 @@ cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows
 }
 
 cudaError_t launch_pack_a(const float* qplain, int qw, long long n_q, int dim, int k_total, int n_kb,
-                          int sub_mode, bool fold, unsigned char* apack, float* qbound, float* qnorm2,
+                          int sub_mode, bool fold, unsigned char* apack, float* qbound, float* qnorm2, float* qprefix,
                           TcMeta* meta_a, const TcMeta* meta_b, cudaStream_t st) {
   if (n_q <= 0) return cudaSuccess;
   tc_meta_reset_kernel<<<1, 32, 0, st>>>(meta_a, nullptr);
   // qplain rows are [qw][dim]: plane 1 (if any) follows plane 0 inside the row
   row_norms_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, st>>>(
-      qplain, nullptr, (long long)qw * dim, dim, n_q, dim, fold ? dim : k_total, sub_mode, qbound, qnorm2, meta_a,
-      nullptr);
+      qplain, nullptr, (long long)qw * dim, dim, n_q, dim, fold ? dim : k_total,
+      fold ? (k_total + 15) / 16 - (dim + 15) / 16 : 0, sub_mode, qbound, qnorm2, qprefix, meta_a, nullptr);
   tc_meta_kernel<<<1, 32, 0, st>>>(meta_a, meta_b, k_total, 1, fold ? 1 : 0, fp16() ? 1 : 0, nullptr);
   launch_pack_operand<BM>(qplain, nullptr, (long long)qw * dim, dim, n_q, dim, k_total, n_kb, sub_mode,
                           fold ? 1 : 0, nullptr, meta_a, nullptr, apack, st);

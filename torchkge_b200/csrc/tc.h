@@ -45,6 +45,8 @@ struct TcScanParams {
   const float* qnorm2;         // [n_q] |a|_2^2 (L2 only)
   const float* cbound;         // [n_rows] >= |b|_2
   const float* cnorm2;         // [n_rows]
+  const float* qprefix;        // [n_q]    P(a) = sqrt(sum_i |a_{<=16 i}|^2): running-magnitude factor (tc_gamma_p)
+  const float* cprefix;        // [n_rows] P(b)
   int32_t* counts;             // [n_q] +=
   unsigned long long* amb_count;  // [n_qt] fill count of each query tile's region
   int2* amb_pairs;                // [n_qt][amb_cap]
@@ -53,8 +55,9 @@ struct TcScanParams {
   const TcMeta* meta_a;        // device: facts of the query image (this call)
   const TcMeta* meta_b;        // device: facts of the candidate image
   uint32_t idesc;              // tcgen05 instruction descriptor (operand format bf16 / fp16)
-  float gamma;                 // tc_gamma(k)
-  float gamma2;                // tc_gamma2(k) (L2 only)
+  float gamma;                 // tc_gamma(k): multiplies |a| |b|
+  float gamma2;                // tc_gamma2(k) (L2 only): multiplies (|a| + |b|)^2
+  float gamma_p;               // tc_gamma_p(): multiplies P(a) P(b) (accumulation inside the tensor core)
   int l2;                      // 1: score = -(|a|^2 + |b|^2 - 2 a.b)
   int n_kb;
   int k_total;
@@ -72,10 +75,17 @@ struct TcScanParams {
 //     (fp16 only: a lo part below fp16's normal range is off by <= 2^-25 in scaled units instead;
 //      that absolute residual is carried by TcMeta::kappa, an additive inflation of the row bounds)
 //   fp32 accumulation inside the tensor core: every tcgen05.mma adds 16 exact products to the
-//     accumulator; MEASURED on B200 (scripts/tc_numerics_probe.py, profiles/r02_tc_numerics_probe.md):
+//     accumulator; MEASURED on B200 (scripts/tc_numerics_probe.py, profiles/r02_tc_numerics_probe.*):
 //     |result - exact| <= TC_ACC_ULPS * 2^-24 * (|acc_in| + sum |products|) per instruction.
-//     All 3 ceil(k/16) instructions see a running magnitude <= sum_k |a_k b_k| (1 + 2^-p)^2
-//                                                       -> TC_ACC_ULPS (3 ceil(k/16) + 2) 2^-24
+//     Summed over the 3 ceil(k/16) instructions of a pair: the products are counted once,
+//     sum |products| <= (1 + 2^-p)^2 sum_k |a_k b_k|                      -> 1.01 TC_ACC_ULPS 2^-24  (in gamma)
+//     and the incoming accumulator of any of the three instructions of k-step i is at most the sum
+//     of the |products| of the first i k-steps, <= 1.01 |a_{<=16 i}| |b_{<=16 i}| (Cauchy-Schwarz on the
+//     prefix), so that, with P(x)^2 = sum_i |x_{<=16 i}|^2 (per row, row_norms_kernel),
+//       sum over instructions of |acc_in| <= 3.03 sum_i |a_{<=16i}| |b_{<=16i}| <= 3.03 P(a) P(b)
+//                                                     -> gamma_p = 3.04 TC_ACC_ULPS 2^-24, times P(a) P(b)
+//     (P(x) <= sqrt(ceil(k/16)) |x|: never worse than charging every instruction the full |a| |b|, and
+//      about half of that when the mass of the vectors is spread evenly over k)
 //   dot models only: the reference's own fp32 evaluation -- every product rounded once (ComplEx:
 //     two products and their sum), then summed in ATen's cascade order, whose tree depth
 //     `ref_depth` (schedule.h: schedule_depth, computed from the very schedule the exact kernels
@@ -86,7 +96,7 @@ struct TcScanParams {
 //   sums in the 8-lane norm order (depth ref_depth), takes an exactly rounded sqrt and squares it:
 //     relative (ref_depth + 10) u on sum x^2;
 //   this side: |a|^2 and |b|^2 rounded to fp32 (2u), |b|^2/2 carried as three half-precision pieces
-//   (u), the <= 6 MMA instructions that accumulate it (6 TC_ACC_ULPS u |b|^2 / 2), threshold
+//   (u), the <= 6 MMA instructions that see it in their accumulator (6 TC_ACC_ULPS u |b|^2 / 2), threshold
 //   arithmetic is directed-rounded                     -> (ref_depth + 18 + 3 TC_ACC_ULPS) * 2^-24
 // tests/test_tc_gpu.py measures the actual error on random AND adversarial operands (cancelling,
 // wide dynamic range, same sign) and requires error <= bound.
@@ -100,10 +110,12 @@ struct TcScanParams {
 constexpr double TC_ACC_ULPS = 10.0;  // per-instruction accumulation error in units of 2^-24 * running magnitude
 inline float tc_gamma(int k_total, int ref_depth, bool l2, bool fp16 = false) {
   const double split = fp16 ? 3.0 * 0x1p-22 * (1.0 + 0x1p-11) : 3.0 * 0x1p-16 * (1.0 + 0x1p-8);
-  const double accum = TC_ACC_ULPS * (3.0 * ((k_total + 15) / 16) + 2.0) * 0x1p-24;
+  const double accum_once = 1.01 * TC_ACC_ULPS * 0x1p-24;   // the products themselves, counted once
   const double ref = l2 ? 0.0 : (ref_depth + 4.0) * 0x1p-24;
-  return (float)(split + accum + ref);
+  (void)k_total;
+  return (float)(split + accum_once + ref);
 }
+inline float tc_gamma_p() { return (float)(3.04 * TC_ACC_ULPS * 0x1p-24); }
 inline float tc_gamma2(int ref_depth) { return (float)((ref_depth + 18.0 + 3.0 * TC_ACC_ULPS) * 0x1p-24); }
 
 size_t a_image_bytes(long long n_q, int n_kb);
@@ -115,10 +127,10 @@ size_t b_image_bytes(long long n_rows, int n_kb);
 // table's content checksum is recomputed (one read of the table) and the packing kernels run only
 // if it differs from the checksum the image was built from -- a cache that cannot go stale.
 cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows, int dim, int k_total,
-                          int n_kb, bool fold, unsigned char* bpack, float* cbound, float* cnorm2,
+                          int n_kb, bool fold, unsigned char* bpack, float* cbound, float* cnorm2, float* cprefix,
                           TcMeta* meta_b, unsigned long long* guard, cudaStream_t st);
 cudaError_t launch_pack_a(const float* qplain, int qw, long long n_q, int dim, int k_total, int n_kb,
-                          int sub_mode, bool fold, unsigned char* apack, float* qbound, float* qnorm2,
+                          int sub_mode, bool fold, unsigned char* apack, float* qbound, float* qnorm2, float* qprefix,
                           TcMeta* meta_a, const TcMeta* meta_b, cudaStream_t st);
 uint32_t instruction_descriptor();
 cudaError_t launch_tc_scan(const TcScanParams& p, cudaStream_t st);
