@@ -726,7 +726,7 @@ int kge_topk_dense(const float* scores, int64_t n, int64_t n_cand, int k, const 
 namespace {
 bool tables_ok(const kge_tables_t* tb) {
   if (!tb || !tb->ent0 || !tb->rel0 || tb->dim < 1) return false;
-  if (tb->model < KGE_TRANSE_L1 || tb->model > KGE_ROTATE) return false;
+  if (tb->model < KGE_TRANSE_L1 || tb->model > KGE_TORUSE_L2) return false;
   if ((tb->model == KGE_COMPLEX || tb->model == KGE_ROTATE) && (!tb->ent1 || !tb->rel1)) return false;
   return true;
 }

@@ -87,6 +87,9 @@ __device__ __forceinline__ float inv_norm_of(const float* row, int dim, int lane
   return 1.0f / fmaxf(sqrtf(s), NORM_EPS);
 }
 
+// torch.frac: the fractional part keeps the sign of its argument
+__device__ __forceinline__ float frac_of(float v) { return v - truncf(v); }
+
 // score of one triple; all lanes return the same value
 __device__ float triple_score(int model, int dim, const RowPtrs& p, int lane, float* inv_h_out,
                               float* inv_t_out) {
@@ -130,6 +133,14 @@ __device__ float triple_score(int model, int dim, const RowPtrs& p, int lane, fl
         const float rh = p.h0[k], ih = p.h1[k], rt = p.t0[k], it = p.t1[k], rr = p.r0[k], ir = p.r1[k];
         const float a = rh * rr - ih * ir - rt, b = rh * ir + ih * rr - it;
         s += sqrtf(a * a + b * b);
+      }
+      return -warp_sum(s);
+    case KGE_TORUSE_L1:   // translation.py:706-720: -diss(frac(h) + frac(r), frac(t)), dissimilarities.py:28-43
+    case KGE_TORUSE_L2:
+      for (int k = lane; k < dim; k += 32) {
+        const float x = (frac_of(p.h0[k]) + frac_of(p.r0[k])) - frac_of(p.t0[k]);
+        if (model == KGE_TORUSE_L1) { const float ax = fabsf(x); s += 2.f * fminf(ax, 1.f - ax); }
+        else { const float x2 = x * x; s += 4.f * fminf(x2, 1.f - x2); }
       }
       return -warp_sum(s);
     default: return 0.f;
@@ -180,6 +191,23 @@ __device__ void triple_backward(int model, int dim, const RowPtrs& p, const Trai
       atomicAdd(gh0 + k, g * d_rh); atomicAdd(gh1 + k, g * d_ih);
       atomicAdd(gt0 + k, g * d_rt); atomicAdd(gt1 + k, g * d_it);
       atomicAdd(gr0 + k, g * d_rr); atomicAdd(gr1 + k, g * d_ir);
+    }
+    return;
+  }
+  if (model == KGE_TORUSE_L1 || model == KGE_TORUSE_L2) {
+    // x = frac(h) + frac(r) - frac(t) (frac has unit slope); min(u, v) sends the gradient to the
+    // smaller argument and, as torch.min does, half to each at an exact tie
+    for (int k = lane; k < dim; k += 32) {
+      const float x = (frac_of(p.h0[k]) + frac_of(p.r0[k])) - frac_of(p.t0[k]);
+      float d;   // d score / d x
+      if (model == KGE_TORUSE_L1) {
+        const float ax = fabsf(x), sg = x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f);
+        d = ax < 1.f - ax ? -2.f * sg : (ax > 1.f - ax ? 2.f * sg : 0.f);
+      } else {
+        const float x2 = x * x;
+        d = x2 < 1.f - x2 ? -8.f * x : (x2 > 1.f - x2 ? 8.f * x : 0.f);
+      }
+      atomicAdd(gh0 + k, g * d); atomicAdd(gr0 + k, g * d); atomicAdd(gt0 + k, -g * d);
     }
     return;
   }

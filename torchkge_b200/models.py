@@ -400,8 +400,9 @@ class TorusEModel(TranslationModel):
     ``dissimilarity_type`` is 'torus_L1' or 'torus_L2' ('L1' on fractional parts is accepted too;
     'torus_eL2' is not on the CUDA path).  Link prediction (``LinkPredictionEvaluator``,
     ``inference_scoring_function``, ``EntityInference``) runs on the scan kernels with their own
-    element kinds; ``scoring_function`` (training) is composed from torch ops on the model's device
-    -- TorusE has no hand-written training kernel yet.
+    element kinds; ``scoring_function`` (training) with the torus dissimilarities runs on the per-triple
+    kernels of csrc/train.cu (forward and backward; the fused margin step too), the plain 'L1' variant is
+    composed from torch ops.
     """
 
     def __init__(self, emb_dim, n_entities, n_relations, dissimilarity_type):
@@ -416,6 +417,9 @@ class TorusEModel(TranslationModel):
     def scoring_function(self, h_idx, t_idx, r_idx):
         """-dissimilarity(frac(h) + frac(r), frac(t)) (translation.py:706-720)."""
         self.normalized = False
+        if self.dissimilarity in (l1_torus_dissimilarity, l2_torus_dissimilarity) and self.ent_emb.weight.is_cuda:
+            from .training import score_triples
+            return score_triples(self, h_idx, t_idx, r_idx)    # kge_score_triples_fwd / _bwd (train.cu)
         h, t, r = self.ent_emb(h_idx), self.ent_emb(t_idx), self.rel_emb(r_idx)
         h.data.frac_()
         t.data.frac_()

@@ -14,7 +14,7 @@ from .engine import ModelSpec, _ptr, _stream
 def _param_tensors(model, code):
     """Parameters in ModelSpec order (ent0, ent1, rel0, rel1); RotatE's relation planes are
     differentiable functions (cos, sin) of its phase parameter."""
-    if code in (_lib.TRANSE_L1, _lib.TRANSE_L2, _lib.DISTMULT):
+    if code in (_lib.TRANSE_L1, _lib.TRANSE_L2, _lib.DISTMULT, _lib.TORUSE_L1, _lib.TORUSE_L2):
         return model.ent_emb.weight, None, model.rel_emb.weight, None
     if code == _lib.RESCAL:
         return model.ent_emb.weight, None, model.rel_mat.weight, None
@@ -85,12 +85,23 @@ class _ScoreTriples(torch.autograd.Function):
         return (None, None, None, None, None, *gs)
 
 
+def _training_code(model):
+    """Kernel selector of the training-side kernels.  TorusE: the torus dissimilarities have their own
+    per-triple kernels (no row normalisation, fractional parts taken on the fly, translation.py:706-720);
+    its plain-'L1' variant is not on the CUDA path (the TransE-L1 kernels L2-normalise the entity rows)."""
+    if type(model).__name__ == "TorusEModel":
+        dname = getattr(model.dissimilarity, "__name__", str(model.dissimilarity))
+        code = {"l1_torus_dissimilarity": _lib.TORUSE_L1, "l2_torus_dissimilarity": _lib.TORUSE_L2}.get(dname)
+        if code is None:
+            raise NotImplementedError("TorusE with dissimilarity %s has no training kernel" % dname)
+        return code
+    return ModelSpec.from_model(model).code
+
+
 def score_triples(model, h_idx, t_idx, r_idx):
     """``model.scoring_function(h_idx, t_idx, r_idx)`` -> (n,) float scores, differentiable with
     respect to the model's embedding tables."""
-    if type(model).__name__ == "TorusEModel":
-        raise NotImplementedError("TorusE scores triples with torch ops (models.TorusEModel.scoring_function)")
-    code = ModelSpec.from_model(model).code
+    code = _training_code(model)
     ent0, ent1, rel0, rel1 = _param_tensors(model, code)
     return _ScoreTriples.apply(code, model.emb_dim, h_idx, t_idx, r_idx, ent0, ent1, rel0, rel1)
 
@@ -225,10 +236,7 @@ def fused_margin_step(model, heads, tails, relations, margin, n_neg=1, negatives
         loss = criterion(pos, neg)
     without materialising nh, nt, pos, neg.
     """
-    if type(model).__name__ == "TorusEModel":
-        raise NotImplementedError("TorusE has no fused training step (its scoring_function works on "
-                                  "fractional parts, not on L2-normalised rows)")
-    spec_code = ModelSpec.from_model(model).code
+    spec_code = _training_code(model)
     ent0, ent1, rel0, rel1 = _param_tensors(model, spec_code)
     nh = nt = None
     if negatives is not None:
