@@ -503,8 +503,9 @@ def run_ours(args, rank, local, world):
     dev = torch.device("cuda", local)
     if world > 1:
         # NCCL's init lines (rank count, transport, NVLS) go to stderr with everything else
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"          # the image default (VERSION) hides the rank / transport lines
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
     if args.workload == "c5":
         return run_c5(args, rank, world, dev)

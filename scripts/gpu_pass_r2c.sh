@@ -17,6 +17,11 @@ tail -3 gpurun_out/bench_c5_err.txt
 timeout 900 python bench.py --steps 10 --warmup 3 --cpu-sample 256 2>gpurun_out/bench_c2_s256_err.txt > gpurun_out/bench_c2_s256.json; echo "c2 s256 rc=$?"; python -c "
 import json;d=json.load(open('gpurun_out/bench_c2_s256.json'));print(d['value'],d['e2e']['value'],d['cpu_baseline'],d['api_reference_kg']['first_call'],d['api_reference_kg']['steady_state'])"
 tail -3 gpurun_out/bench_c2_s256_err.txt
+# the per-rank workload of an 8-GPU query-sharded run (2558 test triples) on one GPU: where does the step go?
+KGE_TRACE=1 timeout 300 python bench.py --n-test 2558 --steps 20 --warmup 5 --no-extras --no-cpu-baseline 2>gpurun_out/bench_c2_q2558_err.txt > gpurun_out/bench_c2_q2558.json; python -c "
+import json;d=json.load(open('gpurun_out/bench_c2_q2558.json'));r=d['roofline'];print('q2558',d['value'],d['ms_per_step'],r['ms_per_launch'],r['recheck_ms_per_launch'],d['e2e']['ms_per_step'])"
+grep trace gpurun_out/bench_c2_q2558_err.txt | tail -14
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_c2_q2558.csv python bench.py --n-test 2558 --steps 2 --warmup 1 --no-extras --no-cpu-baseline > gpurun_out/bench_under_ncu_q2558.txt 2>&1
 # ncu: launch list of two c2 steps, then full captures
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c2.csv python bench.py --steps 2 --warmup 1 --no-extras --no-cpu-baseline > gpurun_out/bench_under_ncu.txt 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_scan_kernel -s 2 -c 1 -o gpurun_out/tc_scan_c2_fp16 -f python bench.py --steps 1 --warmup 1 --no-extras --no-cpu-baseline > gpurun_out/ncu_tc.txt 2>&1
