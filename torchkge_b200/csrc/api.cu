@@ -160,7 +160,7 @@ Workspace carve(void* base, int qw, int dim, int64_t n, int el = -1, int64_t n_r
 int prepare_queries(int model, int side, int dim, int64_t n, const float* hrows,
                     const float* trows, const float* rel0, const float* rel1,
                     const int64_t* r_idx, const HostSchedule* hs, const Workspace& w, int el,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, bool scalar_layout = true) {
   KGE_CUDA_TRY(cudaMemcpyAsync(w.perm, hs->s.perm.data(), (size_t)dim * sizeof(int32_t),
                                cudaMemcpyHostToDevice, stream),
                "upload schedule perm");
@@ -170,9 +170,10 @@ int prepare_queries(int model, int side, int dim, int64_t n, const float* hrows,
   KGE_CUDA_TRY(kge::launch_prep_queries(model, side, dim, n, hrows, trows, rel0, rel1, r_idx,
                                         w.qplain, stream),
                "prep_queries");
-  KGE_CUDA_TRY(kge::launch_pack_queries(w.qplain, kge::elem_qw(el), dim, n, w.perm, w.qpacked,
-                                        stream),
-               "pack_queries");
+  if (scalar_layout)   // the k-major query image of the scalar scan (the tensor-core scan builds its own)
+    KGE_CUDA_TRY(kge::launch_pack_queries(w.qplain, kge::elem_qw(el), dim, n, w.perm, w.qpacked,
+                                          stream),
+                 "pack_queries");
   return KGE_OK;
 }
 
@@ -382,7 +383,7 @@ int kge_rank_side(const kge_rank_args_t* a) {
   const bool casc = hs->s.has_cascade;
 
   int rc = prepare_queries(a->model, a->side, a->dim, a->n, a->hrows, a->trows, a->rel0, a->rel1,
-                           a->r_idx, hs, w, el, st);
+                           a->r_idx, hs, w, el, st, !use_tc);
   if (rc != KGE_OK) return rc;
 
   // true scores: the true entity's row is the gathered tail (tail side) / head (head side) row

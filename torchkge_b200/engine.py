@@ -431,18 +431,20 @@ class QueryShard:
         return t
 
     def all_gather(self, parts):
-        """Per-rank result vectors (one entry per local triple) -> full-length vectors on every rank."""
+        """Per-rank result vectors (one entry per local triple, same dtype) -> full-length vectors on
+        every rank, with ONE collective for all of them."""
         if self.world == 1:
             return list(parts)
         import torch.distributed as dist
-        out = []
-        for x in parts:
-            pad = torch.zeros(self.per, dtype=x.dtype, device=x.device)
-            pad[:x.numel()] = x
-            bufs = [torch.empty_like(pad) for _ in range(self.world)]
-            dist.all_gather(bufs, pad, group=self.group)
-            out.append(torch.cat(bufs)[:self.n])
-        return out
+        k = len(parts)
+        mine = torch.zeros((k, self.per), dtype=parts[0].dtype, device=parts[0].device)
+        for i, x in enumerate(parts):
+            mine[i, :x.numel()] = x
+        everyone = torch.empty((self.world, k, self.per), dtype=mine.dtype, device=mine.device)
+        dist.all_gather([everyone[i] for i in range(self.world)], mine, group=self.group)
+        # rank-major slices of length `per` concatenate to the original order of the triples
+        full = everyone.permute(1, 0, 2).reshape(k, self.world * self.per)[:, :self.n]
+        return [full[i] for i in range(k)]
 
 
 def _csr_slice(filt, lo, hi, n):
