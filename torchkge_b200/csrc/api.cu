@@ -105,12 +105,24 @@ bool tc_is_l2(int el) { return el == kge::EL_L2_TAIL || el == kge::EL_L2_HEAD; }
 // squared norm in three extra k slots (tc.h: launch_pack_b)
 // bound-and-refine on the fp32 pipes (approximate element arithmetic + exact recheck): RotatE
 bool approx_supported(int el) { return el == kge::EL_ROT; }
-// the candidate image ends with its TcMeta record (kge_tc_packed_bytes)
-kge::tc::TcMeta* tc_meta_of(const unsigned char* bpack, int64_t n_rows, int n_kb) {
-  const int64_t n_ct = (n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
-  const size_t off = align_up(kge::tc::b_image_bytes(n_rows, n_kb) + 3 * (size_t)n_ct * kge::tc::TC_BN * sizeof(float), 256);
-  return reinterpret_cast<kge::tc::TcMeta*>(const_cast<unsigned char*>(bpack) + off);
-}
+// Byte offsets inside a tensor-core candidate image (kge_tc_pack_table): operand planes, then per-row
+// norm bounds / squared norms / running-magnitude factors (padded to whole 256-row tiles), then the
+// maxima of the bounds and of the factors over aligned blocks of 32 rows (what one epilogue warp
+// needs per 32-column block), then the TcMeta record.
+struct TcImageLayout {
+  size_t cbound, cnorm2, cprefix, cbmax32, cpmax32, meta, total;
+  TcImageLayout(int64_t n_rows, int n_kb) {
+    const size_t n_ct = (size_t)((n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN);
+    const size_t rows = n_ct * kge::tc::TC_BN * sizeof(float);
+    cbound = kge::tc::b_image_bytes(n_rows, n_kb);
+    cnorm2 = cbound + rows;
+    cprefix = cnorm2 + rows;
+    cbmax32 = cprefix + rows;
+    cpmax32 = cbmax32 + rows / 32;
+    meta = align_up(cpmax32 + rows / 32, 256);
+    total = meta + kge::tc::TC_META_BYTES;
+  }
+};
 int tc_k_total(int el, int dim) { return el == kge::EL_DOT2 ? 2 * dim : (tc_is_l2(el) ? dim + 3 : dim); }
 
 Workspace carve(void* base, int qw, int dim, int64_t n, int el = -1, int64_t n_rows = 0,
@@ -299,9 +311,7 @@ size_t kge_tc_packed_bytes(int model, int64_t n_rows, int dim) {
   const int el = kge::elem_kind_for(model, KGE_SIDE_TAIL);
   if (el < 0 || !tc_supported(el) || n_rows <= 0 || dim < 1) return 0;
   const int n_kb = kge::tc::n_kblocks(tc_k_total(el, dim));
-  const int64_t n_ct = (n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
-  return align_up(kge::tc::b_image_bytes(n_rows, n_kb) + 3 * (size_t)n_ct * kge::tc::TC_BN * sizeof(float), 256) +
-         kge::tc::TC_META_BYTES;
+  return TcImageLayout(n_rows, n_kb).total;
 }
 
 int kge_tc_configure(int bk, int resident, int ct_group, int max_ctas, int fp16) {
@@ -339,13 +349,12 @@ int kge_tc_pack_table_cached(int model, const float* ent0, const float* ent1, in
   DeviceScope device_scope(ent0);
   const int k_total = tc_k_total(el, dim);
   const int n_kb = kge::tc::n_kblocks(k_total);
-  const int64_t n_ct = (n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
   unsigned char* bpack = static_cast<unsigned char*>(tc_packed);
-  float* cbound = reinterpret_cast<float*>(bpack + kge::tc::b_image_bytes(n_rows, n_kb));
-  float* cnorm2 = cbound + (size_t)n_ct * kge::tc::TC_BN;
-  float* cprefix = cnorm2 + (size_t)n_ct * kge::tc::TC_BN;
-  KGE_CUDA_TRY(kge::tc::launch_pack_b(ent0, ent1, n_rows, dim, k_total, n_kb, tc_is_l2(el), bpack, cbound, cnorm2,
-                                      cprefix, tc_meta_of(bpack, n_rows, n_kb),
+  const TcImageLayout L(n_rows, n_kb);
+  auto fptr = [&](size_t off) { return reinterpret_cast<float*>(bpack + off); };
+  KGE_CUDA_TRY(kge::tc::launch_pack_b(ent0, ent1, n_rows, dim, k_total, n_kb, tc_is_l2(el), bpack, fptr(L.cbound),
+                                      fptr(L.cnorm2), fptr(L.cprefix), fptr(L.cbmax32), fptr(L.cpmax32),
+                                      reinterpret_cast<kge::tc::TcMeta*>(bpack + L.meta),
                                       reinterpret_cast<unsigned long long*>(guard),
                                       static_cast<cudaStream_t>(stream)),
                "tc pack table");
@@ -413,7 +422,8 @@ int kge_rank_side(const kge_rank_args_t* a) {
     const int64_t n_ct = (a->n_rows + kge::tc::TC_BN - 1) / kge::tc::TC_BN;
     const bool l2 = el == kge::EL_L2_TAIL || el == kge::EL_L2_HEAD;
     const unsigned char* bpack = static_cast<const unsigned char*>(a->tc_packed);
-    const kge::tc::TcMeta* meta_b = tc_meta_of(bpack, a->n_rows, n_kb);
+    const TcImageLayout L(a->n_rows, n_kb);
+    const kge::tc::TcMeta* meta_b = reinterpret_cast<const kge::tc::TcMeta*>(bpack + L.meta);
     KGE_CUDA_TRY(kge::tc::launch_pack_a(w.qplain, qw, a->n, a->dim, k_total, n_kb,
                                         el == kge::EL_L2_HEAD ? 1 : 0, l2, w.apack, w.qbound, w.qnorm2, w.qprefix,
                                         w.meta_a, meta_b, st),
@@ -423,13 +433,13 @@ int kge_rank_side(const kge_rank_args_t* a) {
     const int regions = (int)((a->n + kge::tc::TC_BM - 1) / kge::tc::TC_BM);  // one per query tile
     const unsigned long long region_cap = w.amb_cap / (unsigned long long)regions;
     KGE_CUDA_TRY(cudaMemsetAsync(w.amb_count, 0, (size_t)regions * sizeof(unsigned long long), st), "tc reset list");
-    const float* cbound = reinterpret_cast<const float*>(bpack + kge::tc::b_image_bytes(a->n_rows, n_kb));
+    auto fptr = [&](size_t off) { return reinterpret_cast<const float*>(bpack + off); };
     kge::tc::TcScanParams tp;
     tp.meta_a = w.meta_a; tp.meta_b = meta_b; tp.idesc = 0;
     tp.apack = w.apack; tp.bpack = bpack; tp.s_true = w.s_true;
     tp.qbound = w.qbound; tp.qnorm2 = w.qnorm2;
-    tp.cbound = cbound; tp.cnorm2 = cbound + (size_t)n_ct * kge::tc::TC_BN;
-    tp.cprefix = cbound + 2 * (size_t)n_ct * kge::tc::TC_BN; tp.qprefix = w.qprefix;
+    tp.cbound = fptr(L.cbound); tp.cnorm2 = fptr(L.cnorm2); tp.cprefix = fptr(L.cprefix);
+    tp.cbmax32 = fptr(L.cbmax32); tp.cpmax32 = fptr(L.cpmax32); tp.qprefix = w.qprefix;
     tp.gamma_p = kge::tc::tc_gamma_p();
     tp.counts = a->raw_count; tp.amb_count = w.amb_count; tp.amb_pairs = w.amb_pairs;
     tp.amb_cap = region_cap; tp.dump = a->tc_dump;

@@ -244,19 +244,37 @@ __device__ __forceinline__ float pair_score(int dim, const float* __restrict__ q
   return acc_finish<EL>(r);
 }
 
+// s_true[i] = score(query i, its true row).  Chain-parallel like the filter pass: 8 lanes per query for
+// the L2 norm, 32 for the cascade sum (pair_score_chains: same bits as the schedule replay), one lane
+// for the sequential L1 norm and for dims below 8.
 template <int EL, bool CASC>
 __global__ void true_scores_kernel(int dim, long long n, const float* __restrict__ qplain,
                                    const float* __restrict__ rows,
                                    const int32_t* __restrict__ perm,
                                    const uint8_t* __restrict__ code, float* __restrict__ s_true) {
   constexpr int QW = ElemTraits<EL>::QW, CW = ElemTraits<EL>::CW;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* q0 = qplain + (size_t)i * QW * dim;
+  constexpr int RED = ElemTraits<EL>::RED;
+  constexpr int LANES = RED == RED_SEQ ? 1 : (RED == RED_NORM2 ? 8 : 32);
+  constexpr int PER_WARP = 32 / LANES;
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long base = warp_global * PER_WARP;
+  if (base >= n) return;
+  const long long i = base + lane / LANES;
+  const bool valid = i < n;
+  const long long ii = valid ? i : base;     // idle groups redo the first query (shuffles stay uniform)
+  const float* q0 = qplain + (size_t)ii * QW * dim;
   const float* q1 = q0 + (size_t)(QW - 1) * dim;
-  const float* c0 = rows + (size_t)i * CW * dim;
+  const float* c0 = rows + (size_t)ii * CW * dim;
   const float* c1 = c0 + (size_t)(CW - 1) * dim;
-  s_true[i] = pair_score<EL, CASC>(dim, q0, q1, c0, c1, perm, code);
+  float s;
+  if constexpr (RED == RED_SEQ) {
+    s = pair_score<EL, CASC>(dim, q0, q1, c0, c1, perm, code);
+  } else {
+    if (RED == RED_SUM && dim < 8) s = pair_score_natural<EL>(dim, q0, q1, c0, c1);
+    else s = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane);
+  }
+  if (valid && (lane % LANES) == 0) s_true[i] = s;
 }
 
 // Filter pass.  For every CSR entry c of query i held by this shard:
@@ -407,8 +425,9 @@ cudaError_t launch_true_scores(int el, bool cascade, int dim, int64_t n, const f
                                const float* rows, const int32_t* perm, const uint8_t* code,
                                float* s_true, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-#define CALL_TRUE(EL, C) \
-  true_scores_kernel<EL, C><<<blocks_for(n, 128), 128, 0, stream>>>(dim, n, qplain, rows, perm, code, s_true)
+#define CALL_TRUE(EL, C)                                                                                   \
+  true_scores_kernel<EL, C><<<blocks_for(n * (ElemTraits<EL>::RED == RED_SEQ ? 1 : (ElemTraits<EL>::RED == RED_NORM2 ? 8 : 32)), 128), \
+                              128, 0, stream>>>(dim, n, qplain, rows, perm, code, s_true)
   KGE_DISPATCH_EL(el, cascade, CALL_TRUE)
 #undef CALL_TRUE
   return cudaGetLastError();

@@ -331,14 +331,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_scan_kernel(const __grid_consta
       // largest candidate norm bound of each of this warp's four 32-column blocks (one coalesced
       // load + one redux each, issued before waiting for the accumulator)
       const int c_begin = col_half * (BN / 2);
+      // (maxima over aligned blocks of 32 rows, precomputed with the image: two broadcast loads per block)
       float cbm[4], cpm[4];
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        const long long c = ct * BN + c_begin + 32 * b + lane;
-        const float x = c < p.n_rows ? p.cbound[c] : 0.f;
-        const float y = c < p.n_rows ? p.cprefix[c] : 0.f;
-        cbm[b] = __fadd_ru(__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(x))), kappa_b);  // x >= 0
-        cpm[b] = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(y)));
+        const long long blk = (ct * BN + c_begin) / 32 + b;
+        cbm[b] = __fadd_ru(__ldg(p.cbmax32 + blk), kappa_b);
+        cpm[b] = __ldg(p.cpmax32 + blk);
       }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       fence_after();
@@ -650,6 +649,22 @@ __global__ void row_norms_kernel(const float* __restrict__ src0, const float* __
 //         alpha (query side) = scale_a * scale_b / phi must itself be an fp16 normal power of two.
 //   An operand with a NaN / inf entry, or whose alpha falls outside fp16, gets scale = NaN: its image,
 //   S and hence both thresholds are NaN, every pair fails both tests and is rechecked exactly.
+// maxima of the row bounds / running-magnitude factors over aligned blocks of 32 rows (rows past the
+// table count as 0): one warp per block
+__global__ void block_max_kernel(const float* __restrict__ bound, const float* __restrict__ prefix, long long n_rows,
+                                 long long n_blocks, float* __restrict__ bmax, float* __restrict__ pmax,
+                                 const unsigned long long* __restrict__ guard) {
+  if (guard_unchanged(guard)) return;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_blocks) return;
+  const long long r = w * 32 + lane;
+  const float x = r < n_rows ? bound[r] : 0.f, y = r < n_rows ? prefix[r] : 0.f;
+  const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(x));   // x, y >= 0 (NaN sorts on top)
+  const unsigned my = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
+  if (lane == 0) { bmax[w] = __uint_as_float(mx); pmax[w] = __uint_as_float(my); }
+}
+
 __global__ void tc_meta_reset_kernel(TcMeta* __restrict__ m, const unsigned long long* __restrict__ guard) {
   if (guard_unchanged(guard)) return;
   if (threadIdx.x == 0) { m->max_abs = 0.f; m->max_norm2 = 0.f; }
@@ -660,22 +675,41 @@ __global__ void tc_guard_commit_kernel(unsigned long long* __restrict__ guard) {
   if (threadIdx.x == 0) { guard[2] = guard[0]; guard[3] = guard[1]; }
 }
 
-// 128-bit content checksum of a table: order-independent sums of position-keyed 64-bit mixes of
-// every 32-bit word (a changed word changes both sums unless 2^-128-improbable cancellations occur)
-__global__ void table_checksum_kernel(const uint32_t* __restrict__ words, long long n_words,
-                                      unsigned long long salt, unsigned long long* __restrict__ out) {
+// 128-bit content checksum of a table: two order-independent sums over its 64-bit words w_i,
+//   h0 = sum w_i (2 i + 1),   h1 = sum (w_i ^ (w_i >> 31) ^ salt) (2 i + 1)        (mod 2^64)
+// The odd, position-dependent multipliers make any single changed word change both sums, and several
+// changed words cancel only by a 2^-64 coincidence per sum.  One pass at HBM speed: 16-byte loads,
+// four in flight per thread.
+__global__ void __launch_bounds__(256) table_checksum_kernel(const uint4* __restrict__ data, long long n_vec,
+                                                             const uint32_t* __restrict__ tail_words,
+                                                             int n_tail, unsigned long long salt,
+                                                             unsigned long long* __restrict__ out) {
   unsigned long long h0 = 0ull, h1 = 0ull;
+  auto add = [&](unsigned long long w, unsigned long long i) {
+    const unsigned long long m = 2ull * i + 1ull;
+    h0 += w * m;
+    h1 += (w ^ (w >> 31) ^ salt) * m;
+  };
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
-    const unsigned long long w = words[i];
-    const unsigned long long pos = (unsigned long long)i + salt;
-    unsigned long long x = (w + 0x9E3779B97F4A7C15ull * (pos + 1ull));
-    x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
-    h0 += x;
-    unsigned long long y = (w ^ 0xD6E8FEB86659FD93ull) * (2ull * pos + 1ull);
-    y ^= y >> 31; y *= 0x94D049BB133111EBull; y ^= y >> 29;
-    h1 += y;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n_vec; i += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(data + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned long long j = 2ull * (unsigned long long)(i + u * stride);
+      add(((unsigned long long)v[u].y << 32) | v[u].x, j);
+      add(((unsigned long long)v[u].w << 32) | v[u].z, j + 1ull);
+    }
   }
+  for (; i < n_vec; i += stride) {
+    const uint4 v = __ldg(data + i);
+    add(((unsigned long long)v.y << 32) | v.x, 2ull * (unsigned long long)i);
+    add(((unsigned long long)v.w << 32) | v.z, 2ull * (unsigned long long)i + 1ull);
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < n_tail)   // words past the last full 16-byte vector
+    add(tail_words[threadIdx.x], 2ull * (unsigned long long)n_vec + threadIdx.x);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     h0 += __shfl_xor_sync(0xffffffffu, h0, o);
@@ -827,6 +861,14 @@ int ct_group(int n_kb) {
   if (config().group > 0) return config().group;
   return resident(n_kb) ? 32 : 16;
 }
+// With few query tiles (a rank's slice of a query-sharded run) whole groups of 32 candidate tiles
+// are too coarse a unit for 148 CTAs: shrink the group until there are >= 32 units per CTA.
+int ct_group_for(int n_kb, long long n_qt, long long n_ct, int sms) {
+  int g = ct_group(n_kb);
+  if (config().group > 0) return g;
+  while (g > 4 && n_qt * ((n_ct + g - 1) / g) < 32ll * sms) g >>= 1;
+  return g;
+}
 
 size_t a_image_bytes(long long n_q, int n_kb) {
   const long long n_qt = (n_q + BM - 1) / BM;
@@ -859,7 +901,7 @@ uint32_t instruction_descriptor() { return fp16() ? IDESC_FP16 : IDESC_BF16; }
 
 cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows, int dim, int k_total,
                           int n_kb, bool fold, unsigned char* bpack, float* cbound, float* cnorm2, float* cprefix,
-                          TcMeta* meta_b, unsigned long long* guard, cudaStream_t st) {
+                          float* cbmax32, float* cpmax32, TcMeta* meta_b, unsigned long long* guard, cudaStream_t st) {
   if (n_rows <= 0) return cudaSuccess;
   if (guard) {
     // checksum of the table as it is now (one pass over it at HBM speed); if it equals the one the
@@ -867,11 +909,21 @@ cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows
     cudaError_t e = cudaMemsetAsync(guard, 0, 2 * sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     const long long n_words = n_rows * dim;
-    const unsigned blocks = (unsigned)min((n_words + 1023) / 1024, (long long)148 * 16);
-    table_checksum_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(ent0), n_words, 0ull, guard);
-    if (ent1)
-      table_checksum_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(ent1), n_words,
-                                                    0x5851F42D4C957F2Dull, guard);
+    auto checksum = [&](const float* tab, unsigned long long salt) {
+      // 16-byte vector loads over the aligned middle of the table; the <= 3 words before it and the
+      // <= 3 words after it go through the kernel's tail path (positions past the vector part)
+      const uint32_t* words = reinterpret_cast<const uint32_t*>(tab);
+      const long long head = min(n_words, (long long)(((16u - (reinterpret_cast<uintptr_t>(tab) & 15u)) & 15u) / 4u));
+      const long long n_vec = (n_words - head) / 4;
+      const int n_tail = (int)(n_words - head - 4 * n_vec);
+      const unsigned blocks = (unsigned)max(1ll, min((n_vec + 1023) / 1024, (long long)148 * 8));
+      table_checksum_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(words + head), n_vec,
+                                                    words + head + 4 * n_vec, n_tail, salt, guard);
+      if (head > 0)
+        table_checksum_kernel<<<1, 32, 0, st>>>(nullptr, 0, words, (int)head, salt ^ 0xA5A5A5A5A5A5A5A5ull, guard);
+    };
+    checksum(ent0, 0ull);
+    if (ent1) checksum(ent1, 0x5851F42D4C957F2Dull);
     table_checksum_finish_kernel<<<1, 32, 0, st>>>(guard);
   }
   tc_meta_reset_kernel<<<1, 32, 0, st>>>(meta_b, guard);
@@ -879,6 +931,11 @@ cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows
   row_norms_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, st>>>(
       ent0, ent1, dim, 0, n_rows, dim, fold ? dim : k_total, fold ? (k_total + 15) / 16 - (dim + 15) / 16 : 0, 0,
       cbound, cnorm2, cprefix, meta_b, guard);
+  {
+    const long long n_blocks = ((n_rows + BN - 1) / BN) * (BN / 32);
+    block_max_kernel<<<(unsigned)((n_blocks * 32 + 255) / 256), 256, 0, st>>>(cbound, cprefix, n_rows, n_blocks, cbmax32,
+                                                                              cpmax32, guard);
+  }
   tc_meta_kernel<<<1, 32, 0, st>>>(meta_b, nullptr, k_total, 0, fold ? 1 : 0, fp16() ? 1 : 0, guard);
   launch_pack_operand<BN>(ent0, ent1, dim, 0, n_rows, dim, k_total, n_kb, 0, fold ? 2 : 0, cnorm2, meta_b, guard,
                           bpack, st);
@@ -934,9 +991,8 @@ cudaError_t launch_variant(const TcScanParams& p, int grid, cudaStream_t st) {
 
 cudaError_t launch_tc_scan(const TcScanParams& p_in, cudaStream_t st) {
   TcScanParams p = p_in;
-  p.ct_group = ct_group(p.n_kb);
   p.idesc = instruction_descriptor();
-  const int grid = scan_grid_size(p.n_q, p.n_rows, p.n_kb);
+  const int grid = scan_grid_size(p.n_q, p.n_rows, p.n_kb, &p.ct_group);
   if (grid <= 0) return cudaSuccess;
   if (bk() == 64) return launch_variant<64, false>(p, grid, st);
   if (resident(p.n_kb)) return launch_variant<32, true>(p, grid, st);
@@ -964,14 +1020,15 @@ cudaError_t launch_recheck(int el, int dim, const unsigned long long* region_cou
   return cudaGetLastError();
 }
 
-int scan_grid_size(long long n_q, long long n_rows, int n_kb) {
+int scan_grid_size(long long n_q, long long n_rows, int n_kb, int* group_out) {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   const long long n_qt = (n_q + BM - 1) / BM, n_ct = (n_rows + BN - 1) / BN;
-  const long long g = ct_group(n_kb);
-  const long long units = n_qt * ((n_ct + g - 1) / g);
   if (config().max_ctas > 0 && config().max_ctas < sms) sms = config().max_ctas;
+  const long long g = ct_group_for(n_kb, n_qt, n_ct, sms);
+  if (group_out) *group_out = (int)g;
+  const long long units = n_qt * ((n_ct + g - 1) / g);
   return (int)(units < sms ? units : sms);
 }
 

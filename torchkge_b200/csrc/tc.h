@@ -47,6 +47,8 @@ struct TcScanParams {
   const float* cnorm2;         // [n_rows]
   const float* qprefix;        // [n_q]    P(a) = sqrt(sum_i |a_{<=16 i}|^2): running-magnitude factor (tc_gamma_p)
   const float* cprefix;        // [n_rows] P(b)
+  const float* cbmax32;        // [n_ct * 8] max of cbound over each aligned block of 32 rows
+  const float* cpmax32;        // [n_ct * 8] max of cprefix over each aligned block of 32 rows
   int32_t* counts;             // [n_q] +=
   unsigned long long* amb_count;  // [n_qt] fill count of each query tile's region
   int2* amb_pairs;                // [n_qt][amb_cap]
@@ -128,7 +130,7 @@ size_t b_image_bytes(long long n_rows, int n_kb);
 // if it differs from the checksum the image was built from -- a cache that cannot go stale.
 cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows, int dim, int k_total,
                           int n_kb, bool fold, unsigned char* bpack, float* cbound, float* cnorm2, float* cprefix,
-                          TcMeta* meta_b, unsigned long long* guard, cudaStream_t st);
+                          float* cbmax32, float* cpmax32, TcMeta* meta_b, unsigned long long* guard, cudaStream_t st);
 cudaError_t launch_pack_a(const float* qplain, int qw, long long n_q, int dim, int k_total, int n_kb,
                           int sub_mode, bool fold, unsigned char* apack, float* qbound, float* qnorm2, float* qprefix,
                           TcMeta* meta_a, const TcMeta* meta_b, cudaStream_t st);
@@ -137,7 +139,7 @@ cudaError_t launch_tc_scan(const TcScanParams& p, cudaStream_t st);
 // The near-tie list is split into one region per QUERY TILE (regions = n_qt): region_counts[regions]
 // (zeroed by the caller), pairs[regions][region_cap].  A region's pairs all belong to the same 128
 // queries, whose rows therefore stay L1-resident during the exact recheck of that region.
-int scan_grid_size(long long n_q, long long n_rows, int n_kb);
+int scan_grid_size(long long n_q, long long n_rows, int n_kb, int* group_out = nullptr);
 cudaError_t launch_recheck(int el, int dim, const unsigned long long* region_counts, int regions,
                            unsigned long long region_cap, const int2* pairs, const float* qplain,
                            const float* ent0, const float* ent1, const float* s_true, int32_t* counts,
