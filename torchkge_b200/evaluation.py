@@ -12,6 +12,14 @@ from .engine import (DEFAULT_CHUNK, ModelSpec, QueryShard, default_engine, rank_
 from .exceptions import NotYetEvaluatedError
 
 
+def _check_index_range(heads, tails, rels, n_ent, n_rel):
+    """nn.Embedding raises on an out-of-range index; the kernels would read out of bounds.  The index
+    tensors of a graph live on the host, so the check is a few microseconds there."""
+    for name, x, hi in (("head", heads, n_ent), ("tail", tails, n_ent), ("relation", rels, n_rel)):
+        if x.numel() and not x.is_cuda and (int(x.min()) < 0 or int(x.max()) >= hi):
+            raise IndexError("%s index out of range [0, %d)" % (name, hi))
+
+
 class LinkPredictionEvaluator(object):
     """Evaluate an embedding model by link prediction (Bordes et al. 2013).
 
@@ -73,6 +81,7 @@ class LinkPredictionEvaluator(object):
         if qshard is not None:      # this rank's contiguous slice of the facts
             heads, tails, rels = (x[qshard.lo:qshard.hi] for x in (heads, tails, rels))
         n_here = int(heads.shape[0])
+        _check_index_range(heads, tails, rels, spec.n_ent, spec.n_rel)
         h_d = heads.to(dev, non_blocking=True)
         t_d = tails.to(dev, non_blocking=True)
         r_d = rels.to(dev, non_blocking=True)
@@ -209,6 +218,7 @@ class RelationPredictionEvaluator(object):
                 "(model.cuda()); this package has no CPU execution path")
         dev = spec.ent0.device
         kg = self.kg
+        _check_index_range(kg.head_idx, kg.tail_idx, kg.relations, spec.n_ent, spec.n_rel)
         h_d, t_d, r_d = (x.to(dev, non_blocking=True) for x in (kg.head_idx, kg.tail_idx, kg.relations))
         csr = filter_csr(kg.dict_of_rels, kg.head_idx, kg.tail_idx, kg.relations)
         csr = tuple(x.to(dev, non_blocking=True) for x in csr)
