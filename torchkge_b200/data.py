@@ -241,7 +241,7 @@ def dict_filter_csr(kg, which, key1, key2, true_idx, device):
     dictionary = kg.dict_of_tails if which == "tail" else kg.dict_of_heads
     cache = kg.__dict__.setdefault("_b200_filter_cache", {})
     key = (which, str(device), id(dictionary), len(dictionary), key1.data_ptr(), key2.data_ptr(),
-           true_idx.data_ptr(), int(key1.shape[0]))
+           true_idx.data_ptr(), int(key1.shape[0]), int(key1.sum()), int(key2.sum()), int(true_idx.sum()))
     hit = cache.get(key)
     if hit is not None:
         return hit

@@ -94,8 +94,24 @@ class LinkPredictionEvaluator(object):
             # sorted-array filters (torchkge_b200.data.KnowledgeGraph): the index is resident on
             # the device (uploaded at first use, like weights); the per-row lists of this test set
             # come from searchsorted + gather on the device
-            csr_tail = lambda: index.csr("tail", h_d, r_d, t_d)   # noqa: E731
-            csr_head = lambda: index.csr("head", t_d, r_d, h_d)   # noqa: E731
+            # ... once per (graph, test slice, device): the lists depend only on the graph, so they are
+            # kept on the graph object like the index itself (keyed on the host index tensors)
+            def from_index(which, k1, k2, true, k1_d, k2_d, true_d):
+                def build():
+                    cache = kg.__dict__.setdefault("_b200_filter_cache", {})
+                    # identity of the host tensors + a cheap content fingerprint (in-place edits of a
+                    # test set are unusual, but must not be served stale lists)
+                    key = (which, str(dev), id(index), k1.data_ptr(), k2.data_ptr(), true.data_ptr(), n_here,
+                           int(k1.sum()), int(k2.sum()), int(true.sum()))
+                    hit = cache.get(key)
+                    if hit is None:
+                        while len(cache) >= 4:
+                            cache.pop(next(iter(cache)))
+                        hit = cache[key] = index.csr(which, k1_d, k2_d, true_d)
+                    return hit
+                return build
+            csr_tail = from_index("tail", heads, rels, tails, h_d, r_d, t_d)
+            csr_head = from_index("head", tails, rels, heads, t_d, r_d, h_d)
         else:
             # the reference's dictionaries (torchkge.data_structures.KnowledgeGraph): distinct
             # keys flattened once on the host, expanded on the device, cached on the graph
