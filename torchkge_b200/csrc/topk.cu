@@ -77,6 +77,29 @@ __global__ void __launch_bounds__(MERGE_THREADS)
   const long long m_lo = mask_offs ? mask_offs[q] : 0, m_hi = mask_offs ? mask_offs[q + 1] : 0;
   const int fresh = SORT_N - k;     // new entries taken per pass
   if (cnt == 0) return;             // nothing collected: list and threshold stay as they are
+  if (k <= 32 && cnt <= 128) {
+    // the usual case after the first chunk: a handful of new candidates against a short list --
+    // one warp keeps the list in registers (one key per lane, descending) and inserts one at a time
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    unsigned long long mykey = lane < k ? mine[lane] : 0ull;
+    for (unsigned long long e = 0; e < cnt; ++e) {
+      const int2 v = list[e];
+      float s = __int_as_float(v.x);
+      if (m_hi > m_lo && masked(mask_ids, m_lo, m_hi, (long long)v.y)) s = -INFINITY;
+      const unsigned long long key = make_key(s, v.y);
+      const unsigned ahead = __ballot_sync(0xffffffffu, lane < k && mykey > key);
+      const int pos = __popc(ahead);                    // keys ahead of the new one keep their place
+      if (pos >= k) continue;
+      const unsigned long long up = __shfl_up_sync(0xffffffffu, mykey, 1);
+      if (lane > pos) mykey = up;                       // everything behind moves down one slot
+      if (lane == pos) mykey = key;
+    }
+    if (lane < k) mine[lane] = mykey;
+    const unsigned long long kth = __shfl_sync(0xffffffffu, mykey, k - 1);
+    if (lane == 0) thr[q] = kth == 0ull ? -INFINITY : key_score((unsigned)(kth >> 32));
+    return;
+  }
   for (unsigned long long t0 = 0; t0 < cnt; t0 += fresh) {
     for (int i = threadIdx.x; i < SORT_N; i += MERGE_THREADS) {
       unsigned long long key = 0ull;
