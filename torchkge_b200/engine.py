@@ -472,6 +472,10 @@ class LazyRanks:
         if self.overflow is not None:
             flag = int(self.overflow.item()) if flag_host is None else int(flag_host)
             if flag > 0:
+                import warnings
+                warnings.warn("torchkge_b200: the near-tie list of %d bound-and-refine call(s) overflowed "
+                              "(adversarial or degenerate embeddings?); recomputing the ranks on the exact "
+                              "scalar scan" % flag, RuntimeWarning)
                 self.ranks, self.overflow = self._redo(), None
         return self.ranks
 
@@ -509,6 +513,11 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
         # RotatE has no tensor-core form; its bound-and-refine runs on the fp32 pipes (KGE_FLAG_APPROX_SCAN)
         refine = (not exact and tc_packed is None and spec.code == _lib.ROTATE
                   and getattr(engine, "tensor_core", False))
+        if tc_packed is not None or refine:
+            # the near-tie list of one call holds n * n_rows / 128 pairs at most 2^28 (2 GB): keep the
+            # facts per call small enough for tables of many millions of rows, so that running out of
+            # room stays the exception it is meant to be
+            chunk = min(chunk, max(1024, ((1 << 35) // max(spec.n_rows, 1)) // 128 * 128))
         # counters raw_t, sub_t, raw_h, sub_h and, behind them, one slot for the overflow flag so
         # that a sharded run needs a single all-reduce
         buf = torch.zeros(4 * n + 1, dtype=torch.int32, device=dev)
@@ -546,9 +555,22 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
         for k in (0, 1):
             if callable(filts[k]):
                 filts[k] = filts[k]()
+        # chunk boundaries of the CSRs: one device -> host read for all of them (none for a single chunk)
+        cuts = [None, None]
+        if n > chunk:
+            starts = torch.tensor(list(range(0, n, chunk)) + [n], device=dev)
+            for k in (0, 1):
+                if filts[k] is not None:
+                    cuts[k] = dict(zip(starts.tolist(), filts[k][0][starts].tolist()))
         for handle, which, lo, hi, sub in pending:
             if filts[which] is not None:
-                engine.filter_side(handle, _csr_slice(filts[which], lo, hi, n), sub[lo:hi])
+                offs, ids = filts[which][0], filts[which][1]
+                if cuts[which] is None:
+                    part = (offs, ids)
+                else:
+                    a, b = cuts[which][lo], cuts[which][hi]
+                    part = ((offs[lo:hi + 1] - a).contiguous(), ids[a:b].contiguous())
+                engine.filter_side(handle, part, sub[lo:hi])
         mark("filters enqueued")
         del pending
         overflow = None
