@@ -21,6 +21,8 @@ WORKLOADS = {
     "c2": dict(model="TransE", diss="L2", dim=200, n_ent=1000000, n_rel=1000, n_facts=21000000, n_test=20466),
     "c3": dict(model="ComplEx", diss=None, dim=400, n_ent=1000000, n_rel=1000, n_facts=21000000, n_test=20466),
     "c4": dict(model="RotatE", diss=None, dim=1000, n_ent=5000000, n_rel=1000, n_facts=21000000, n_test=20466),
+    # C4's model at a tenth of its table: small enough for the CPU oracle to score in one piece (parity sample)
+    "c4s": dict(model="RotatE", diss=None, dim=1000, n_ent=500000, n_rel=1000, n_facts=10500000, n_test=20466),
     "tiny": dict(model="TransE", diss="L2", dim=32, n_ent=2000, n_rel=20, n_facts=30000, n_test=512),
 }
 
