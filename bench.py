@@ -67,7 +67,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--cpu-sample", type=int, default=0,
-                    help="test triples in the CPU-baseline sample (0: 32 at |E| >= 100k, 4 for c4, else 2048)")
+                    help="test triples in the CPU-baseline sample (0: 32 at |E| >= 100k, 1 for c4, else 2048)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the sub-records (second decomposition, reference-KG API, c5 training step)")
@@ -350,6 +350,8 @@ def oracle_ranks_sharded(kind, code, wl, seed, th, tt, tr, dh, dt, dev, n_shards
         lo, hi = min(n_ent, s * per), min(n_ent, (s + 1) * per)
         if hi <= lo:
             continue
+        print("cpu oracle: entity rows [%d, %d) (%d of %d), %.0f s of scoring so far" % (lo, hi, s + 1, n_shards, cpu_s),
+              file=sys.stderr, flush=True)
         tabs = S.make_tables(code, dim, n_ent, n_rel, lo, hi, seed, dev)
         tabs = {k: (v.cpu() if v is not None else None) for k, v in tabs.items()}
         rows = hi - lo
@@ -748,7 +750,7 @@ def run_ours(args, rank, local, world):
         torch.set_num_threads(cores)
         big = n_ent >= 100000
         sharded = table_bytes(wl) > 8e9
-        ns = args.cpu_sample or ((4 if sharded else 32) if big else 2048)
+        ns = args.cpu_sample or ((1 if sharded else 32) if big else 2048)   # a 40 GB table costs minutes per triple
         ns = min(n_test, ns)
         th, tt, tr = (graph[k][:ns].cpu() for k in ("test_h", "test_t", "test_r"))
         dh, dt = S.filters_as_dicts(graph, n_ent, n_rel, limit=ns)  # reference-style dicts, sample keys
