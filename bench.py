@@ -227,8 +227,8 @@ def parallelism_text(mode, world):
     return {"single": "single GPU",
             "queries": "test triples sharded x%d, table replicated, no data-path collective "
                        "(rank vectors all-gathered inside the timed region)" % world,
-            "entities": "entity-range shards x%d, query rows exchanged by all-reduce, 1 all-reduce of the "
-                        "rank counters (inside the timed region)" % world}[mode]
+            "entities": "entity table range-partitioned x%d (each rank holds and scans only its rows), query rows "
+                        "exchanged by all-reduce, 1 all-reduce of the rank counters (inside the timed region)" % world}[mode]
 
 
 def workload_config(name, wl, world, mode="single", n_test=None):
@@ -549,8 +549,10 @@ def run_ours(args, rank, local, world):
     def measure(mode, clocks):
         """One decomposition: device-resident timing, end-to-end timing, full-test-set parity of the
         timed path against the exact scalar scan."""
-        local_storage = (mode == "entities" and not fits)
-        shard = EntityShard(n_ent, rank, world, None, local_storage=local_storage) if mode == "entities" else None
+        # entity decomposition: every rank generates and HOLDS only its range of rows (the table is
+        # range-partitioned for real, also when it would fit one GPU)
+        local_storage = mode == "entities"
+        shard = EntityShard(n_ent, rank, world, None, local_storage=True) if mode == "entities" else None
         if local_storage:
             lo, hi = shard.lo, shard.hi
             tabs = S.make_tables(code, dim, n_ent, n_rel, lo, hi, args.seed, dev)
@@ -761,6 +763,8 @@ def run_ours(args, rank, local, world):
                                   "seeds (40 GB table); time = scoring + counting only")
         else:
             full = main_tabs if main_tabs["ent0"].shape[0] == n_ent else full_tabs
+            if not full:
+                full = S.make_tables(code, dim, n_ent, n_rel, 0, n_ent, args.seed, dev)
             P = oracle_params_from_tables(kind, {k: (v.cpu() if v is not None else None) for k, v in full.items()})
             refimpl = CpuReference(kind, wl, P)
             t0 = time.perf_counter()
