@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 6
+#define KGE_ABI_VERSION 7
 
 /* error codes */
 #define KGE_OK 0
@@ -216,6 +216,8 @@ typedef struct {
   const float* true_score_in; /* [n] or NULL: use these true scores instead of scoring true_rows
                                (undirected relation prediction ranks the swapped (t, ?, h) scores
                                against the directed true score, evaluation.py:99-107) */
+  const int32_t* filt_qid;  /* [n_filt] or NULL: the triple (row of the CSR) every filter entry belongs to;
+                               saves the filter pass a binary search in filt_offs per entry */
 } kge_rank_args_t;
 
 #define KGE_FLAG_TENSOR_CORE 1 /* use the tensor-core bound-and-refine scan when the model has one */

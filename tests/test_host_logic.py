@@ -124,8 +124,9 @@ def test_filter_index_equals_dictionary_semantics():
     qr = torch.cat([r[:300], torch.randint(0, 6, (150,), generator=g)])
     for which, d, k1, k2, tr in (("tail", dt, qh, qr, qt), ("head", dh, qt, qr, qh)):
         o1, i1 = filter_csr(d, k1, k2, tr)
-        o2, i2 = idx.csr(which, k1, k2, tr)
+        o2, i2, q2 = idx.csr(which, k1, k2, tr)
         assert torch.equal(o1, o2)
+        assert torch.equal(q2.long(), torch.repeat_interleave(torch.arange(450), o2[1:] - o2[:-1]))
         for q in range(450):
             assert sorted(i1[o1[q]:o1[q + 1]].tolist()) == sorted(i2[o2[q]:o2[q + 1]].tolist())
     kg = tk.KnowledgeGraph(h[:40], t[:40], r[:40], 300, 6, filter_facts=(h, t, r))
@@ -225,13 +226,14 @@ def test_dict_filter_csr_equals_filter_csr_and_caches():
     kg = tk.KnowledgeGraph(qh, qt, qr, 200, 5, dict_of_heads=dh, dict_of_tails=dt)
     for which, d, k1, k2, tr in (("tail", dt, qh, qr, qt), ("head", dh, qt, qr, qh)):
         o1, i1 = filter_csr(d, k1, k2, tr)
-        o2, i2, nbytes = dict_filter_csr(kg, which, k1, k2, tr, torch.device("cpu"))
+        (o2, i2, q2), nbytes = dict_filter_csr(kg, which, k1, k2, tr, torch.device("cpu"))
         assert torch.equal(o1, o2) and nbytes > 0
+        assert torch.equal(q2.long(), torch.repeat_interleave(torch.arange(k1.shape[0]), o2[1:] - o2[:-1]))
         for q in range(k1.shape[0]):
             assert sorted(i1[o1[q]:o1[q + 1]].tolist()) == sorted(i2[o2[q]:o2[q + 1]].tolist())
         again = dict_filter_csr(kg, which, k1, k2, tr, torch.device("cpu"))
-        assert again[0] is o2 and again[1] is i2          # served from the cache on the graph
+        assert again[0][0] is o2 and again[0][1] is i2    # served from the cache on the graph
     # editing a dictionary (its size changes) invalidates the cached rows
     dt[(999, 0)] = {1, 2}
-    o3, i3, _ = dict_filter_csr(kg, "tail", qh, qr, qt, torch.device("cpu"))
+    (o3, i3, _), _ = dict_filter_csr(kg, "tail", qh, qr, qt, torch.device("cpu"))
     assert torch.equal(o3, filter_csr(dt, qh, qr, qt)[0])

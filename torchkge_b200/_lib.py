@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libkge_b200.so")
 TRANSE_L1, TRANSE_L2, DISTMULT, RESCAL, COMPLEX, ROTATE, TORUSE_L1, TORUSE_L2 = range(8)
 SIDE_TAIL, SIDE_HEAD, SIDE_REL = 0, 1, 2
 TILE_C, TILE_Q = 128, 64
-ABI_VERSION = 6
+ABI_VERSION = 7
 FLAG_TENSOR_CORE = 1
 FLAG_APPROX_SCAN = 2
 LOSS_LOGISTIC, LOSS_BCE = 1, 2
@@ -44,7 +44,7 @@ class RankArgs(ctypes.Structure):
         ("raw_count", _p), ("filt_sub", _p), ("true_score", _p),
         ("workspace", _p), ("workspace_bytes", _c.c_size_t), ("stream", _p),
         ("tc_packed", _p), ("tc_stats", _p), ("tc_dump", _p),
-        ("true_rows", _p), ("true_score_in", _p),
+        ("true_rows", _p), ("true_score_in", _p), ("filt_qid", _p),
     ]
 
 

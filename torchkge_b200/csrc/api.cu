@@ -458,7 +458,7 @@ int kge_rank_side(const kge_rank_args_t* a) {
                  "tc recheck");
     if (a->filt_offs && a->n_filt > 0)
       KGE_CUDA_TRY(kge::launch_filter(el, casc, a->dim, a->n, a->n_filt, w.qplain, a->ent0, a->ent1,
-                                      a->ent_lo, a->n_rows, a->filt_offs, a->filt_ids, w.perm,
+                                      a->ent_lo, a->n_rows, a->filt_offs, a->filt_ids, a->filt_qid, w.perm,
                                       w.code, w.s_true, a->filt_sub, st),
                    "filter pass");
   } else if (a->n_rows > 0) {
@@ -501,7 +501,7 @@ int kge_rank_side(const kge_rank_args_t* a) {
 
     if (a->filt_offs && a->n_filt > 0)
       KGE_CUDA_TRY(kge::launch_filter(el, casc, a->dim, a->n, a->n_filt, w.qplain, a->ent0, a->ent1,
-                                      a->ent_lo, a->n_rows, a->filt_offs, a->filt_ids, w.perm,
+                                      a->ent_lo, a->n_rows, a->filt_offs, a->filt_ids, a->filt_qid, w.perm,
                                       w.code, w.s_true, a->filt_sub, st),
                    "filter pass");
   }
@@ -522,7 +522,7 @@ int kge_filter_side(const kge_rank_args_t* a) {
   Workspace w = carve(a->workspace, kge::elem_qw(el), a->dim, a->n);  // leading part only
   if (w.bytes > a->workspace_bytes) return fail(KGE_ERR_ARG, "kge_filter_side: workspace too small");
   KGE_CUDA_TRY(kge::launch_filter(el, hs->s.has_cascade, a->dim, a->n, a->n_filt, w.qplain, a->ent0,
-                                  a->ent1, a->ent_lo, a->n_rows, a->filt_offs, a->filt_ids, w.perm,
+                                  a->ent1, a->ent_lo, a->n_rows, a->filt_offs, a->filt_ids, a->filt_qid, w.perm,
                                   w.code, w.s_true, a->filt_sub, static_cast<cudaStream_t>(a->stream)),
                "filter pass");
   return KGE_OK;

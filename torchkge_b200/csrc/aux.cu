@@ -288,7 +288,8 @@ __global__ void filter_kernel(int dim, long long n, long long n_filt,
                               const float* __restrict__ qplain, const float* __restrict__ ent0,
                               const float* __restrict__ ent1, long long ent_lo,
                               long long n_rows, const int64_t* __restrict__ offs,
-                              const int64_t* __restrict__ ids, const int32_t* __restrict__ perm,
+                              const int64_t* __restrict__ ids, const int32_t* __restrict__ qid,
+                              const int32_t* __restrict__ perm,
                               const uint8_t* __restrict__ code, const float* __restrict__ s_true,
                               int32_t* __restrict__ filt_sub) {
   constexpr int QW = ElemTraits<EL>::QW, CW = ElemTraits<EL>::CW;
@@ -306,11 +307,15 @@ __global__ void filter_kernel(int dim, long long n, long long n_filt,
     const long long row = ids[ee] - ent_lo;
     const bool held = in_range && row >= 0 && row < n_rows;
     const long long rr = held ? row : 0;
-    // query owning CSR entry ee: largest i with offs[i] <= ee
+    // query owning CSR entry ee: given, or the largest i with offs[i] <= ee
     long long lo = 0, hi = n;
-    while (hi - lo > 1) {
-      const long long mid = (lo + hi) >> 1;
-      if (offs[mid] <= ee) lo = mid; else hi = mid;
+    if (qid != nullptr) {
+      lo = qid[ee];
+    } else {
+      while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (offs[mid] <= ee) lo = mid; else hi = mid;
+      }
     }
     const long long i = lo;
     const float* q0 = qplain + (size_t)i * QW * dim;
@@ -436,12 +441,12 @@ cudaError_t launch_true_scores(int el, bool cascade, int dim, int64_t n, const f
 cudaError_t launch_filter(int el, bool cascade, int dim, int64_t n, int64_t n_filt,
                           const float* qplain, const float* ent0, const float* ent1,
                           int64_t ent_lo, int64_t n_rows, const int64_t* offs,
-                          const int64_t* ids, const int32_t* perm, const uint8_t* code,
+                          const int64_t* ids, const int32_t* qid, const int32_t* perm, const uint8_t* code,
                           const float* s_true, int32_t* filt_sub, cudaStream_t stream) {
   if (n <= 0 || n_filt <= 0) return cudaSuccess;
 #define CALL_FILT(EL, C)                                                                   \
   filter_kernel<EL, C><<<filter_blocks(n_filt), 128, 0, stream>>>(                         \
-      dim, n, n_filt, qplain, ent0, ent1, ent_lo, n_rows, offs, ids, perm, code, s_true,   \
+      dim, n, n_filt, qplain, ent0, ent1, ent_lo, n_rows, offs, ids, qid, perm, code, s_true,   \
       filt_sub)
   KGE_DISPATCH_EL(el, cascade, CALL_FILT)
 #undef CALL_FILT

@@ -87,7 +87,7 @@ cudaError_t launch_true_scores(int el, bool cascade, int dim, int64_t n, const f
 cudaError_t launch_filter(int el, bool cascade, int dim, int64_t n, int64_t n_filt,
                           const float* qplain,
                           const float* ent0, const float* ent1, int64_t ent_lo, int64_t n_rows,
-                          const int64_t* offs, const int64_t* ids, const int32_t* perm,
+                          const int64_t* offs, const int64_t* ids, const int32_t* qid, const int32_t* perm,
                           const uint8_t* code, const float* s_true, int32_t* filt_sub,
                           cudaStream_t stream);
 

@@ -73,8 +73,9 @@ class FilterIndex:
         start = torch.cumsum(full, 0) - full
         pos = torch.arange(row.numel(), device=dev) - start[row] + lo[row]
         ids = kv[pos] - kq[row]
-        ids = ids[ids != true_idx[row]]
-        return offs, ids.contiguous()
+        keep = ids != true_idx[row]
+        # third array: the row every entry belongs to (the filter kernel then needs no bisection)
+        return offs, ids[keep].contiguous(), row[keep].to(torch.int32).contiguous()
 
     def as_dicts(self):
         """(dict_of_heads, dict_of_tails) for code that wants the reference's containers."""
@@ -207,7 +208,8 @@ def expand_unique_sets(row_uid, has_true, uoffs, flat, true_idx):
     row_uid (n,) int64: which unique set a row uses (any value where has_true is False);
     has_true (n,) bool: the row's true entity is a member of its set (otherwise the row is left
     unfiltered, get_true_targets' KeyError quirk); uoffs (u+1,), flat (m,): the unique sets, CSR;
-    true_idx (n,).  All on one device.  Returns (offs (n+1,), ids) with the true entity removed.
+    true_idx (n,).  All on one device.  Returns (offs (n+1,), ids, row of every entry (int32)) with
+    the true entity removed.
     """
     dev = row_uid.device
     n = row_uid.numel()
@@ -222,8 +224,8 @@ def expand_unique_sets(row_uid, has_true, uoffs, flat, true_idx):
     start = torch.cumsum(full, 0) - full
     pos = torch.arange(row.numel(), device=dev) - start[row] + uoffs[uid][row]
     ids = flat[pos]
-    ids = ids[ids != true_idx[row]]
-    return offs, ids.contiguous()
+    keep = ids != true_idx[row]
+    return offs, ids[keep].contiguous(), row[keep].to(torch.int32).contiguous()
 
 
 def dict_filter_csr(kg, which, key1, key2, true_idx, device):
@@ -244,7 +246,7 @@ def dict_filter_csr(kg, which, key1, key2, true_idx, device):
            true_idx.data_ptr(), int(key1.shape[0]), int(key1.sum()), int(key2.sum()), int(true_idx.sum()))
     hit = cache.get(key)
     if hit is not None:
-        return hit
+        return hit      # ((offs, ids, row of entry), bytes uploaded)
     n = int(key1.shape[0])
     get = dictionary.get
     uniq, sets = {}, []
@@ -274,5 +276,5 @@ def dict_filter_csr(kg, which, key1, key2, true_idx, device):
     nbytes = 8 * (row_uid.size + uoffs.size + flat.size) + has_true.size
     while len(cache) >= 4:          # tail + head of the current test set, and one generation back
         cache.pop(next(iter(cache)))
-    cache[key] = csr + (nbytes,)
+    cache[key] = (csr, nbytes)
     return cache[key]

@@ -250,8 +250,9 @@ class CudaEngine:
         a.rel0, a.rel1 = _ptr(spec.rel0), _ptr(spec.rel1)
         a.hrows, a.trows, a.r_idx, a.true_idx = _ptr(hrows), _ptr(trows), _ptr(r_idx), _ptr(true_idx)
         if filt is not None:
-            offs, ids = filt
+            offs, ids = filt[0], filt[1]
             a.filt_offs, a.filt_ids, a.n_filt = _ptr(offs), _ptr(ids), ids.shape[0]
+            a.filt_qid = _ptr(filt[2]) if len(filt) > 2 else None
         a.raw_count, a.filt_sub, a.true_score = _ptr(raw_count), _ptr(filt_sub), _ptr(true_score)
         a.true_rows, a.true_score_in = _ptr(true_rows), _ptr(true_score_in)
         a.workspace, a.workspace_bytes, a.stream = _ptr(ws), ws_bytes, _stream(dev)
@@ -265,10 +266,13 @@ class CudaEngine:
         """Sparse filter pass for a side whose dense scan was enqueued earlier by rank_side
         (with filt=None); ``handle`` is what that call returned."""
         a = handle[0]
-        offs, ids = filt
+        offs, ids = filt[0], filt[1]
         if ids.shape[0] == 0:
             return
         a.filt_offs, a.filt_ids, a.n_filt = _ptr(offs), _ptr(ids), ids.shape[0]
+        # optional third array: the CSR row of every entry (int32), spares the kernel a bisection per entry
+        a.filt_qid = _ptr(filt[2]) if len(filt) > 2 and filt[2] is not None else None
+        self._keep = filt
         a.filt_sub = _ptr(filt_sub)
         a.stream = _stream(filt_sub.device)
         _lib.check(self.lib.kge_filter_side(ctypes.byref(a)), "kge_filter_side")
@@ -448,13 +452,16 @@ class QueryShard:
 
 
 def _csr_slice(filt, lo, hi, n):
-    """CSR rows [lo, hi) with offsets rebased to 0."""
-    offs, ids = filt
+    """CSR rows [lo, hi) with offsets (and row ids, when present) rebased to 0."""
+    offs, ids = filt[0], filt[1]
     if lo == 0 and hi == n:
-        return offs, ids
+        return filt
     base = int(offs[lo].item())
     end = int(offs[hi].item())
-    return (offs[lo:hi + 1] - base).contiguous(), ids[base:end].contiguous()
+    out = ((offs[lo:hi + 1] - base).contiguous(), ids[base:end].contiguous())
+    if len(filt) > 2 and filt[2] is not None:
+        out = out + ((filt[2][base:end] - lo).contiguous(),)
+    return out
 
 
 class LazyRanks:
@@ -565,11 +572,14 @@ def rank_link_prediction(spec, h_idx, t_idx, r_idx, filt_tail, filt_head, shard=
         for handle, which, lo, hi, sub in pending:
             if filts[which] is not None:
                 offs, ids = filts[which][0], filts[which][1]
+                qid = filts[which][2] if len(filts[which]) > 2 else None
                 if cuts[which] is None:
-                    part = (offs, ids)
+                    part = filts[which]
                 else:
                     a, b = cuts[which][lo], cuts[which][hi]
                     part = ((offs[lo:hi + 1] - a).contiguous(), ids[a:b].contiguous())
+                    if qid is not None:
+                        part = part + ((qid[a:b] - lo).contiguous(),)
                 engine.filter_side(handle, part, sub[lo:hi])
         mark("filters enqueued")
         del pending

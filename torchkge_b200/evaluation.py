@@ -117,9 +117,9 @@ class LinkPredictionEvaluator(object):
             # keys flattened once on the host, expanded on the device, cached on the graph
             def from_dicts(which, k1, k2, true):
                 def build():
-                    offs, ids, nbytes = dict_filter_csr(kg, which, k1, k2, true, dev)
+                    csr, nbytes = dict_filter_csr(kg, which, k1, k2, true, dev)
                     stats["h2d_bytes"] += nbytes
-                    return offs, ids
+                    return csr
                 return build
             csr_tail = from_dicts("tail", heads, rels, tails)
             csr_head = from_dicts("head", tails, rels, heads)

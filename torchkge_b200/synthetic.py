@@ -150,16 +150,17 @@ def _csr_for(keys_all, vals_all, keys_q, true_q):
     ids, q_of = ids[keep], q_of[keep]
     offs = torch.zeros(keys_q.numel() + 1, dtype=torch.int64, device=keys_q.device)
     offs[1:] = torch.cumsum(torch.bincount(q_of, minlength=keys_q.numel()), 0)
-    return offs, ids.contiguous(), (lo, hi, ks, vs)
+    return offs, ids.contiguous(), q_of.to(torch.int32).contiguous()
 
 
 def make_filters(graph, n_ent, n_rel):
     """Device CSRs of the filter sets of the test triples (true entity removed), computed from
-    ALL facts of the graph: (csr_tail, csr_head) with csr = (offs int64 (n+1,), ids int64)."""
+    ALL facts of the graph: (csr_tail, csr_head) with csr = (offs int64 (n+1,), ids int64, rows int32)."""
     h, t, r = graph["heads"], graph["tails"], graph["rels"]
     th, tt, tr = graph["test_h"], graph["test_t"], graph["test_r"]
-    csr_t = _csr_for(h * n_rel + r, t, th * n_rel + tr, tt)[:2]
-    csr_h = _csr_for(t * n_rel + r, h, tt * n_rel + tr, th)[:2]
+    # (offs, ids, row of every entry): the third array spares the filter kernel a bisection per entry
+    csr_t = _csr_for(h * n_rel + r, t, th * n_rel + tr, tt)
+    csr_h = _csr_for(t * n_rel + r, h, tt * n_rel + tr, th)
     return csr_t, csr_h
 
 
