@@ -237,3 +237,18 @@ def test_dict_filter_csr_equals_filter_csr_and_caches():
     dt[(999, 0)] = {1, 2}
     (o3, i3, _), _ = dict_filter_csr(kg, "tail", qh, qr, qt, torch.device("cpu"))
     assert torch.equal(o3, filter_csr(dt, qh, qr, qt)[0])
+
+
+def test_csr_slices_carry_the_row_of_entry_array():
+    """engine._csr_slice on (offs, ids, rows) triples: offsets and row ids are rebased to the slice."""
+    from torchkge_b200.engine import _csr_slice
+    offs = torch.tensor([0, 2, 2, 5, 6, 9])
+    ids = torch.arange(100, 109)
+    rows = torch.repeat_interleave(torch.arange(5), offs[1:] - offs[:-1]).to(torch.int32)
+    whole = _csr_slice((offs, ids, rows), 0, 5, 5)
+    assert whole[0] is offs and whole[2] is rows
+    o, i, q = _csr_slice((offs, ids, rows), 2, 5, 5)
+    assert o.tolist() == [0, 3, 4, 7] and i.tolist() == list(range(102, 109))
+    assert q.tolist() == [0, 0, 0, 1, 2, 2, 2]
+    o2, i2 = _csr_slice((offs, ids), 1, 3, 5)
+    assert o2.tolist() == [0, 0, 3] and i2.tolist() == [102, 103, 104]
