@@ -820,7 +820,9 @@ def run_ours(args, rank, local, world):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE tc_scan launch, from the committed ncu capture
 # profiles/r02_tc_scan_fp16_ncu_summary.md (the 0.9 GB operand image read once + the near-tie list writes)
-TRAFFIC = {("c2", 1): 1.025e9 + 0.037e9}
+TRAFFIC = {("c2", 1): 1.025e9 + 0.037e9,
+           # profiles/r02_tc_scan_c3_ncu_summary.md: both operand images stream at K = 800 (no resident query image)
+           ("c3", 1): 12.975e9 + 0.156e9}
 
 
 def measure_reference_kg(S, graph, wl, model, ranks_dev, args):
