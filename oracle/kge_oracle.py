@@ -153,9 +153,21 @@ def rotate_scores_all(P, h_idx, t_idx, r_idx, side):
         im_q = re_r * im_e - im_r * re_e
     dre = re_q.view(b, 1, d) - re_c
     dim_ = im_q.view(b, 1, d) - im_c
-    # complex modulus as in the authors' code: stack + norm over the stacked axis.  (ATen's
-    # element-wise torch.sqrt is not correctly rounded on CPU; the norm kernel's sqrt is.)
-    return -torch.stack([dre, dim_], dim=0).norm(dim=0).sum(dim=2)
+    return -complex_modulus(dre, dim_).sum(dim=2)
+
+
+def complex_modulus(re, im, authors_form=False):
+    """|re + i im| element-wise, as the authors' code computes it: ``stack([re, im]).norm(dim=0)``,
+    i.e. sqrt_rn(fl(fl(re^2) + fl(im^2))) with a CORRECTLY ROUNDED square root (ATen's element-wise
+    fp32 ``torch.sqrt`` is not: 0.35 % of values are off by one ulp on CPU).  The stacked norm is a
+    reduction over an axis of length 2 and runs at a few tens of M elements/s; the default form
+    takes the square root in float64 and rounds once more to float32 -- the same bits (a float64 sqrt
+    of a float32 value rounds to the correctly rounded float32 sqrt; tests/test_oracle_golden.py checks the
+    two forms against each other) at memory speed, which is what makes oracle samples at the C4
+    table size affordable."""
+    if authors_form:
+        return torch.stack([re, im], dim=0).norm(dim=0)
+    return torch.sqrt((re * re + im * im).double()).float()
 
 
 # --------------------------------------------------------------------------- filter + rank
@@ -318,7 +330,7 @@ def score_triples(kind, P, h_idx, t_idx, r_idx):
         re_r, im_r = re_rel[r_idx], im_rel[r_idx]
         dre = (re_h * re_r - im_h * im_r) - re_t
         dim_ = (re_h * im_r + im_h * re_r) - im_t
-        return -torch.stack([dre, dim_], dim=0).norm(dim=0).sum(dim=1)
+        return -complex_modulus(dre, dim_).sum(dim=1)
     raise ValueError(kind)
 
 
