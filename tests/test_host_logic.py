@@ -252,3 +252,21 @@ def test_csr_slices_carry_the_row_of_entry_array():
     assert q.tolist() == [0, 0, 0, 1, 2, 2, 2]
     o2, i2 = _csr_slice((offs, ids), 1, 3, 5)
     assert o2.tolist() == [0, 0, 3] and i2.tolist() == [102, 103, 104]
+
+
+def test_data_loader_batches_in_fact_order():
+    """utils.DataLoader (torchkge/utils/data.py:83-151): consecutive slices of the three index tensors,
+    a partial last batch, len() = number of batches."""
+    from torchkge_b200.utils import DataLoader
+    h, t, r = helpers.random_graph(40, 3, 100, seed=0)
+    kg = tk.KnowledgeGraph(h, t, r, 40, 3)
+    dl = DataLoader(kg, batch_size=32)
+    batches = list(dl)
+    assert len(dl) == len(batches) == -(-kg.n_facts // 32)
+    assert torch.equal(torch.cat([b[0] for b in batches]), kg.head_idx)
+    assert torch.equal(torch.cat([b[1] for b in batches]), kg.tail_idx)
+    assert torch.equal(torch.cat([b[2] for b in batches]), kg.relations)
+    assert all(b[0].shape[0] == 32 for b in batches[:-1]) and 1 <= batches[-1][0].shape[0] <= 32
+    assert list(dl)[0][0].data_ptr() == batches[0][0].data_ptr()      # a second pass starts over
+    with pytest.raises(ValueError):
+        DataLoader(kg, batch_size=8, use_cuda="sometimes")

@@ -158,6 +158,33 @@ class KnowledgeGraph:
         return self.n_facts
 
 
+class DataLoader:
+    """Batches of (heads, tails, relations) index tensors of a graph, in fact order, for the tutorial
+    training loop ``for h, t, r in DataLoader(kg, batch_size, use_cuda='all')`` (torchkge/utils/data.py:
+    83-151; no shuffling there either).  ``use_cuda``: None (batches stay where the graph's tensors
+    are), 'all' (the three index tensors are moved to the current CUDA device once) or 'batch' (every
+    batch is moved when it is handed out)."""
+
+    def __init__(self, kg, batch_size, use_cuda=None):
+        if use_cuda not in (None, "all", "batch"):
+            raise ValueError("use_cuda must be None, 'all' or 'batch'")
+        if int(batch_size) < 1:
+            raise ValueError("batch_size must be a positive integer")
+        self.batch_size, self.use_cuda = int(batch_size), use_cuda
+        self._columns = [kg.head_idx, kg.tail_idx, kg.relations]
+        if use_cuda == "all":
+            self._columns = [x.cuda() for x in self._columns]
+
+    def __len__(self):
+        return -(-self._columns[0].shape[0] // self.batch_size)
+
+    def __iter__(self):
+        n = self._columns[0].shape[0]
+        for lo in range(0, n, self.batch_size):
+            batch = tuple(x[lo:lo + self.batch_size] for x in self._columns)
+            yield tuple(x.cuda() for x in batch) if self.use_cuda == "batch" else batch
+
+
 def build_filter_dicts(heads, tails, relations):
     """(dict_of_heads keyed (t, r), dict_of_tails keyed (h, r)) as defaultdict(set)."""
     order = torch.arange(heads.shape[0])
