@@ -276,23 +276,16 @@ def dict_filter_csr(kg, which, key1, key2, true_idx, device):
         return hit      # ((offs, ids, row of entry), bytes uploaded)
     n = int(key1.shape[0])
     get = dictionary.get
-    uniq, sets = {}, []
-    row_uid = np.full(n, -1, dtype=np.int64)
-    has_true = np.zeros(n, dtype=bool)
-    for i, (a, b, c) in enumerate(zip(key1.tolist(), key2.tolist(), true_idx.tolist())):
-        k = (a, b)
-        u = uniq.get(k)
-        if u is None:
-            s = get(k)
-            if s is None:
-                u = -1
-            else:
-                u = len(sets)
-                sets.append(s)
-            uniq[k] = u
-        if u >= 0:
-            row_uid[i] = u
-            has_true[i] = c in sets[u]
+    # per-row work in C-level loops (zip / dict.fromkeys / comprehensions): ~0.1 us per row
+    keys = list(zip(key1.tolist(), key2.tolist()))
+    uid_of = {k: u for u, k in enumerate(dict.fromkeys(keys))}          # distinct keys, first-seen order
+    found = [get(k) for k in uid_of]                                     # their sets (None: unknown key)
+    empty = frozenset()
+    sets = [x if x is not None else empty for x in found]
+    uids = [uid_of[k] for k in keys]
+    row_uid = np.fromiter(uids, dtype=np.int64, count=n)
+    # get_true_targets: a row whose true entity is not in its set is left unfiltered
+    has_true = np.fromiter((c in sets[u] for c, u in zip(true_idx.tolist(), uids)), dtype=bool, count=n)
     lens = np.fromiter(map(len, sets), dtype=np.int64, count=len(sets))
     uoffs = np.zeros(len(sets) + 1, dtype=np.int64)
     np.cumsum(lens, out=uoffs[1:])
