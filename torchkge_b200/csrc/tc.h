@@ -108,7 +108,8 @@ struct TcScanParams {
 // ulp; lower bits are cut toward zero: 1 + 15 x 2^-25 gives 1 + 3 ulp, 1 + 15 x 2^-26 gives 1), adds
 // exactly and cuts the sum toward zero to 24 bits.  Hence per instruction
 //   |result - exact| < 16 * 2^-25 * 2^Emax + 2^-23 |result| <= (8 + 2) * 2^-24 * (|acc_in| + sum |products|)
-// Largest value observed on random / adversarial operands: 4.3 (same-sign, wide exponent range).
+// Largest value observed on random / adversarial operands: 5.1 (same-sign, wide exponent range).
+// tests/test_tc_model_cpu.py replays this model in exact arithmetic against every crafted probe result.
 constexpr double TC_ACC_ULPS = 10.0;  // per-instruction accumulation error in units of 2^-24 * running magnitude
 inline float tc_gamma(int k_total, int ref_depth, bool l2, bool fp16 = false) {
   const double split = fp16 ? 3.0 * 0x1p-22 * (1.0 + 0x1p-11) : 3.0 * 0x1p-16 * (1.0 + 0x1p-8);
