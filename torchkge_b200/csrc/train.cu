@@ -653,8 +653,10 @@ __device__ __forceinline__ Vec vec_load_smem(const float* row, int dim, int lane
   return v;
 }
 
-template <int MODEL, bool BWD>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+// MINB: minimum resident CTAs per SM the register allocation is held to (0: the compiler's choice --
+// 72 registers forward, 128 backward; 5 holds the backward form to 96 registers, 20 warps per SM)
+template <int MODEL, bool BWD, int MINB = 0>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB == 0 ? 1 : MINB)
 margin_step_ring_kernel(MarginStepParams a, TrainGrads gr, const float* __restrict__ gloss) {
   extern __shared__ __align__(128) unsigned char ring_smem[];
   const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -861,21 +863,32 @@ __host__ inline bool ring_step_ok(const MarginStepParams& a) {
   return enabled && a.n_neg <= 8192 && a.n_ent < 0x7FFFFFFFll && ring_smem_bytes(a) <= 96 * 1024;
 }
 
-template <int MODEL, bool BWD>
-cudaError_t launch_ring(const MarginStepParams& a, const TrainGrads& gr, const float* gloss, cudaStream_t st) {
+template <int MODEL, bool BWD, int MINB>
+cudaError_t launch_ring_variant(const MarginStepParams& a, const TrainGrads& gr, const float* gloss, cudaStream_t st) {
   const size_t smem = ring_smem_bytes(a);
   static bool configured[64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (smem > 48 * 1024 && (dev < 0 || dev >= 64 || !configured[dev])) {
-    e = cudaFuncSetAttribute(margin_step_ring_kernel<MODEL, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    e = cudaFuncSetAttribute(margin_step_ring_kernel<MODEL, BWD, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             96 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const unsigned blocks = (unsigned)((a.b + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-  margin_step_ring_kernel<MODEL, BWD><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(a, gr, gloss);
+  margin_step_ring_kernel<MODEL, BWD, MINB><<<blocks, WARPS_PER_BLOCK * 32, smem, st>>>(a, gr, gloss);
   return cudaGetLastError();
+}
+
+// KGE_TRAIN_BWD_BLOCKS=5 holds the backward kernel to 96 registers (5 CTAs = 20 warps per SM)
+template <int MODEL, bool BWD>
+cudaError_t launch_ring(const MarginStepParams& a, const TrainGrads& gr, const float* gloss, cudaStream_t st) {
+  if constexpr (BWD) {
+    static const bool tight = [] { const char* v = getenv("KGE_TRAIN_BWD_BLOCKS"); return v && v[0] == '5'; }();
+    if (tight) return launch_ring_variant<MODEL, true, 5>(a, gr, gloss, st);
+  }
+  return launch_ring_variant<MODEL, BWD, 0>(a, gr, gloss, st);
 }
 
 __host__ inline bool fast_step_ok(const MarginStepParams& a) {
