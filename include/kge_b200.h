@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 7
+#define KGE_ABI_VERSION 8
 
 /* error codes */
 #define KGE_OK 0
@@ -58,9 +58,18 @@ typedef enum {
   KGE_TORUSE_L1 = 6, /* torchkge/models/translation.py:655 + utils/dissimilarities.py:28-34 (torus_L1);
                         link-prediction side only (kge_rank_side / kge_score_all), tables already
                         reduced to their fractional parts (TorusEModel.normalize_parameters) */
-  KGE_TORUSE_L2 = 7  /* same + utils/dissimilarities.py:37-43 (torus_L2); torus_eL2 (cosine) is not
+  KGE_TORUSE_L2 = 7, /* same + utils/dissimilarities.py:37-43 (torus_L2); torus_eL2 (cosine) is not
                         on the path */
+  KGE_ANALOGY = 8    /* torchkge/models/bilinear.py:559-763, scalar_dim == complex_dim == dim: THREE planes
+                        per row (scalar, real, imaginary), see "three-plane tables" below */
 } kge_model_t;
+
+/* Three-plane tables (KGE_ANALOGY).  Every entry point takes at most two pointers per table
+ * (ent0 / ent1, rel0 / rel1, hrows / trows rows of [planes][dim]).  For a three-plane model the planes
+ * of a table must be EQUALLY SPACED in memory -- e.g. one [3][n_rows][dim] array, or row ranges of
+ * one -- and the caller passes planes 0 and 1: the library reads plane 2 at ent1 + (ent1 - ent0)
+ * (likewise rel1 + (rel1 - rel0), and for gradient tables).  No signature changes with the number
+ * of planes. */
 
 /* Which element of the triple is being completed. */
 typedef enum {
@@ -69,7 +78,7 @@ typedef enum {
   KGE_SIDE_REL = 2   /* (h, ?, t)  RelationPredictionEvaluator, evaluation.py:94-97: the candidate
                         table (packed / ent0 / ent1) is the RELATION table (rel_emb; re_/im_rel_emb),
                         rel0 / rel1 / r_idx are unused, true_rows is required.  TransE L1/L2, DistMult,
-                        ComplEx (RESCAL's batched matmul and RotatE are not on this path). */
+                        ComplEx, Analogy (RESCAL's batched matmul and RotatE are not on this path). */
 } kge_side_t;
 
 /* Geometry of the packed layouts, fixed at build time; exported so that callers can
@@ -82,9 +91,9 @@ int kge_abi_version(void);
 const char* kge_last_error(void);
 
 /* Number of fp32 planes per entity row / per query for a model:
- * candidates: 1 (TransE, DistMult, RESCAL) or 2 (ComplEx, RotatE: re, im);
+ * candidates: 1 (TransE, DistMult, RESCAL), 2 (ComplEx, RotatE: re, im) or 3 (Analogy: sc, re, im);
  * queries: 1, or 2 for TransE head side (r and t stay separate, interfaces.py:256-260)
- * and for ComplEx / RotatE. */
+ * and for ComplEx / RotatE, 3 for Analogy. */
 int kge_cand_planes(int model);
 int kge_query_planes(int model, int side);
 

@@ -7,7 +7,7 @@ fallback.
 What this is: a restatement, in plain PyTorch CPU tensor ops, of the algorithm torchkge
 v0.17.7 (commit 3adb934) runs for
   * all-entity scoring      models/interfaces.py:240-260, models/bilinear.py:98-121,
-                            224-245, 501-528 (+ utils/dissimilarities.py:11-25)
+                            224-245, 501-528, 682-711 (+ utils/dissimilarities.py:11-25)
   * filtering               utils/modeling.py:53-102
   * ranking                 utils/operations.py:37-61
   * the evaluator loop      evaluation.py:263-308
@@ -34,7 +34,8 @@ from collections import defaultdict
 
 import torch
 
-KINDS = ("transe_l1", "transe_l2", "distmult", "rescal", "complex", "rotate", "toruse_l1", "toruse_l2")
+KINDS = ("transe_l1", "transe_l2", "distmult", "rescal", "complex", "rotate", "toruse_l1", "toruse_l2",
+         "analogy")
 
 
 # --------------------------------------------------------------------------- dissimilarities
@@ -116,6 +117,23 @@ def scores_all(kind, P, h_idx, t_idx, r_idx, side):
         # bilinear.py:517-522
         return (re_c * (re_r * re_t + im_r * im_t).view(b, 1, d)
                 + im_c * (re_r * im_t - im_r * re_t).view(b, 1, d)).sum(dim=2)
+    if kind == "analogy":
+        names = ("sc_ent", "re_ent", "im_ent")
+        ds, dc = P["sc_ent"].shape[1], P["re_ent"].shape[1]
+        sc_c = P["sc_ent"].view(1, -1, ds).expand(b, -1, ds)
+        re_c = P["re_ent"].view(1, -1, dc).expand(b, -1, dc)
+        im_c = P["im_ent"].view(1, -1, dc).expand(b, -1, dc)
+        sc_h, re_h, im_h = _rows(P, names, h_idx)
+        sc_t, re_t, im_t = _rows(P, names, t_idx)
+        sc_r, re_r, im_r = _rows(P, ("sc_rel", "re_rel", "im_rel"), r_idx)
+        if tail:  # bilinear.py:692-698
+            return ((sc_h * sc_r).view(b, 1, ds) * sc_c
+                    + (re_h * re_r - im_h * im_r).view(b, 1, dc) * re_c
+                    + (re_h * im_r + im_h * re_r).view(b, 1, dc) * im_c).sum(dim=2)
+        # bilinear.py:699-705
+        return (sc_c * (sc_r * sc_t).view(b, 1, ds)
+                + re_c * (re_r * re_t + im_r * im_t).view(b, 1, dc)
+                + im_c * (re_r * im_t - im_r * re_t).view(b, 1, dc)).sum(dim=2)
     if kind == "rotate":
         return rotate_scores_all(P, h_idx, t_idx, r_idx, side)
     raise ValueError(kind)
@@ -255,6 +273,17 @@ def relation_scores_all(kind, P, h_idx, t_idx):
         im_r = P["im_rel"].view(1, -1, d).expand(b, -1, -1)
         return ((re_h * re_t + im_h * im_t).view(b, 1, d) * re_r
                 + (re_h * im_t - im_h * re_t).view(b, 1, d) * im_r).sum(dim=2)
+    if kind == "analogy":   # bilinear.py:706-711
+        names = ("sc_ent", "re_ent", "im_ent")
+        ds, dc = P["sc_ent"].shape[1], P["re_ent"].shape[1]
+        sc_h, re_h, im_h = _rows(P, names, h_idx)
+        sc_t, re_t, im_t = _rows(P, names, t_idx)
+        sc_r = P["sc_rel"].view(1, -1, ds).expand(b, -1, -1)
+        re_r = P["re_rel"].view(1, -1, dc).expand(b, -1, -1)
+        im_r = P["im_rel"].view(1, -1, dc).expand(b, -1, -1)
+        return (sc_r * (sc_h * sc_t).view(b, 1, ds)
+                + re_r * (re_h * re_t + im_h * im_t).view(b, 1, dc)
+                + im_r * (re_h * im_t - im_h * re_t).view(b, 1, dc)).sum(dim=2)
     raise ValueError(kind)
 
 
@@ -323,6 +352,12 @@ def score_triples(kind, P, h_idx, t_idx, r_idx):
         re_t, im_t = _rows(P, ("re_ent", "im_ent"), t_idx)
         re_r, im_r = _rows(P, ("re_rel", "im_rel"), r_idx)
         return (re_h * (re_r * re_t + im_r * im_t) + im_h * (re_r * im_t - im_r * re_t)).sum(dim=1)
+    if kind == "analogy":   # bilinear.py:634-650
+        sc_h, re_h, im_h = _rows(P, ("sc_ent", "re_ent", "im_ent"), h_idx)
+        sc_t, re_t, im_t = _rows(P, ("sc_ent", "re_ent", "im_ent"), t_idx)
+        sc_r, re_r, im_r = _rows(P, ("sc_rel", "re_rel", "im_rel"), r_idx)
+        return ((sc_h * sc_r * sc_t).sum(dim=1) +
+                (re_h * (re_r * re_t + im_r * im_t) + im_h * (re_r * im_t - im_r * re_t)).sum(dim=1))
     if kind == "rotate":
         re_h, im_h = _rows(P, ("re_ent", "im_ent"), h_idx)
         re_t, im_t = _rows(P, ("re_ent", "im_ent"), t_idx)
@@ -412,6 +447,11 @@ def init_params(kind, n_ent, n_rel, d, generator=None):
     if kind == "complex":
         return {"re_ent": xavier(n_ent, d), "im_ent": xavier(n_ent, d),
                 "re_rel": xavier(n_rel, d), "im_rel": xavier(n_rel, d)}
+    if kind == "analogy":   # bilinear.py:620-631: d = emb_dim, split in halves (scalar_share 0.5); raw Xavier
+        ds = d // 2
+        dc = d - ds
+        return {"sc_ent": xavier(n_ent, ds), "re_ent": xavier(n_ent, dc), "im_ent": xavier(n_ent, dc),
+                "sc_rel": xavier(n_rel, ds), "re_rel": xavier(n_rel, dc), "im_rel": xavier(n_rel, dc)}
     if kind == "rotate":
         ph = (torch.rand(n_rel, d, generator=generator) * 2 - 1) * 3.141592653589793
         return {"re_ent": xavier(n_ent, d), "im_ent": xavier(n_ent, d), "rel_phase": ph}

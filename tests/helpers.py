@@ -13,6 +13,7 @@ KIND_TO_CLASS = {
     "rotate": lambda d, ne, nr: tk.RotatEModel(d, ne, nr),
     "toruse_l1": lambda d, ne, nr: tk.TorusEModel(d, ne, nr, dissimilarity_type="torus_L1"),
     "toruse_l2": lambda d, ne, nr: tk.TorusEModel(d, ne, nr, dissimilarity_type="torus_L2"),
+    "analogy": lambda d, ne, nr: tk.AnalogyModel(d, ne, nr),     # d = emb_dim: two halves
 }
 
 
@@ -36,6 +37,10 @@ def oracle_params(kind, model):
         return {"ent": g(model.ent_emb.weight), "rel_mat": g(model.rel_mat.weight)}
     if kind == "complex":
         return {"re_ent": g(model.re_ent_emb.weight), "im_ent": g(model.im_ent_emb.weight),
+                "re_rel": g(model.re_rel_emb.weight), "im_rel": g(model.im_rel_emb.weight)}
+    if kind == "analogy":
+        return {"sc_ent": g(model.sc_ent_emb.weight), "re_ent": g(model.re_ent_emb.weight),
+                "im_ent": g(model.im_ent_emb.weight), "sc_rel": g(model.sc_rel_emb.weight),
                 "re_rel": g(model.re_rel_emb.weight), "im_rel": g(model.im_rel_emb.weight)}
     if kind == "rotate":
         re_r, im_r = model.relation_planes()  # computed on the model's device: same bits for both
@@ -82,11 +87,14 @@ import numpy as np  # noqa: E402
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["toy_transe_l1", "toy_transe_l2", "toy_distmult", "toy_rescal", "toy_complex",
                 "syn_transe_l1", "syn_transe_l2", "syn_distmult", "syn_rescal", "syn_complex"]
+#: same layout, from tests/golden/make_golden_analogy.py (AnalogyModel, models/bilinear.py:559-763)
+ANALOGY_CASES = ["toy_analogy", "syn_analogy"]
 
 _STATE_TO_ORACLE = {
     "ent_emb.weight": "ent", "rel_emb.weight": "rel", "rel_mat.weight": "rel_mat",
     "re_ent_emb.weight": "re_ent", "im_ent_emb.weight": "im_ent",
     "re_rel_emb.weight": "re_rel", "im_rel_emb.weight": "im_rel",
+    "sc_ent_emb.weight": "sc_ent", "sc_rel_emb.weight": "sc_rel",
 }
 
 

@@ -13,12 +13,12 @@ using namespace kge;
 namespace {
 template <int EL, bool CASC>
 float replay(int dim, const float* q0, const float* q1, const float* c0, const float* c1,
-             const int32_t* perm, const uint8_t* code) {
+             const int32_t* perm, const uint8_t* code, const float* qm, const float* cm) {
   Acc r;
   acc_reset(r);
   for (int pos = 0; pos < dim; ++pos) {
     const int k = perm[pos];
-    acc_step<EL, CASC>(r, code[pos], q0[k], q1[k], c0[k], c1[k]);
+    acc_step<EL, CASC>(r, code[pos], q0[k], q1[k], c0[k], c1[k], qm[k], cm[k]);
   }
   return acc_finish<EL>(r);
 }
@@ -33,12 +33,14 @@ void run(int mode, int casc, int dim, int nq, int nc, const float* q, const floa
       const float* q1 = q0 + (size_t)(QW - 1) * dim;
       const float* c0 = c + (size_t)j * CW * dim;
       const float* c1 = c0 + (size_t)(CW - 1) * dim;
+      const float* qm = q0 + (size_t)(QW / 2) * dim;   // middle plane (three-plane kinds)
+      const float* cm = c0 + (size_t)(CW / 2) * dim;
       float s;
-      if (mode == 0) s = casc ? replay<EL, true>(dim, q0, q1, c0, c1, perm, code)
-                              : replay<EL, false>(dim, q0, q1, c0, c1, perm, code);
+      if (mode == 0) s = casc ? replay<EL, true>(dim, q0, q1, c0, c1, perm, code, qm, cm)
+                              : replay<EL, false>(dim, q0, q1, c0, c1, perm, code, qm, cm);
       else {
         if constexpr (ElemTraits<EL>::RED == RED_SEQ) s = 0.f / 0.f;  // no natural form
-        else s = pair_score_natural<EL>(dim, q0, q1, c0, c1);
+        else s = pair_score_natural<EL>(dim, q0, q1, c0, c1, qm, cm);
       }
       out[(size_t)i * nc + j] = s;
     }
@@ -61,6 +63,7 @@ extern "C" int host_scores(int el, int mode, int casc, int dim, int nq, int nc, 
     case EL_TL1_HEAD: run<EL_TL1_HEAD>(mode, casc, dim, nq, nc, q, c, perm, code, out); break;
     case EL_TL2_TAIL: run<EL_TL2_TAIL>(mode, casc, dim, nq, nc, q, c, perm, code, out); break;
     case EL_TL2_HEAD: run<EL_TL2_HEAD>(mode, casc, dim, nq, nc, q, c, perm, code, out); break;
+    case EL_DOT3: run<EL_DOT3>(mode, casc, dim, nq, nc, q, c, perm, code, out); break;
     default: return 1;
   }
   return 0;

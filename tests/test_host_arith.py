@@ -30,6 +30,7 @@ KINDS = {
     "rot": (6, _lib.ROTATE, 2, 2), "dot_mid": (7, _lib.DISTMULT, 2, 1),
     "tl1_tail": (8, _lib.TORUSE_L1, 1, 1), "tl1_head": (9, _lib.TORUSE_L1, 2, 1),
     "tl2_tail": (10, _lib.TORUSE_L2, 1, 1), "tl2_head": (11, _lib.TORUSE_L2, 2, 1),
+    "dot3": (12, _lib.ANALOGY, 3, 3),
 }
 
 
@@ -56,6 +57,9 @@ def _aten(kind, q, c):
         return (q0 * c0).sum(dim=2)
     if kind == "dot2":
         return (q0 * c0 + q1 * c1).sum(dim=2)
+    if kind == "dot3":       # Analogy, bilinear.py:695-698: scalar, real, imaginary planes
+        qm, cm = q[:, 1].view(nq, 1, d), c[:, 1].view(1, nc, d).expand(nq, nc, d)
+        return (q0 * c0 + qm * cm + q1 * c1).sum(dim=2)
     if kind == "dot_mid":
         return ((q0 * c0) * q1).sum(dim=2)
     if kind == "rot":

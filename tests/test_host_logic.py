@@ -58,6 +58,61 @@ def test_model_spec_reads_reference_parameter_names():
     assert ModelSpec.from_model(tk.TransEModel(8, 12, 3)).code == _lib.TRANSE_L2
 
 
+def test_model_spec_of_a_three_plane_model():
+    """Analogy (bilinear.py:559-763): the three planes of a table are equally spaced views of one
+    stacked copy -- the C ABI takes planes 0 and 1 and finds plane 2 at the same spacing -- and stay
+    so under narrowing to a shard; the plane width is scalar_dim, not emb_dim."""
+    from torchkge_b200.engine import _equally_spaced, relation_spec
+    m = tk.AnalogyModel(16, 12, 3)
+    assert (m.scalar_dim, m.complex_dim) == (8, 8)
+    assert set(m.state_dict()) == {"sc_ent_emb.weight", "re_ent_emb.weight", "im_ent_emb.weight",
+                                   "sc_rel_emb.weight", "re_rel_emb.weight", "im_rel_emb.weight"}
+    s = ModelSpec.from_model(m)
+    assert s.code == _lib.ANALOGY and s.dim == 8 and s.n_rows == 12 and s.cand_planes == 3
+    assert torch.equal(s.ent0, m.sc_ent_emb.weight) and torch.equal(s.ent1, m.re_ent_emb.weight)
+    assert torch.equal(s.ent2, m.im_ent_emb.weight) and torch.equal(s.rel2, m.im_rel_emb.weight)
+    assert _equally_spaced(s.ent0, s.ent1, s.ent2) and _equally_spaced(s.rel0, s.rel1, s.rel2)
+    sub = s.narrowed(4, 9)
+    assert sub.ent_lo == 4 and sub.n_rows == 5 and _equally_spaced(sub.ent0, sub.ent1, sub.ent2)
+    assert torch.equal(sub.ent2, m.im_ent_emb.weight[4:9])
+    r = relation_spec(s)
+    assert r.n_rows == 3 and r.cand_planes == 3 and torch.equal(r.ent2, m.im_rel_emb.weight)
+    with pytest.raises(ValueError):      # planes that are not views of one stacked tensor
+        ModelSpec(_lib.ANALOGY, 8, 12, 3, s.ent0, s.ent1.clone(), s.rel0, s.rel1, ent2=s.ent2, rel2=s.rel2)
+    with pytest.raises(NotImplementedError):   # odd emb_dim: the reference's inference fails on it too
+        ModelSpec.from_model(tk.AnalogyModel(7, 12, 3))
+    lib = _lib.load()
+    assert lib.kge_cand_planes(_lib.ANALOGY) == 3
+    assert [lib.kge_query_planes(_lib.ANALOGY, side) for side in (0, 1, 2)] == [3, 3, 3]
+    assert lib.kge_tc_packed_bytes(_lib.ANALOGY, 1000, 64) == 0       # exact scalar scan only
+    assert lib.kge_packed_table_floats(_lib.ANALOGY, 1000, 64) == 8 * 64 * 3 * 128
+
+
+def test_analogy_constructor_draws_the_reference_weights():
+    """Same RNG calls in the same order as bilinear.py:620-631: replaying the fixture's recipe
+    (tests/golden/make_golden.py: seed, constructor, row-wise perturbation) with THIS package's class
+    reproduces the weights the unmodified reference drew, bit for bit."""
+    from tests import helpers
+    g = helpers.load_golden("toy_analogy")
+    torch.manual_seed(7)
+    m = tk.AnalogyModel(g["dim"], g["n_ent"], g["n_rel"])
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(1.0 + 0.5 * torch.rand(p.shape[0], 1))
+    assert list(m.state_dict()) == list(g["state"])
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, g["state"][k]), k
+    # unequal widths (scalar_share != 0.5) are scored with torch ops: the reference's expression
+    m = tk.AnalogyModel(10, 7, 2, scalar_share=0.3)
+    assert (m.scalar_dim, m.complex_dim) == (3, 7)
+    h, t, r = torch.tensor([0, 1, 2]), torch.tensor([3, 4, 5]), torch.tensor([0, 1, 0])
+    re_h, im_h, re_t, im_t = m.re_ent_emb(h), m.im_ent_emb(h), m.re_ent_emb(t), m.im_ent_emb(t)
+    re_r, im_r = m.re_rel_emb(r), m.im_rel_emb(r)
+    want = ((m.sc_ent_emb(h) * m.sc_rel_emb(r) * m.sc_ent_emb(t)).sum(dim=1) +
+            (re_h * (re_r * re_t + im_r * im_t) + im_h * (re_r * im_t - im_r * re_t)).sum(dim=1))
+    assert torch.equal(m.scoring_function(h, t, r), want)
+
+
 def test_state_dict_keys_match_reference_contract():
     assert set(tk.TransEModel(4, 5, 2).state_dict()) == {"ent_emb.weight", "rel_emb.weight"}
     assert set(tk.RESCALModel(4, 5, 2).state_dict()) == {"ent_emb.weight", "rel_mat.weight"}

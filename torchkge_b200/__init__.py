@@ -7,7 +7,7 @@ sm_100a CUDA kernels reached through the C ABI of ``lib/libkge_b200.so``.
 from .exceptions import (NotYetEvaluatedError, NotYetImplementedError, SanityError,  # noqa: F401
                          SizeMismatchError, WrongArgumentsError, WrongDimensionError)
 from .data import KnowledgeGraph  # noqa: F401
-from .models import (ComplExModel, DistMultModel, RESCALModel, RotatEModel,  # noqa: F401
+from .models import (AnalogyModel, ComplExModel, DistMultModel, RESCALModel, RotatEModel,  # noqa: F401
                      TorusEModel, TransEModel)
 from .evaluation import (LinkPredictionEvaluator, RelationPredictionEvaluator,  # noqa: F401
                          TripletClassificationEvaluator)

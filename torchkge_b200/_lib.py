@@ -12,17 +12,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libkge_b200.so")
 
 # kge_model_t / kge_side_t (include/kge_b200.h)
-TRANSE_L1, TRANSE_L2, DISTMULT, RESCAL, COMPLEX, ROTATE, TORUSE_L1, TORUSE_L2 = range(8)
+TRANSE_L1, TRANSE_L2, DISTMULT, RESCAL, COMPLEX, ROTATE, TORUSE_L1, TORUSE_L2, ANALOGY = range(9)
 SIDE_TAIL, SIDE_HEAD, SIDE_REL = 0, 1, 2
 TILE_C, TILE_Q = 128, 64
-ABI_VERSION = 7
+ABI_VERSION = 8
 FLAG_TENSOR_CORE = 1
 FLAG_APPROX_SCAN = 2
 LOSS_LOGISTIC, LOSS_BCE = 1, 2
 
 MODEL_NAMES = {TRANSE_L1: "TransE-L1", TRANSE_L2: "TransE-L2", DISTMULT: "DistMult",
                RESCAL: "RESCAL", COMPLEX: "ComplEx", ROTATE: "RotatE",
-               TORUSE_L1: "TorusE-L1", TORUSE_L2: "TorusE-L2"}
+               TORUSE_L1: "TorusE-L1", TORUSE_L2: "TorusE-L2", ANALOGY: "Analogy"}
 
 
 class KgeLibraryError(RuntimeError):

@@ -189,7 +189,7 @@ int prepare_queries(int model, int side, int dim, int64_t n, const float* hrows,
   return KGE_OK;
 }
 
-bool model_needs_rel1(int model) { return model == KGE_COMPLEX || model == KGE_ROTATE; }
+bool model_needs_rel1(int model) { return model == KGE_COMPLEX || model == KGE_ROTATE || model == KGE_ANALOGY; }
 
 // Optional CUDA-event bracketing of the scan launches (kge_scan_timing_*).
 std::mutex g_timing_mu;
@@ -265,7 +265,7 @@ int kge_pack_table(int model, const float* ent0, const float* ent1, int64_t n_ro
                    float* packed, void* stream) {
   const int planes = kge_cand_planes(model);
   if (planes == 0) return fail(KGE_ERR_ARG, "kge_pack_table: unknown model");
-  if (!ent0 || !packed || (planes == 2 && !ent1))
+  if (!ent0 || !packed || (planes >= 2 && !ent1))
     return fail(KGE_ERR_ARG, "kge_pack_table: null table pointer");
   const HostSchedule* hs = get_schedule(model, dim);
   if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_pack_table: unsupported dim");
@@ -292,7 +292,7 @@ int kge_gather_rows(int model, const float* ent0, const float* ent1, int64_t ent
   const int planes = kge_cand_planes(model);
   if (planes == 0) return fail(KGE_ERR_ARG, "kge_gather_rows: unknown model");
   if (n == 0) return KGE_OK;
-  if (!ent0 || !idx || !out || (planes == 2 && !ent1))
+  if (!ent0 || !idx || !out || (planes >= 2 && !ent1))
     return fail(KGE_ERR_ARG, "kge_gather_rows: null pointer");
   DeviceScope device_scope(ent0);
   KGE_CUDA_TRY(kge::launch_gather_rows(ent0, ent1, planes, ent_lo, n_rows, dim, idx, n, out,
@@ -370,7 +370,7 @@ int kge_rank_side(const kge_rank_args_t* a) {
   const bool rel_side = a->side == KGE_SIDE_REL;
   if (!a->ent0 || (!a->rel0 && !rel_side) || !a->hrows || !a->trows || !a->raw_count || !a->workspace)
     return fail(KGE_ERR_ARG, "kge_rank_side: null pointer");
-  if (kge::elem_cw(el) == 2 && !a->ent1) return fail(KGE_ERR_ARG, "kge_rank_side: ent1 required");
+  if (kge::elem_cw(el) >= 2 && !a->ent1) return fail(KGE_ERR_ARG, "kge_rank_side: ent1 required");
   if (!rel_side && model_needs_rel1(a->model) && !a->rel1)
     return fail(KGE_ERR_ARG, "kge_rank_side: rel1 required");
   if (rel_side && !a->true_rows && !a->true_score_in)
@@ -515,7 +515,7 @@ int kge_filter_side(const kge_rank_args_t* a) {
   if (a->n == 0 || a->n_filt == 0 || a->n_rows == 0) return KGE_OK;
   if (!a->ent0 || !a->filt_offs || !a->filt_ids || !a->filt_sub || !a->workspace)
     return fail(KGE_ERR_ARG, "kge_filter_side: null pointer");
-  if (kge::elem_cw(el) == 2 && !a->ent1) return fail(KGE_ERR_ARG, "kge_filter_side: ent1 required");
+  if (kge::elem_cw(el) >= 2 && !a->ent1) return fail(KGE_ERR_ARG, "kge_filter_side: ent1 required");
   const HostSchedule* hs = get_schedule(a->model, a->dim);
   if (!hs) return fail(KGE_ERR_UNSUPPORTED, "kge_filter_side: unsupported dim");
   DeviceScope device_scope(a->ent0);
@@ -737,13 +737,13 @@ int kge_topk_dense(const float* scores, int64_t n, int64_t n_cand, int k, const 
 namespace {
 bool tables_ok(const kge_tables_t* tb) {
   if (!tb || !tb->ent0 || !tb->rel0 || tb->dim < 1) return false;
-  if (tb->model < KGE_TRANSE_L1 || tb->model > KGE_TORUSE_L2) return false;
-  if ((tb->model == KGE_COMPLEX || tb->model == KGE_ROTATE) && (!tb->ent1 || !tb->rel1)) return false;
+  if (tb->model < KGE_TRANSE_L1 || tb->model > KGE_ANALOGY) return false;
+  if (model_needs_rel1(tb->model) && (!tb->ent1 || !tb->rel1)) return false;
   return true;
 }
 bool grads_ok(const kge_tables_t* tb, const kge_grads_t* g) {
   if (!g || !g->ent0 || !g->rel0) return false;
-  if ((tb->model == KGE_COMPLEX || tb->model == KGE_ROTATE) && (!g->ent1 || !g->rel1)) return false;
+  if (model_needs_rel1(tb->model) && (!g->ent1 || !g->rel1)) return false;
   return true;
 }
 kge::TrainTables to_tables(const kge_tables_t* tb) {

@@ -18,6 +18,8 @@ int elem_kind_for(int model, int side) {
       case KGE_TRANSE_L2: return EL_L2_HEAD;
       case KGE_DISTMULT: return EL_DOT_MID;
       case KGE_COMPLEX: return EL_DOT2;
+      //   Analogy  (sc_c (sc_h sc_t) + re_c (re_h re_t + im_h im_t) + im_c (re_h im_t - im_h re_t)).sum   bilinear.py:709-712
+      case KGE_ANALOGY: return EL_DOT3;
       default: return -1;  // RESCAL (batched matmul in the reference) and RotatE: not on this path
     }
   }
@@ -31,6 +33,7 @@ int elem_kind_for(int model, int side) {
     case KGE_ROTATE: return EL_ROT;
     case KGE_TORUSE_L1: return tail ? EL_TL1_TAIL : EL_TL1_HEAD;
     case KGE_TORUSE_L2: return tail ? EL_TL2_TAIL : EL_TL2_HEAD;
+    case KGE_ANALOGY: return EL_DOT3;
     default: return -1;
   }
 }
@@ -38,11 +41,12 @@ int elem_kind_for(int model, int side) {
 int elem_qw(int el) {
   switch (el) {
     case EL_DOT1: case EL_L1_TAIL: case EL_L2_TAIL: case EL_TL1_TAIL: case EL_TL2_TAIL: return 1;
+    case EL_DOT3: return 3;
     default: return 2;
   }
 }
 
-int elem_cw(int el) { return (el == EL_DOT2 || el == EL_ROT) ? 2 : 1; }
+int elem_cw(int el) { return el == EL_DOT3 ? 3 : ((el == EL_DOT2 || el == EL_ROT) ? 2 : 1); }
 
 namespace {
 
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(256) pack_table_kernel(const float* __restrict
   const int k0 = blockIdx.y * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int pl = 0; pl < planes; ++pl) {
-    const float* ent = pl == 0 ? ent0 : ent1;
+    const float* ent = pl == 0 ? ent0 : (pl == 1 ? ent1 : third_plane(ent0, ent1));
     for (int r = warp; r < TILE_C; r += 8) {
       const long long row = ct * TILE_C + r;
       const int k = k0 + lane;
@@ -93,7 +97,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ ent0, const float* 
   const long long i = w / planes;
   const int pl = (int)(w - i * planes);
   const long long row = idx[i] - ent_lo;
-  const float* ent = pl == 0 ? ent0 : ent1;
+  const float* ent = pl == 0 ? ent0 : (pl == 1 ? ent1 : third_plane(ent0, ent1));
   float* dst = out + (size_t)w * dim;
   const bool own = row >= 0 && row < n_rows;
   for (int k = lane; k < dim; k += 32) dst[k] = own ? ent[(size_t)row * dim + k] : 0.f;
@@ -108,6 +112,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ ent0, const float* 
 //   ComplEx head q0 = re_r*re_t + im_r*im_t ; q1 = re_r*im_t - im_r*re_t   bilinear.py:521-522
 //   RotatE       same algebra as ComplEx with (rel0, rel1) = (cos, sin) of the phases:
 //                tail q = h o r ; head q = t o conj(r)
+//   Analogy      DistMult on the scalar plane, ComplEx on the (real, imaginary) planes  bilinear.py:694-706
 // Relation prediction (side = KGE_SIDE_REL, candidates = relation rows; rel0/rel1 unused):
 //   TransE / DistMult  q0 = h, q1 = t
 //   ComplEx  q0 = re_h*re_t + im_h*im_t ; q1 = re_h*im_t - im_h*re_t       bilinear.py:527-528
@@ -124,7 +129,16 @@ __global__ void prep_queries_kernel(int model, int side, int dim, long long n,
   const int k = (int)(gid - i * dim);
   const bool tail = side == KGE_SIDE_TAIL;
   if (side == KGE_SIDE_REL) {
-    if (model == KGE_COMPLEX) {
+    if (model == KGE_ANALOGY) {   // bilinear.py:709-712; planes (scalar, real, imaginary)
+      const float* hp = hrows + (size_t)i * 3 * dim + k;
+      const float* tp = trows + (size_t)i * 3 * dim + k;
+      const float sc_h = hp[0], re_h = hp[dim], im_h = hp[2 * dim];
+      const float sc_t = tp[0], re_t = tp[dim], im_t = tp[2 * dim];
+      float* q = qplain + (size_t)i * 3 * dim + k;
+      q[0] = __fmul_rn(sc_h, sc_t);
+      q[dim] = __fadd_rn(__fmul_rn(re_h, re_t), __fmul_rn(im_h, im_t));
+      q[2 * dim] = __fsub_rn(__fmul_rn(re_h, im_t), __fmul_rn(im_h, re_t));
+    } else if (model == KGE_COMPLEX) {
       const float re_h = hrows[((size_t)i * 2 + 0) * dim + k], im_h = hrows[((size_t)i * 2 + 1) * dim + k];
       const float re_t = trows[((size_t)i * 2 + 0) * dim + k], im_t = trows[((size_t)i * 2 + 1) * dim + k];
       qplain[((size_t)i * 2 + 0) * dim + k] = __fadd_rn(__fmul_rn(re_h, re_t), __fmul_rn(im_h, im_t));
@@ -174,6 +188,26 @@ __global__ void prep_queries_kernel(int model, int side, int dim, long long n,
       }
       qplain[((size_t)i * 2 + 0) * dim + k] = q0;
       qplain[((size_t)i * 2 + 1) * dim + k] = q1;
+      break;
+    }
+    case KGE_ANALOGY: {
+      // tail (bilinear.py:695-699): q = (sc_h sc_r, re_h re_r - im_h im_r, re_h im_r + im_h re_r)
+      // head (bilinear.py:702-706): q = (sc_r sc_t, re_r re_t + im_r im_t, re_r im_t - im_r re_t)
+      const float sc_r = rel0[(size_t)r * dim + k];
+      const float re_r = rel1[(size_t)r * dim + k];
+      const float im_r = third_plane(rel0, rel1)[(size_t)r * dim + k];
+      const float* ep = (tail ? hrows : trows) + (size_t)i * 3 * dim + k;
+      const float sc_e = ep[0], re_e = ep[dim], im_e = ep[2 * dim];
+      float* q = qplain + (size_t)i * 3 * dim + k;
+      if (tail) {
+        q[0] = __fmul_rn(sc_e, sc_r);
+        q[dim] = __fsub_rn(__fmul_rn(re_e, re_r), __fmul_rn(im_e, im_r));
+        q[2 * dim] = __fadd_rn(__fmul_rn(re_e, im_r), __fmul_rn(im_e, re_r));
+      } else {
+        q[0] = __fmul_rn(sc_r, sc_e);
+        q[dim] = __fadd_rn(__fmul_rn(re_r, re_e), __fmul_rn(im_r, im_e));
+        q[2 * dim] = __fsub_rn(__fmul_rn(re_r, im_e), __fmul_rn(im_r, re_e));
+      }
       break;
     }
     default: break;
@@ -267,12 +301,14 @@ __global__ void true_scores_kernel(int dim, long long n, const float* __restrict
   const float* q1 = q0 + (size_t)(QW - 1) * dim;
   const float* c0 = rows + (size_t)ii * CW * dim;
   const float* c1 = c0 + (size_t)(CW - 1) * dim;
+  const float* qm = q0 + (size_t)(QW / 2) * dim;   // middle plane (three-plane kinds)
+  const float* cm = c0 + (size_t)(CW / 2) * dim;
   float s;
   if constexpr (RED == RED_SEQ) {
     s = pair_score<EL, CASC>(dim, q0, q1, c0, c1, perm, code);
   } else {
-    if (RED == RED_SUM && dim < 8) s = pair_score_natural<EL>(dim, q0, q1, c0, c1);
-    else s = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane);
+    if (RED == RED_SUM && dim < 8) s = pair_score_natural<EL>(dim, q0, q1, c0, c1, qm, cm);
+    else s = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane, qm, cm);
   }
   if (valid && (lane % LANES) == 0) s_true[i] = s;
 }
@@ -321,13 +357,15 @@ __global__ void filter_kernel(int dim, long long n, long long n_filt,
     const float* q0 = qplain + (size_t)i * QW * dim;
     const float* q1 = q0 + (size_t)(QW - 1) * dim;
     const float* c0 = ent0 + (size_t)rr * dim;
-    const float* c1 = (CW == 2 ? ent1 : ent0) + (size_t)rr * dim;
+    const float* c1 = (CW == 3 ? third_plane(ent0, ent1) : (CW == 2 ? ent1 : ent0)) + (size_t)rr * dim;
+    const float* qm = q0 + (size_t)(QW / 2) * dim;   // middle plane (three-plane kinds)
+    const float* cm = (CW == 3 ? ent1 : ent0) + (size_t)rr * dim;
     float s;
     if constexpr (RED == RED_SEQ) {
       s = pair_score<EL, CASC>(dim, q0, q1, c0, c1, perm, code);
     } else {
-      if (small_sum) s = pair_score_natural<EL>(dim, q0, q1, c0, c1);
-      else s = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane);
+      if (small_sum) s = pair_score_natural<EL>(dim, q0, q1, c0, c1, qm, cm);
+      else s = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane, qm, cm);
     }
     const bool leader = (lane % LANES) == 0;
     if (held && leader) {
@@ -413,6 +451,7 @@ cudaError_t launch_fill_f32(float* dst, float value, int64_t n, cudaStream_t str
   switch (el) {                                                             \
     case EL_DOT1: if (cascade) { CALL(EL_DOT1, true); } else { CALL(EL_DOT1, false); } break; \
     case EL_DOT2: if (cascade) { CALL(EL_DOT2, true); } else { CALL(EL_DOT2, false); } break; \
+    case EL_DOT3: if (cascade) { CALL(EL_DOT3, true); } else { CALL(EL_DOT3, false); } break; \
     case EL_ROT: if (cascade) { CALL(EL_ROT, true); } else { CALL(EL_ROT, false); } break;    \
     case EL_DOT_MID: if (cascade) { CALL(EL_DOT_MID, true); } else { CALL(EL_DOT_MID, false); } break; \
     case EL_TL1_TAIL: if (cascade) { CALL(EL_TL1_TAIL, true); } else { CALL(EL_TL1_TAIL, false); } break; \

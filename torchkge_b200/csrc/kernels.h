@@ -11,6 +11,15 @@ namespace kge {
 constexpr int TILE_Q = KGE_TILE_Q;  // queries per CTA tile
 constexpr int TILE_C = KGE_TILE_C;  // candidates per CTA tile
 
+// Three-plane models (KGE_ANALOGY) hand over planes 0 and 1 of a table; the planes are equally
+// spaced in memory (include/kge_b200.h), so plane 2 follows from the two pointers.
+__host__ __device__ inline const float* third_plane(const float* p0, const float* p1) {
+  return p1 == nullptr ? nullptr : p1 + (p1 - p0);
+}
+__host__ __device__ inline float* third_plane(float* p0, float* p1) {
+  return p1 == nullptr ? nullptr : p1 + (p1 - p0);
+}
+
 // model/side -> element kind (-1 if unsupported)
 int elem_kind_for(int model, int side);
 int elem_qw(int el);

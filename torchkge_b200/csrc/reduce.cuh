@@ -27,7 +27,9 @@ enum ElemKind : int {
   EL_TL1_HEAD = 9,
   EL_TL2_TAIL = 10,  // 4*min(x^2, 1-x^2)         dissimilarities.py:37-43
   EL_TL2_HEAD = 11,
-  EL_COUNT = 12
+  // Analogy (bilinear.py:694-712), three planes (scalar, real, imaginary) of equal width:
+  EL_DOT3 = 12,      // (q0*c0 + qm*cm) + q1*c1   (qm / cm: the middle plane)
+  EL_COUNT = 13
 };
 
 template <int EL> struct ElemTraits;
@@ -43,18 +45,23 @@ template <> struct ElemTraits<EL_TL1_TAIL> { static constexpr int QW = 1, CW = 1
 template <> struct ElemTraits<EL_TL1_HEAD> { static constexpr int QW = 2, CW = 1, RED = RED_SUM; };
 template <> struct ElemTraits<EL_TL2_TAIL> { static constexpr int QW = 1, CW = 1, RED = RED_SUM; };
 template <> struct ElemTraits<EL_TL2_HEAD> { static constexpr int QW = 2, CW = 1, RED = RED_SUM; };
+template <> struct ElemTraits<EL_DOT3> { static constexpr int QW = 3, CW = 3, RED = RED_SUM; };
 
 // torch.min(a, b) element-wise: NaN propagates (ATen minimum), otherwise the smaller
 __device__ __forceinline__ float aten_min(float a, float b) { return (a != a || a < b) ? a : b; }
 
 // For the L2 kinds returns the difference x (the caller squares it, fused or not); for all
-// other kinds returns the finished term.
+// other kinds returns the finished term.  q0 / c0 = first plane, q1 / c1 = LAST plane, qm / cm =
+// middle plane (three-plane kinds only).
 template <int EL>
-__device__ __forceinline__ float elem_value(float q0, float q1, float c0, float c1) {
+__device__ __forceinline__ float elem_value(float q0, float q1, float c0, float c1, float qm = 0.f,
+                                            float cm = 0.f) {
   if constexpr (EL == EL_DOT1) {
     return __fmul_rn(q0, c0);
   } else if constexpr (EL == EL_DOT2) {
     return __fadd_rn(__fmul_rn(q0, c0), __fmul_rn(q1, c1));
+  } else if constexpr (EL == EL_DOT3) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(q0, c0), __fmul_rn(qm, cm)), __fmul_rn(q1, c1));
   } else if constexpr (EL == EL_L1_TAIL) {
     return fabsf(__fsub_rn(q0, c0));
   } else if constexpr (EL == EL_L1_HEAD) {
@@ -118,8 +125,9 @@ __device__ __forceinline__ void acc_reset(Acc& r) { r.a = r.a1 = r.p = r.t = 0.f
 
 // Fast path: position whose code is fast_code<EL>().
 template <int EL>
-__device__ __forceinline__ void acc_step_fast(Acc& r, float q0, float q1, float c0, float c1) {
-  float v = elem_value<EL>(q0, q1, c0, c1);
+__device__ __forceinline__ void acc_step_fast(Acc& r, float q0, float q1, float c0, float c1,
+                                              float qm = 0.f, float cm = 0.f) {
+  float v = elem_value<EL>(q0, q1, c0, c1, qm, cm);
   if constexpr (elem_is_l2<EL>()) v = __fmul_rn(v, v);
   if constexpr (ElemTraits<EL>::RED == RED_SEQ)
     r.t = __fadd_rn(r.t, v);
@@ -130,8 +138,8 @@ __device__ __forceinline__ void acc_step_fast(Acc& r, float q0, float q1, float 
 // General path for ONE pair (sparse pair scorer).  `code` is uniform across the warp there too.
 template <int EL, bool CASC>
 __device__ __forceinline__ void acc_step(Acc& r, uint8_t code, float q0, float q1, float c0,
-                                         float c1) {
-  const float v = elem_value<EL>(q0, q1, c0, c1);
+                                         float c1, float qm = 0.f, float cm = 0.f) {
+  const float v = elem_value<EL>(q0, q1, c0, c1, qm, cm);
   const uint8_t mode = code & SC_MODE_MASK;
   if constexpr (elem_is_l2<EL>()) {
     if (mode == SC_MODE_A)
@@ -161,8 +169,8 @@ __device__ __forceinline__ void acc_step(Acc& r, uint8_t code, float q0, float q
 // scan hoists the uniform tests out of its pair loops, so no per-pair selects are generated.
 template <int EL>
 __device__ __forceinline__ void acc_elem_mode(Acc& r, uint8_t mode, float q0, float q1, float c0,
-                                              float c1) {
-  const float v = elem_value<EL>(q0, q1, c0, c1);
+                                              float c1, float qm = 0.f, float cm = 0.f) {
+  const float v = elem_value<EL>(q0, q1, c0, c1, qm, cm);
   if constexpr (elem_is_l2<EL>()) {
     if (mode == SC_MODE_A)
       r.a = __fadd_rn(r.a, __fmul_rn(v, v));
@@ -189,7 +197,7 @@ __device__ __forceinline__ void acc_t_add_a(Acc& r) { r.t = __fadd_rn(r.t, r.a);
 // (dissimilarities.py:25 computes norm(p=2)**2; interfaces.py:254,260 negate).
 template <int EL>
 __device__ __forceinline__ float acc_finish(const Acc& r) {
-  if constexpr (EL == EL_DOT1 || EL == EL_DOT2 || EL == EL_DOT_MID) {
+  if constexpr (EL == EL_DOT1 || EL == EL_DOT2 || EL == EL_DOT3 || EL == EL_DOT_MID) {
     return r.t;
   } else if constexpr (elem_is_l2<EL>()) {
     const float n = __fsqrt_rn(r.t);
@@ -206,13 +214,19 @@ __device__ __forceinline__ float acc_finish(const Acc& r) {
 // accumulators live in registers (8 for the L2 norm, 32 (+32 cascade) for the cascade sum).
 template <int EL>
 __device__ __forceinline__ float elem_at(const float* q0, const float* q1, const float* c0,
-                                         const float* c1, int k) {
-  return elem_value<EL>(q0[k], q1[k], c0[k], c1[k]);
+                                         const float* c1, int k, const float* qm = nullptr,
+                                         const float* cm = nullptr) {
+  if constexpr (ElemTraits<EL>::CW == 3)
+    return elem_value<EL>(q0[k], q1[k], c0[k], c1[k], qm[k], cm[k]);
+  else
+    return elem_value<EL>(q0[k], q1[k], c0[k], c1[k]);
 }
 
 template <int EL>
 __device__ float pair_score_natural(int dim, const float* __restrict__ q0, const float* __restrict__ q1,
-                                    const float* __restrict__ c0, const float* __restrict__ c1) {
+                                    const float* __restrict__ c0, const float* __restrict__ c1,
+                                    const float* __restrict__ qm = nullptr,
+                                    const float* __restrict__ cm = nullptr) {
   if constexpr (ElemTraits<EL>::RED == RED_NORM2) {
     const int main_len = dim - dim % 8;
     float acc[8];
@@ -221,7 +235,7 @@ __device__ float pair_score_natural(int dim, const float* __restrict__ q0, const
     for (int k = 0; k < main_len; k += 8) {
 #pragma unroll
       for (int l = 0; l < 8; ++l) {
-        const float x = elem_at<EL>(q0, q1, c0, c1, k + l);
+        const float x = elem_at<EL>(q0, q1, c0, c1, k + l, qm, cm);
         acc[l] = __fadd_rn(acc[l], __fmul_rn(x, x));
       }
     }
@@ -234,12 +248,12 @@ __device__ float pair_score_natural(int dim, const float* __restrict__ q0, const
     for (; k + 4 <= dim; k += 4) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float x = elem_at<EL>(q0, q1, c0, c1, k + j);
+        const float x = elem_at<EL>(q0, q1, c0, c1, k + j, qm, cm);
         t = __fadd_rn(t, __fmul_rn(x, x));
       }
     }
     for (; k < dim; ++k) {
-      const float x = elem_at<EL>(q0, q1, c0, c1, k);
+      const float x = elem_at<EL>(q0, q1, c0, c1, k, qm, cm);
       t = __fmaf_rn(x, x, t);
     }
     Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
@@ -249,7 +263,7 @@ __device__ float pair_score_natural(int dim, const float* __restrict__ q0, const
     if (dim >= 8) {
       const int vec_size = dim / 8, rows = vec_size / 4;
       const bool casc = rows >= 16;
-      for (int k = vec_size * 8; k < dim; ++k) t = __fadd_rn(t, elem_at<EL>(q0, q1, c0, c1, k));
+      for (int k = vec_size * 8; k < dim; ++k) t = __fadd_rn(t, elem_at<EL>(q0, q1, c0, c1, k, qm, cm));
       float acc[4][8], acc1[4][8];
 #pragma unroll
       for (int m = 0; m < 4; ++m)
@@ -261,7 +275,7 @@ __device__ float pair_score_natural(int dim, const float* __restrict__ q0, const
         for (int m = 0; m < 4; ++m)
 #pragma unroll
           for (int l = 0; l < 8; ++l)
-            acc[m][l] = __fadd_rn(acc[m][l], elem_at<EL>(q0, q1, c0, c1, k0 + m * 8 + l));
+            acc[m][l] = __fadd_rn(acc[m][l], elem_at<EL>(q0, q1, c0, c1, k0 + m * 8 + l, qm, cm));
         if (((i + 1) & 15) == 0) {
 #pragma unroll
           for (int m = 0; m < 4; ++m)
@@ -277,7 +291,7 @@ __device__ float pair_score_natural(int dim, const float* __restrict__ q0, const
       }
       for (int j = rows * 4; j < vec_size; ++j) {
 #pragma unroll
-        for (int l = 0; l < 8; ++l) acc[0][l] = __fadd_rn(acc[0][l], elem_at<EL>(q0, q1, c0, c1, j * 8 + l));
+        for (int l = 0; l < 8; ++l) acc[0][l] = __fadd_rn(acc[0][l], elem_at<EL>(q0, q1, c0, c1, j * 8 + l, qm, cm));
       }
 #pragma unroll
       for (int l = 0; l < 8; ++l) {
@@ -293,9 +307,9 @@ __device__ float pair_score_natural(int dim, const float* __restrict__ q0, const
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int i = 0; i < rows; ++i) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m) acc[m] = __fadd_rn(acc[m], elem_at<EL>(q0, q1, c0, c1, i * 4 + m));
+        for (int m = 0; m < 4; ++m) acc[m] = __fadd_rn(acc[m], elem_at<EL>(q0, q1, c0, c1, i * 4 + m, qm, cm));
       }
-      for (int k = rows * 4; k < dim; ++k) acc[0] = __fadd_rn(acc[0], elem_at<EL>(q0, q1, c0, c1, k));
+      for (int k = rows * 4; k < dim; ++k) acc[0] = __fadd_rn(acc[0], elem_at<EL>(q0, q1, c0, c1, k, qm, cm));
       float pl = acc[0];
       if (rows > 0) {
 #pragma unroll
@@ -372,13 +386,15 @@ template <int EL>
 __device__ __forceinline__ float pair_score_chains(int dim, const float* __restrict__ q0,
                                                    const float* __restrict__ q1,
                                                    const float* __restrict__ c0,
-                                                   const float* __restrict__ c1, int lane) {
+                                                   const float* __restrict__ c1, int lane,
+                                                   const float* __restrict__ qm = nullptr,
+                                                   const float* __restrict__ cm = nullptr) {
   if constexpr (ElemTraits<EL>::RED == RED_NORM2) {
     const int l8 = lane & 7, g8 = lane & 24;  // lane of the norm, first lane of this pair's group
     const int main_len = dim - dim % 8;
     float acc = 0.f;
     for (int k = l8; k < main_len; k += 8) {
-      const float x = elem_at<EL>(q0, q1, c0, c1, k);
+      const float x = elem_at<EL>(q0, q1, c0, c1, k, qm, cm);
       acc = __fadd_rn(acc, __fmul_rn(x, x));
     }
     float t = 0.f;
@@ -391,12 +407,12 @@ __device__ __forceinline__ float pair_score_chains(int dim, const float* __restr
     for (; k + 4 <= dim; k += 4) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float x = elem_at<EL>(q0, q1, c0, c1, k + j);
+        const float x = elem_at<EL>(q0, q1, c0, c1, k + j, qm, cm);
         t = __fadd_rn(t, __fmul_rn(x, x));
       }
     }
     for (; k < dim; ++k) {
-      const float x = elem_at<EL>(q0, q1, c0, c1, k);
+      const float x = elem_at<EL>(q0, q1, c0, c1, k, qm, cm);
       t = __fmaf_rn(x, x, t);
     }
     Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;
@@ -405,12 +421,12 @@ __device__ __forceinline__ float pair_score_chains(int dim, const float* __restr
     const int vec_size = dim / 8, rows = vec_size / 4;
     float acc = 0.f, acc1 = 0.f;
     for (int i = 0; i < rows; ++i) {
-      acc = __fadd_rn(acc, elem_at<EL>(q0, q1, c0, c1, i * 32 + lane));
+      acc = __fadd_rn(acc, elem_at<EL>(q0, q1, c0, c1, i * 32 + lane, qm, cm));
       if (((i + 1) & 15) == 0) { acc1 = __fadd_rn(acc1, acc); acc = 0.f; }
     }
     if (rows >= 16) acc = __fadd_rn(acc, acc1);
     if (lane < 8)
-      for (int j = rows * 4; j < vec_size; ++j) acc = __fadd_rn(acc, elem_at<EL>(q0, q1, c0, c1, j * 8 + lane));
+      for (int j = rows * 4; j < vec_size; ++j) acc = __fadd_rn(acc, elem_at<EL>(q0, q1, c0, c1, j * 8 + lane, qm, cm));
     const int l = lane & 7;
     float pl = __shfl_sync(0xffffffffu, acc, l);
 #pragma unroll
@@ -419,7 +435,7 @@ __device__ __forceinline__ float pair_score_chains(int dim, const float* __restr
       if (rows > 0) pl = __fadd_rn(pl, v);
     }
     float t = 0.f;
-    for (int k = vec_size * 8; k < dim; ++k) t = __fadd_rn(t, elem_at<EL>(q0, q1, c0, c1, k));
+    for (int k = vec_size * 8; k < dim; ++k) t = __fadd_rn(t, elem_at<EL>(q0, q1, c0, c1, k, qm, cm));
 #pragma unroll
     for (int ll = 0; ll < 8; ++ll) t = __fadd_rn(t, __shfl_sync(0xffffffffu, pl, ll));
     Acc r; r.a = r.a1 = r.p = 0.f; r.t = t;

@@ -195,16 +195,16 @@ __global__ void __launch_bounds__(Cfg<EL, G>::THREADS, 1)
   _Pragma("unroll") for (int c = 0; c < TC; ++c) { stmt; }
       auto consume = [&](int kk, float (&qv)[QW][TQ], float (&cv)[CW][TC]) {
         if (!((special >> kk) & 1u)) {
-          KGE_FOR_PAIRS(acc_step_fast<EL>(acc[i][c], qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c]))
+          KGE_FOR_PAIRS(acc_step_fast<EL>(acc[i][c], qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c], qv[QW / 2][i], cv[CW / 2][c]))
         } else {
           const uint8_t code = p.code[kc * KC + kk];
           const uint8_t mode = code & SC_MODE_MASK;
           if (mode == SC_MODE_A) {
-            KGE_FOR_PAIRS(acc_elem_mode<EL>(acc[i][c], SC_MODE_A, qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c]))
+            KGE_FOR_PAIRS(acc_elem_mode<EL>(acc[i][c], SC_MODE_A, qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c], qv[QW / 2][i], cv[CW / 2][c]))
           } else if (mode == SC_MODE_T) {
-            KGE_FOR_PAIRS(acc_elem_mode<EL>(acc[i][c], SC_MODE_T, qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c]))
+            KGE_FOR_PAIRS(acc_elem_mode<EL>(acc[i][c], SC_MODE_T, qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c], qv[QW / 2][i], cv[CW / 2][c]))
           } else {
-            KGE_FOR_PAIRS(acc_elem_mode<EL>(acc[i][c], SC_MODE_T_FMA, qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c]))
+            KGE_FOR_PAIRS(acc_elem_mode<EL>(acc[i][c], SC_MODE_T_FMA, qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c], qv[QW / 2][i], cv[CW / 2][c]))
           }
           if constexpr (CASC) {
             if (code & SC_CASC1) { KGE_FOR_PAIRS(acc_casc1(acc[i][c])) }
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(Cfg<EL, G>::THREADS, 1)
           for (int j = 0; j < run; ++j) {
             float qv[QW][TQ], cv[CW][TC];
             load_operands(kk + j, qv, cv);
-            KGE_FOR_PAIRS(acc_step_fast<EL>(acc[i][c], qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c]))
+            KGE_FOR_PAIRS(acc_step_fast<EL>(acc[i][c], qv[0][i], qv[QW - 1][i], cv[0][c], cv[CW - 1][c], qv[QW / 2][i], cv[CW / 2][c]))
           }
           kk += run;
           if (kk < kn) {
@@ -369,6 +369,8 @@ cudaError_t launch_scan_g(int el, bool cascade, ScanParams& p, cudaStream_t stre
       return cascade ? launch_one<EL_DOT1, true, G>(p, stream) : launch_one<EL_DOT1, false, G>(p, stream);
     case EL_DOT2:
       return cascade ? launch_one<EL_DOT2, true, G>(p, stream) : launch_one<EL_DOT2, false, G>(p, stream);
+    case EL_DOT3:
+      return cascade ? launch_one<EL_DOT3, true, G>(p, stream) : launch_one<EL_DOT3, false, G>(p, stream);
     case EL_ROT:
       return cascade ? launch_one<EL_ROT, true, G>(p, stream) : launch_one<EL_ROT, false, G>(p, stream);
     case EL_DOT_MID:

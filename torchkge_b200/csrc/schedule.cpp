@@ -30,7 +30,8 @@ int reduce_kind_for_model(int model) {
     case KGE_COMPLEX:
     case KGE_ROTATE:
     case KGE_TORUSE_L1:
-    case KGE_TORUSE_L2: return RED_SUM;
+    case KGE_TORUSE_L2:
+    case KGE_ANALOGY: return RED_SUM;
     default: return -1;
   }
 }

@@ -78,6 +78,7 @@ struct RowPtrs {
   const float* h0; const float* h1;  // head planes
   const float* t0; const float* t1;  // tail planes
   const float* r0; const float* r1;  // relation planes (RESCAL: r0 = matrix)
+  const float* h2; const float* t2; const float* r2;  // third planes (Analogy) or nullptr
 };
 
 __device__ __forceinline__ float inv_norm_of(const float* row, int dim, int lane) {
@@ -143,6 +144,12 @@ __device__ float triple_score(int model, int dim, const RowPtrs& p, int lane, fl
         else { const float x2 = x * x; s += 4.f * fminf(x2, 1.f - x2); }
       }
       return -warp_sum(s);
+    case KGE_ANALOGY:   // bilinear.py:634-650: DistMult on the scalar plane + ComplEx on (real, imaginary)
+      for (int k = lane; k < dim; k += 32) {
+        const float rh = p.h1[k], ih = p.h2[k], rt = p.t1[k], it = p.t2[k], rr = p.r1[k], ir = p.r2[k];
+        s += p.h0[k] * p.r0[k] * p.t0[k] + (rh * (rr * rt + ir * it) + ih * (rr * it - ir * rt));
+      }
+      return warp_sum(s);
     default: return 0.f;
   }
 }
@@ -157,6 +164,13 @@ __device__ __forceinline__ RowPtrs make_rows(int model, int dim, const TrainTabl
   const size_t rstride = model == KGE_RESCAL ? (size_t)dim * dim : (size_t)dim;
   p.r0 = tb.rel0 + (size_t)r * rstride;
   p.r1 = tb.rel1 ? tb.rel1 + (size_t)r * rstride : nullptr;
+  p.h2 = p.t2 = p.r2 = nullptr;
+  if (model == KGE_ANALOGY) {   // planes equally spaced in memory (include/kge_b200.h)
+    const float* e2 = tb.ent1 + (tb.ent1 - tb.ent0);
+    p.h2 = e2 + (size_t)h * dim;
+    p.t2 = e2 + (size_t)t * dim;
+    p.r2 = tb.rel1 + (tb.rel1 - tb.rel0) + (size_t)r * dim;
+  }
   return p;
 }
 
@@ -191,6 +205,24 @@ __device__ void triple_backward(int model, int dim, const RowPtrs& p, const Trai
       atomicAdd(gh0 + k, g * d_rh); atomicAdd(gh1 + k, g * d_ih);
       atomicAdd(gt0 + k, g * d_rt); atomicAdd(gt1 + k, g * d_it);
       atomicAdd(gr0 + k, g * d_rr); atomicAdd(gr1 + k, g * d_ir);
+    }
+    return;
+  }
+  if (model == KGE_ANALOGY) {
+    float* gh1 = gr.ent1 + (size_t)h * dim;
+    float* gt1 = gr.ent1 + (size_t)t * dim;
+    float* gr1 = gr.rel1 + (size_t)r * dim;
+    float* ge2 = gr.ent1 + (gr.ent1 - gr.ent0);
+    float* gh2 = ge2 + (size_t)h * dim;
+    float* gt2 = ge2 + (size_t)t * dim;
+    float* gr2 = gr.rel1 + (gr.rel1 - gr.rel0) + (size_t)r * dim;
+    for (int k = lane; k < dim; k += 32) {
+      const float sh = p.h0[k], st = p.t0[k], sr = p.r0[k];
+      atomicAdd(gh0 + k, g * (sr * st)); atomicAdd(gt0 + k, g * (sh * sr)); atomicAdd(gr0 + k, g * (sh * st));
+      const float rh = p.h1[k], ih = p.h2[k], rt = p.t1[k], it = p.t2[k], rr = p.r1[k], ir = p.r2[k];
+      atomicAdd(gh1 + k, g * (rr * rt + ir * it)); atomicAdd(gh2 + k, g * (rr * it - ir * rt));
+      atomicAdd(gt1 + k, g * (rh * rr - ih * ir)); atomicAdd(gt2 + k, g * (rh * ir + ih * rr));
+      atomicAdd(gr1 + k, g * (rh * rt + ih * it)); atomicAdd(gr2 + k, g * (rh * it - ih * rt));
     }
     return;
   }

@@ -24,21 +24,38 @@ class ModelSpec:
     ``ent_emb.weight`` / ``rel_emb.weight`` (TransE models/translation.py:63-64, DistMult
     models/bilinear.py:183-184), ``ent_emb.weight`` / ``rel_mat.weight`` (RESCAL
     models/bilinear.py:55-56), ``re_/im_ent_emb.weight`` + ``re_/im_rel_emb.weight``
-    (ComplEx models/bilinear.py:455-458).
+    (ComplEx models/bilinear.py:455-458); Analogy (models/bilinear.py:623-631) has three planes per
+    table -- ``sc_/re_/im_ent_emb.weight``, ``sc_/re_/im_rel_emb.weight`` -- handed over as views of one
+    stacked (3, n, dim) copy (``stacked``): the C ABI takes planes 0 and 1 and finds plane 2 at the
+    same spacing (include/kge_b200.h, "three-plane tables").
     """
 
-    def __init__(self, code, dim, n_ent, n_rel, ent0, ent1, rel0, rel1, ent_lo=0):
+    def __init__(self, code, dim, n_ent, n_rel, ent0, ent1, rel0, rel1, ent_lo=0, ent2=None, rel2=None):
         self.code = code
         self.dim = int(dim)
         self.n_ent = int(n_ent)      # global number of entities
         self.n_rel = int(n_rel)
         self.ent0, self.ent1, self.rel0, self.rel1 = ent0, ent1, rel0, rel1
+        self.ent2, self.rel2 = ent2, rel2
         self.ent_lo = int(ent_lo)    # global id of row 0 of ent0/ent1
         self.n_rows = int(ent0.shape[0])
+        if code == _lib.ANALOGY:
+            for name, planes in (("entity", (ent0, ent1, ent2)), ("relation", (rel0, rel1, rel2))):
+                if planes[0] is None and name == "relation":
+                    continue         # relation prediction: the candidates are the relation rows
+                if any(x is None for x in planes) or not _equally_spaced(*planes):
+                    raise ValueError("Analogy %s planes must be equally spaced views of one stacked "
+                                     "tensor (ModelSpec.stacked)" % name)
 
     @property
     def cand_planes(self):
-        return 2 if self.code in (_lib.COMPLEX, _lib.ROTATE) else 1
+        return 3 if self.code == _lib.ANALOGY else (2 if self.code in (_lib.COMPLEX, _lib.ROTATE) else 1)
+
+    @staticmethod
+    def stacked(planes):
+        """[plane tensors (n, d)] -> the views (p0, p1, p2) of one contiguous (3, n, d) copy."""
+        s = torch.stack([ModelSpec._f32(x) for x in planes])
+        return s[0], s[1], s[2]
 
     def narrowed(self, lo, hi):
         """Same model restricted to entity rows [lo, hi) (views, no copy)."""
@@ -46,8 +63,9 @@ class ModelSpec:
         if a < 0 or b > self.n_rows:
             raise ValueError("shard [%d,%d) outside held rows" % (lo, hi))
         e1 = None if self.ent1 is None else self.ent1[a:b]
+        e2 = None if self.ent2 is None else self.ent2[a:b]
         return ModelSpec(self.code, self.dim, self.n_ent, self.n_rel, self.ent0[a:b], e1,
-                         self.rel0, self.rel1, ent_lo=lo)
+                         self.rel0, self.rel1, ent_lo=lo, ent2=e2, rel2=self.rel2)
 
     @staticmethod
     def _f32(t):
@@ -95,13 +113,29 @@ class ModelSpec:
             re_r, im_r = model.relation_planes()
             return cls(_lib.ROTATE, model.emb_dim, model.n_ent, model.n_rel,
                        f(model.re_ent_emb.weight), f(model.im_ent_emb.weight), f(re_r), f(im_r))
+        if name == "AnalogyModel":
+            if model.scalar_dim != model.complex_dim:
+                # the reference's own inference_scoring_function adds (b, n, scalar_dim) and
+                # (b, n, complex_dim) tensors (bilinear.py:695-698): it needs equal widths too
+                raise NotImplementedError("Analogy link prediction needs scalar_dim == complex_dim "
+                                          "(got %d and %d)" % (model.scalar_dim, model.complex_dim))
+            e = cls.stacked([model.sc_ent_emb.weight, model.re_ent_emb.weight, model.im_ent_emb.weight])
+            r = cls.stacked([model.sc_rel_emb.weight, model.re_rel_emb.weight, model.im_rel_emb.weight])
+            return cls(_lib.ANALOGY, model.scalar_dim, model.n_ent, model.n_rel, e[0], e[1], r[0], r[1],
+                       ent2=e[2], rel2=r[2])
         raise NotImplementedError(
             "%s has no CUDA link-prediction path (supported: TransE L1/L2, TorusE torus_L1/torus_L2, "
-            "DistMult, RESCAL, ComplEx, RotatE)" % name)
+            "DistMult, RESCAL, ComplEx, Analogy, RotatE)" % name)
 
 
 def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _equally_spaced(p0, p1, p2):
+    """planes of a three-plane table as the C ABI expects them: plane 2 at p1 + (p1 - p0)"""
+    return (p0.shape == p1.shape == p2.shape and p0.is_contiguous() and p1.is_contiguous() and p2.is_contiguous()
+            and p2.data_ptr() - p1.data_ptr() == p1.data_ptr() - p0.data_ptr())
 
 
 def _stream(device):
@@ -610,15 +644,18 @@ def relation_spec(spec):
     """The model seen from relation prediction: the candidate table is the RELATION table
     (``inference_prepare_candidates(..., entities=False)``: translation.py:118-121,
     bilinear.py:263-265, 551-554)."""
+    cand2 = None
     if spec.code in (_lib.TRANSE_L1, _lib.TRANSE_L2, _lib.DISTMULT):
         cand0, cand1 = spec.rel0, None
     elif spec.code == _lib.COMPLEX:
         cand0, cand1 = spec.rel0, spec.rel1
+    elif spec.code == _lib.ANALOGY:
+        cand0, cand1, cand2 = spec.rel0, spec.rel1, spec.rel2
     else:
         raise NotImplementedError(
-            "%s has no scan-based relation-prediction path (TransE L1/L2, DistMult, ComplEx have; RESCAL "
-            "goes through the dense kge_rescal_rel_scores)" % _lib.MODEL_NAMES.get(spec.code, spec.code))
-    return ModelSpec(spec.code, spec.dim, spec.n_rel, spec.n_rel, cand0, cand1, None, None)
+            "%s has no scan-based relation-prediction path (TransE L1/L2, DistMult, ComplEx, Analogy have; "
+            "RESCAL goes through the dense kge_rescal_rel_scores)" % _lib.MODEL_NAMES.get(spec.code, spec.code))
+    return ModelSpec(spec.code, spec.dim, spec.n_rel, spec.n_rel, cand0, cand1, None, None, ent2=cand2)
 
 
 def rank_relation_prediction(spec, h_idx, t_idx, r_idx, filt, directed=True, engine=None,

@@ -2,8 +2,8 @@
 and method signatures (torchkge/models/interfaces.py, translation.py:18-125,
 bilinear.py:14-267, 414-556), whose scoring bodies are calls into the CUDA engine.
 
-Only what lies on the hot path is here: TransE (L1 / L2), DistMult, RESCAL, ComplEx and the
-RotatE addition.  ``state_dict`` keys equal the reference's, so weights move freely between
+Only what lies on the hot path is here: TransE (L1 / L2), TorusE, DistMult, RESCAL, ComplEx, Analogy
+and the RotatE addition.  ``state_dict`` keys equal the reference's, so weights move freely between
 the two packages.  The pre-0.17 method names ``lp_prep_cands`` / ``lp_scoring_function``
 (docs/history.rst:37-42) are kept as aliases.
 """
@@ -138,8 +138,11 @@ def _dense_scores(model, h, t, r):
     if code == _lib.ROTATE:
         # inference_prepare_candidates hands out (cos, sin) planes for RotatE
         pass
+    if code == _lib.ANALOGY:    # three planes: equally spaced views of one stacked copy
+        tables, rel = list(ModelSpec.stacked(tables)), list(ModelSpec.stacked(rel))
     spec = ModelSpec(code, d, n_cand, b, tables[0], tables[1] if len(tables) > 1 else None,
-                     rel[0], rel[1] if len(rel) > 1 else None)
+                     rel[0], rel[1] if len(rel) > 1 else None,
+                     ent2=tables[2] if len(tables) > 2 else None, rel2=rel[2] if len(rel) > 2 else None)
     eng = default_engine()
     rows = torch.stack([x.detach().contiguous() for x in ent], dim=1).contiguous()  # (b, planes, d)
     with _device_guard(rows.device):
@@ -166,8 +169,12 @@ def _dense_relation_scores(model, hp, tp, rp):
     b, n_rel, d = rp[0].shape
     tables = [c[0].detach().contiguous() for c in rp]
     code = model._kernel_code()
-    rspec = relation_spec(ModelSpec(code, d, model.n_ent, n_rel, tables[0], None, tables[0],
-                                    tables[1] if len(tables) > 1 else None))
+    if code == _lib.ANALOGY:
+        cands = ModelSpec.stacked(tables)
+        rspec = ModelSpec(code, d, n_rel, n_rel, cands[0], cands[1], None, None, ent2=cands[2])
+    else:
+        rspec = relation_spec(ModelSpec(code, d, model.n_ent, n_rel, tables[0], None, tables[0],
+                                        tables[1] if len(tables) > 1 else None))
     eng = default_engine()
     hrows = torch.stack([x.detach().contiguous() for x in hp], dim=1).contiguous()  # (b, planes, d)
     trows = torch.stack([x.detach().contiguous() for x in tp], dim=1).contiguous()
@@ -348,6 +355,65 @@ class ComplExModel(BilinearModel):
             cands = (self._expand(self.re_ent_emb.weight, b), self._expand(self.im_ent_emb.weight, b))
         else:
             cands = (self._expand(self.re_rel_emb.weight, b), self._expand(self.im_rel_emb.weight, b))
+        return h, t, r, cands
+
+
+class AnalogyModel(BilinearModel):
+    """ANALOGY (Liu et al. 2017) -- torchkge/models/bilinear.py:559-763: DistMult on ``scalar_dim``
+    coordinates plus ComplEx on ``complex_dim`` coordinates (scalar_share of emb_dim, half by default).
+
+    Link prediction, relation prediction and top-k inference run on the scan kernels with the
+    three-plane element (csrc/reduce.cuh: EL_DOT3) and need scalar_dim == complex_dim -- as does the
+    reference's own ``inference_scoring_function``, which adds the (b, n, scalar_dim) and
+    (b, n, complex_dim) products element-wise (bilinear.py:695-698).  ``scoring_function`` runs on the
+    per-triple kernels of csrc/train.cu under the same condition and is composed from torch ops
+    otherwise.
+    """
+
+    def __init__(self, emb_dim, n_entities, n_relations, scalar_share=0.5):
+        super().__init__(emb_dim, n_entities, n_relations)
+        self.scalar_dim = int(self.emb_dim * scalar_share)
+        self.complex_dim = int((self.emb_dim - self.scalar_dim))
+        self.sc_ent_emb = init_embedding(self.n_ent, self.scalar_dim)
+        self.re_ent_emb = init_embedding(self.n_ent, self.complex_dim)
+        self.im_ent_emb = init_embedding(self.n_ent, self.complex_dim)
+        self.sc_rel_emb = init_embedding(self.n_rel, self.scalar_dim)
+        self.re_rel_emb = init_embedding(self.n_rel, self.complex_dim)
+        self.im_rel_emb = init_embedding(self.n_rel, self.complex_dim)
+
+    def scoring_function(self, h_idx, t_idx, r_idx):
+        """(sc_h * sc_r * sc_t).sum(1) + Re(<h, r, conj(t)>) on the complex part (bilinear.py:634-650)."""
+        if self.scalar_dim == self.complex_dim and self.sc_ent_emb.weight.is_cuda:
+            from .training import score_triples
+            return score_triples(self, h_idx, t_idx, r_idx)    # kge_score_triples_fwd / _bwd (train.cu)
+        sc_h, re_h, im_h = self.sc_ent_emb(h_idx), self.re_ent_emb(h_idx), self.im_ent_emb(h_idx)
+        sc_t, re_t, im_t = self.sc_ent_emb(t_idx), self.re_ent_emb(t_idx), self.im_ent_emb(t_idx)
+        sc_r, re_r, im_r = self.sc_rel_emb(r_idx), self.re_rel_emb(r_idx), self.im_rel_emb(r_idx)
+        return ((sc_h * sc_r * sc_t).sum(dim=1) +
+                (re_h * (re_r * re_t + im_r * im_t) + im_h * (re_r * im_t - im_r * re_t)).sum(dim=1))
+
+    def _kernel_code(self):
+        if self.scalar_dim != self.complex_dim:
+            raise NotImplementedError("Analogy on the CUDA path needs scalar_dim == complex_dim (got %d and %d)"
+                                      % (self.scalar_dim, self.complex_dim))
+        return _lib.ANALOGY
+
+    def normalize_parameters(self):
+        pass
+
+    def get_embeddings(self):
+        return (self.sc_ent_emb.weight.data, self.re_ent_emb.weight.data, self.im_ent_emb.weight.data,
+                self.sc_rel_emb.weight.data, self.re_rel_emb.weight.data, self.im_rel_emb.weight.data)
+
+    def inference_prepare_candidates(self, h_idx, t_idx, r_idx, entities=True):
+        b = h_idx.shape[0]
+        h = (self.sc_ent_emb(h_idx), self.re_ent_emb(h_idx), self.im_ent_emb(h_idx))
+        t = (self.sc_ent_emb(t_idx), self.re_ent_emb(t_idx), self.im_ent_emb(t_idx))
+        r = (self.sc_rel_emb(r_idx), self.re_rel_emb(r_idx), self.im_rel_emb(r_idx))
+        if entities:
+            cands = tuple(self._expand(e.weight, b) for e in (self.sc_ent_emb, self.re_ent_emb, self.im_ent_emb))
+        else:
+            cands = tuple(self._expand(e.weight, b) for e in (self.sc_rel_emb, self.re_rel_emb, self.im_rel_emb))
         return h, t, r, cands
 
 

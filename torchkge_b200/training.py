@@ -24,13 +24,32 @@ def _param_tensors(model, code):
     if code == _lib.ROTATE:
         ph = model.rel_emb.weight
         return model.re_ent_emb.weight, model.im_ent_emb.weight, torch.cos(ph), torch.sin(ph)
+    if code == _lib.ANALOGY:
+        # three planes per table: one stacked (3, n, dim) tensor in the ent0 / rel0 slot (autograd
+        # splits its gradient back onto the three embeddings); see _plane_ptrs
+        return (torch.stack([model.sc_ent_emb.weight, model.re_ent_emb.weight, model.im_ent_emb.weight]), None,
+                torch.stack([model.sc_rel_emb.weight, model.re_rel_emb.weight, model.im_rel_emb.weight]), None)
     raise NotImplementedError(code)
+
+
+def _kernel_dim(model, code):
+    """Width of one plane: emb_dim, or Analogy's scalar_dim (= complex_dim on this path)."""
+    return model.scalar_dim if code == _lib.ANALOGY else model.emb_dim
+
+
+def _plane_ptrs(x0, x1):
+    """(plane 0, plane 1) pointers of a table: a stacked (3, n, dim) tensor stands for three equally
+    spaced planes, of which the C ABI takes the first two (include/kge_b200.h, "three-plane tables")."""
+    if x0 is not None and x0.dim() == 3:
+        return _ptr(x0[0]), _ptr(x0[1])
+    return _ptr(x0), _ptr(x1)
 
 
 def _tables(code, dim, tensors):
     tb = _lib.Tables()
     tb.model, tb.dim = code, dim
-    tb.ent0, tb.ent1, tb.rel0, tb.rel1 = (_ptr(x) for x in tensors)
+    tb.ent0, tb.ent1 = _plane_ptrs(tensors[0], tensors[1])
+    tb.rel0, tb.rel1 = _plane_ptrs(tensors[2], tensors[3])
     return tb
 
 
@@ -48,7 +67,8 @@ def _idx(t, dev):
 def _zero_grads(tensors):
     gs = [None if x is None else torch.zeros_like(x, dtype=torch.float32) for x in tensors]
     g = _lib.Grads()
-    g.ent0, g.ent1, g.rel0, g.rel1 = (_ptr(x) for x in gs)
+    g.ent0, g.ent1 = _plane_ptrs(gs[0], gs[1])
+    g.rel0, g.rel1 = _plane_ptrs(gs[2], gs[3])
     return gs, g
 
 
@@ -95,6 +115,10 @@ def _training_code(model):
         if code is None:
             raise NotImplementedError("TorusE with dissimilarity %s has no training kernel" % dname)
         return code
+    if type(model).__name__ == "AnalogyModel":
+        if model.scalar_dim != model.complex_dim:
+            raise NotImplementedError("the Analogy training kernels need scalar_dim == complex_dim")
+        return _lib.ANALOGY
     return ModelSpec.from_model(model).code
 
 
@@ -103,7 +127,7 @@ def score_triples(model, h_idx, t_idx, r_idx):
     respect to the model's embedding tables."""
     code = _training_code(model)
     ent0, ent1, rel0, rel1 = _param_tensors(model, code)
-    return _ScoreTriples.apply(code, model.emb_dim, h_idx, t_idx, r_idx, ent0, ent1, rel0, rel1)
+    return _ScoreTriples.apply(code, _kernel_dim(model, code), h_idx, t_idx, r_idx, ent0, ent1, rel0, rel1)
 
 
 class _MarginLoss(torch.autograd.Function):
@@ -244,5 +268,5 @@ def fused_margin_step(model, heads, tails, relations, margin, n_neg=1, negatives
         n_neg = int(nh.shape[0] // heads.shape[0])
     elif bern_probs is None:
         raise ValueError("either negatives or bern_probs must be given")
-    return _MarginStep.apply(spec_code, model.emb_dim, model.n_ent, margin, n_neg, heads, tails,
+    return _MarginStep.apply(spec_code, _kernel_dim(model, spec_code), model.n_ent, margin, n_neg, heads, tails,
                              relations, nh, nt, bern_probs, seed, offset, ent0, ent1, rel0, rel1)
