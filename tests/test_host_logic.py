@@ -84,7 +84,8 @@ def test_model_spec_of_a_three_plane_model():
     lib = _lib.load()
     assert lib.kge_cand_planes(_lib.ANALOGY) == 3
     assert [lib.kge_query_planes(_lib.ANALOGY, side) for side in (0, 1, 2)] == [3, 3, 3]
-    assert lib.kge_tc_packed_bytes(_lib.ANALOGY, 1000, 64) == 0       # exact scalar scan only
+    # tensor-core image: one K = 3 x 64 contraction, the size of ComplEx's at 2 x 96
+    assert lib.kge_tc_packed_bytes(_lib.ANALOGY, 1000, 64) == lib.kge_tc_packed_bytes(_lib.COMPLEX, 1000, 96) > 0
     assert lib.kge_packed_table_floats(_lib.ANALOGY, 1000, 64) == 8 * 64 * 3 * 128
 
 

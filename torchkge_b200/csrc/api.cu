@@ -98,10 +98,11 @@ struct Workspace {
 };
 
 bool tc_supported(int el) {
-  return el == kge::EL_DOT1 || el == kge::EL_DOT2 || el == kge::EL_L2_TAIL || el == kge::EL_L2_HEAD;
+  return el == kge::EL_DOT1 || el == kge::EL_DOT2 || el == kge::EL_DOT3 || el == kge::EL_L2_TAIL ||
+         el == kge::EL_L2_HEAD;
 }
 bool tc_is_l2(int el) { return el == kge::EL_L2_TAIL || el == kge::EL_L2_HEAD; }
-// contraction length of the operand images: both planes for ComplEx; L2 carries the candidate's
+// contraction length of the operand images: all planes for ComplEx / Analogy; L2 carries the candidate's
 // squared norm in three extra k slots (tc.h: launch_pack_b)
 // bound-and-refine on the fp32 pipes (approximate element arithmetic + exact recheck): RotatE
 bool approx_supported(int el) { return el == kge::EL_ROT; }
@@ -123,7 +124,10 @@ struct TcImageLayout {
     total = meta + kge::tc::TC_META_BYTES;
   }
 };
-int tc_k_total(int el, int dim) { return el == kge::EL_DOT2 ? 2 * dim : (tc_is_l2(el) ? dim + 3 : dim); }
+int tc_k_total(int el, int dim) {
+  if (el == kge::EL_DOT3) return 3 * dim;   // all three planes of Analogy
+  return el == kge::EL_DOT2 ? 2 * dim : (tc_is_l2(el) ? dim + 3 : dim);
+}
 
 Workspace carve(void* base, int qw, int dim, int64_t n, int el = -1, int64_t n_rows = 0,
                 int flags = 0) {
@@ -344,7 +348,7 @@ int kge_tc_pack_table_cached(int model, const float* ent0, const float* ent1, in
   const int el = kge::elem_kind_for(model, KGE_SIDE_TAIL);
   if (el < 0 || !tc_supported(el)) return fail(KGE_ERR_UNSUPPORTED, "kge_tc_pack_table: model has no tensor-core path");
   if (n_rows <= 0) return KGE_OK;
-  if (!ent0 || !tc_packed || (kge::elem_cw(el) == 2 && !ent1))
+  if (!ent0 || !tc_packed || (kge::elem_cw(el) >= 2 && !ent1))
     return fail(KGE_ERR_ARG, "kge_tc_pack_table: null pointer");
   DeviceScope device_scope(ent0);
   const int k_total = tc_k_total(el, dim);

@@ -473,7 +473,11 @@ __device__ __forceinline__ float operand_value(const float* __restrict__ p0,
                                                const float* __restrict__ p1, int dim, int k,
                                                int k_total) {
   if (k >= k_total) return 0.f;
-  return k < dim ? p0[k] : p1[k - dim];
+  if (k < dim) return p0[k];
+  if (k < 2 * dim) return p1[k - dim];
+  // third plane of a three-plane row (Analogy: k_total = 3 dim): the planes are equally spaced, both in
+  // a query row ([3][dim], p1 = p0 + dim) and across the stacked candidate table (include/kge_b200.h)
+  return (p1 + (p1 - p0))[k - 2 * dim];
 }
 
 // Half-precision formats of the split: bf16 (8 significant bits) or fp16 (11; operands pre-scaled)
@@ -782,8 +786,10 @@ __global__ void recheck_kernel(int dim, const unsigned long long* __restrict__ r
       const int2 pr = list[i];
       const float* q0 = qplain + (size_t)pr.x * QW * dim;
       const float* c0 = ent0 + (size_t)pr.y * dim;
-      if (pair_score_natural<EL>(dim, q0, q0 + (size_t)(QW - 1) * dim, c0,
-                                 (CW == 2 ? ent1 : ent0) + (size_t)pr.y * dim) >= s_true[pr.x])
+      const float* c1 = (CW == 3 ? ent1 + (ent1 - ent0) : (CW == 2 ? ent1 : ent0)) + (size_t)pr.y * dim;
+      const float* cm = (CW == 3 ? ent1 : ent0) + (size_t)pr.y * dim;   // middle plane (three-plane kinds)
+      if (pair_score_natural<EL>(dim, q0, q0 + (size_t)(QW - 1) * dim, c0, c1, q0 + (size_t)(QW / 2) * dim, cm) >=
+          s_true[pr.x])
         atomicAdd(&counts[pr.x], 1);
     }
     return;
@@ -795,8 +801,10 @@ __global__ void recheck_kernel(int dim, const unsigned long long* __restrict__ r
     const float* q0 = qplain + (size_t)pr.x * QW * dim;
     const float* q1 = q0 + (size_t)(QW - 1) * dim;
     const float* c0 = ent0 + (size_t)pr.y * dim;
-    const float* c1 = (CW == 2 ? ent1 : ent0) + (size_t)pr.y * dim;
-    const float sc = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane);
+    const float* c1 = (CW == 3 ? ent1 + (ent1 - ent0) : (CW == 2 ? ent1 : ent0)) + (size_t)pr.y * dim;
+    const float* qm = q0 + (size_t)(QW / 2) * dim;                      // middle plane (three-plane kinds)
+    const float* cm = (CW == 3 ? ent1 : ent0) + (size_t)pr.y * dim;
+    const float sc = pair_score_chains<EL>(dim, q0, q1, c0, c1, lane, qm, cm);
     const bool leader = NORM ? ((lane & 7) == 0) : (lane == 0);
     if (valid && leader && sc >= s_true[pr.x]) atomicAdd(&counts[pr.x], 1);
   }
@@ -924,6 +932,7 @@ cudaError_t launch_pack_b(const float* ent0, const float* ent1, long long n_rows
     };
     checksum(ent0, 0ull);
     if (ent1) checksum(ent1, 0x5851F42D4C957F2Dull);
+    if (ent1 && !fold && k_total == 3 * dim) checksum(ent1 + (ent1 - ent0), 0x2545F4914F6CDD1Dull);   // third plane
     table_checksum_finish_kernel<<<1, 32, 0, st>>>(guard);
   }
   tc_meta_reset_kernel<<<1, 32, 0, st>>>(meta_b, guard);
@@ -1010,6 +1019,7 @@ cudaError_t launch_recheck(int el, int dim, const unsigned long long* region_cou
   switch (el) {
     case EL_DOT1: CALL_RC(EL_DOT1); break;
     case EL_DOT2: CALL_RC(EL_DOT2); break;
+    case EL_DOT3: CALL_RC(EL_DOT3); break;
     case EL_L2_TAIL: CALL_RC(EL_L2_TAIL); break;
     case EL_L2_HEAD: CALL_RC(EL_L2_HEAD); break;
     case EL_ROT: CALL_RC(EL_ROT); break;

@@ -221,7 +221,9 @@ class CudaEngine:
         if nbytes == 0:
             return None
         dev = spec.ent0.device
-        if self.tc_cache_entries <= 0:
+        # a three-plane spec reads a stacked COPY of the weights made for this call (ModelSpec.stacked):
+        # its address changes every time, so there is nothing to cache an image under
+        if self.tc_cache_entries <= 0 or getattr(spec, "ent2", None) is not None:
             out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             _lib.check(self.lib.kge_tc_pack_table(spec.code, _ptr(spec.ent0), _ptr(spec.ent1), spec.n_rows,
                                                   spec.dim, _ptr(out), _stream(dev)), "kge_tc_pack_table")
