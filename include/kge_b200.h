@@ -116,7 +116,7 @@ int kge_schedule_depth(int model, int dim);
  * Replaces the zero-copy `expand` of ent_emb.weight in inference_prepare_candidates
  * (translation.py:105-125, bilinear.py:123-143, 247-267, 530-556). */
 /* ---- tensor-core operand image of a table shard (optional, see kge_rank_args_t.flags) ----
- * For models whose score is a dot product or a squared L2 distance (DistMult, RESCAL, ComplEx,
+ * For models whose score is a dot product or a squared L2 distance (DistMult, RESCAL, ComplEx, Analogy,
  * TransE-L2) the dense scan can run as a split GEMM (x = hi + lo in bf16 or fp16, three MMAs per
  * fp32 product) on the tensor cores that decides
  * every (query, candidate) pair whose approximate score differs from the true score by more

@@ -362,7 +362,8 @@ class AnalogyModel(BilinearModel):
     """ANALOGY (Liu et al. 2017) -- torchkge/models/bilinear.py:559-763: DistMult on ``scalar_dim``
     coordinates plus ComplEx on ``complex_dim`` coordinates (scalar_share of emb_dim, half by default).
 
-    Link prediction, relation prediction and top-k inference run on the scan kernels with the
+    Link prediction (tensor-core bound-and-refine over the concatenated planes, or the exact scalar
+    scan), relation prediction and top-k inference run on the scan kernels with the
     three-plane element (csrc/reduce.cuh: EL_DOT3) and need scalar_dim == complex_dim -- as does the
     reference's own ``inference_scoring_function``, which adds the (b, n, scalar_dim) and
     (b, n, complex_dim) products element-wise (bilinear.py:695-698).  ``scoring_function`` runs on the
