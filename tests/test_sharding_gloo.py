@@ -17,7 +17,7 @@ from torchkge_b200.data import filter_csr
 from torchkge_b200.engine import EntityShard, ModelSpec, rank_link_prediction
 
 _KIND_OF_CODE = {_lib.TRANSE_L1: "transe_l1", _lib.TRANSE_L2: "transe_l2",
-                 _lib.DISTMULT: "distmult", _lib.COMPLEX: "complex"}
+                 _lib.DISTMULT: "distmult", _lib.COMPLEX: "complex", _lib.ANALOGY: "analogy"}
 
 
 class OracleEngine:
@@ -28,6 +28,7 @@ class OracleEngine:
 
     def gather_rows(self, spec, idx):
         planes = [spec.ent0] + ([spec.ent1] if spec.ent1 is not None else [])
+        planes += [spec.ent2] if getattr(spec, "ent2", None) is not None else []
         out = torch.zeros(idx.shape[0], len(planes), spec.dim)
         own = (idx >= spec.ent_lo) & (idx < spec.ent_lo + spec.n_rows)
         for p, tab in enumerate(planes):
@@ -41,6 +42,11 @@ class OracleEngine:
         # candidates = shard rows, then the n head rows, then the n tail rows
         if spec.ent1 is None:
             P = {"ent": torch.cat([spec.ent0, hrows[:, 0], trows[:, 0]]), "rel": spec.rel0}
+        elif kind == "analogy":     # three planes: scalar, real, imaginary
+            P = {"sc_ent": torch.cat([spec.ent0, hrows[:, 0], trows[:, 0]]),
+                 "re_ent": torch.cat([spec.ent1, hrows[:, 1], trows[:, 1]]),
+                 "im_ent": torch.cat([spec.ent2, hrows[:, 2], trows[:, 2]]),
+                 "sc_rel": spec.rel0, "re_rel": spec.rel1, "im_rel": spec.rel2}
         else:
             P = {"re_ent": torch.cat([spec.ent0, hrows[:, 0], trows[:, 0]]),
                  "im_ent": torch.cat([spec.ent1, hrows[:, 1], trows[:, 1]]),
@@ -104,7 +110,7 @@ def _worker(rank, world, port, kind, storage, ret):
 
 
 @pytest.mark.parametrize("kind,storage", [("distmult", "full"), ("transe_l2", "local"),
-                                          ("complex", "local")])
+                                          ("complex", "local"), ("analogy", "local")])
 def test_two_rank_sharded_ranking_equals_single_process(kind, storage):
     world = 2
     port = _free_port()
