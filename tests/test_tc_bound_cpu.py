@@ -68,6 +68,40 @@ def test_reference_sum_is_within_depth_times_u_of_the_real_dot(kind, d):
     assert (np.abs(ref - exact) <= bound).all(), float((np.abs(ref - exact) / bound).max())
 
 
+@pytest.mark.parametrize("planes", [2, 3])
+@pytest.mark.parametrize("kind", ["normalised", "cancelling", "wide"])
+@pytest.mark.parametrize("d", [7, 13, 100, 200, 520])
+def test_reference_multi_plane_sum_is_within_depth_times_u(planes, kind, d):
+    """ComplEx (`q0*c0 + q1*c1`, bilinear.py:514-515) and Analogy (`q0*c0 + qm*cm + q1*c1`,
+    bilinear.py:695-698) add their rounded products element-wise before the one sum over the last
+    axis: two resp. three rounded products and one resp. two rounded additions per element still fit
+    the `+ 4` of (depth + 4) u sum|products| -- the reference-side term of tc_gamma for the
+    concatenated K = planes * d contraction the tensor-core scan evaluates.  `cancelling` makes the
+    planes cancel each other (small element, large products)."""
+    lib = _lib.load()
+    model = _lib.COMPLEX if planes == 2 else _lib.ANALOGY
+    depth = lib.kge_schedule_depth(model, d)
+    assert depth >= 0
+    rng = np.random.default_rng(1000 * planes + d)
+    n = 300
+    a, b = _vectors(rng, n, planes * d, kind)
+    if kind == "cancelling":    # plane 1 against plane 0: nearly equal products of opposite sign
+        a[:, d:2 * d] = a[:, :d]
+        b[:, d:2 * d] = -b[:, :d] * np.float32(1 + 2 ** -12)
+    ta, tb = torch.from_numpy(a).view(n, planes, d), torch.from_numpy(b).view(n, planes, d)
+    q = [ta[:, p].view(n, 1, d) for p in range(planes)]
+    c = [tb[:, p].view(n, 1, d) for p in range(planes)]
+    if planes == 2:
+        ref = (q[0] * c[0] + q[1] * c[1]).sum(dim=2)
+    else:
+        ref = (q[0] * c[0] + q[1] * c[1] + q[2] * c[2]).sum(dim=2)
+    ref = ref.view(-1).double().numpy()
+    A, B = a.astype(np.float64), b.astype(np.float64)
+    exact = (A * B).sum(1)
+    bound = (depth + 4) * 2.0 ** -24 * (np.abs(A) * np.abs(B)).sum(1)
+    assert (np.abs(ref - exact) <= bound).all(), float((np.abs(ref - exact) / bound).max())
+
+
 @pytest.mark.parametrize("kind", ["normalised", "wide"])
 @pytest.mark.parametrize("d", [8, 50, 200, 203, 1000])
 def test_reference_l2_norm_is_within_depth_times_u(kind, d):
