@@ -162,9 +162,10 @@ def test_sampler_and_training_refuse_cpu_tensors():
     s = tk.BernoulliNegativeSampler(kg, seed=0)
     with pytest.raises(_lib.KgeLibraryError):
         s.corrupt_batch(h[:10], t[:10], r[:10])
-    m = tk.DistMultModel(8, 50, 3)
-    with pytest.raises(_lib.KgeLibraryError):
-        m.scoring_function(h[:10], t[:10], r[:10])
+    for m in (tk.DistMultModel(8, 50, 3), tk.AnalogyModel(8, 50, 3), tk.TorusEModel(8, 50, 3, "torus_L2"),
+              tk.ComplExModel(8, 50, 3)):
+        with pytest.raises(_lib.KgeLibraryError):      # no CPU execution path for a kernel configuration
+            m.scoring_function(h[:10], t[:10], r[:10])
 
 
 def test_filter_index_equals_dictionary_semantics():

@@ -384,9 +384,11 @@ class AnalogyModel(BilinearModel):
 
     def scoring_function(self, h_idx, t_idx, r_idx):
         """(sc_h * sc_r * sc_t).sum(1) + Re(<h, r, conj(t)>) on the complex part (bilinear.py:634-650)."""
-        if self.scalar_dim == self.complex_dim and self.sc_ent_emb.weight.is_cuda:
-            from .training import score_triples
-            return score_triples(self, h_idx, t_idx, r_idx)    # kge_score_triples_fwd / _bwd (train.cu)
+        if self.scalar_dim == self.complex_dim:
+            from .training import score_triples     # kge_score_triples_fwd / _bwd (train.cu); CPU tensors raise
+            return score_triples(self, h_idx, t_idx, r_idx)
+        # unequal widths (scalar_share != 0.5 or an odd emb_dim): not a kernel configuration; the
+        # reference's expression in torch ops on the model's device
         sc_h, re_h, im_h = self.sc_ent_emb(h_idx), self.re_ent_emb(h_idx), self.im_ent_emb(h_idx)
         sc_t, re_t, im_t = self.sc_ent_emb(t_idx), self.re_ent_emb(t_idx), self.im_ent_emb(t_idx)
         sc_r, re_r, im_r = self.sc_rel_emb(r_idx), self.re_rel_emb(r_idx), self.im_rel_emb(r_idx)
@@ -484,9 +486,10 @@ class TorusEModel(TranslationModel):
     def scoring_function(self, h_idx, t_idx, r_idx):
         """-dissimilarity(frac(h) + frac(r), frac(t)) (translation.py:706-720)."""
         self.normalized = False
-        if self.dissimilarity in (l1_torus_dissimilarity, l2_torus_dissimilarity) and self.ent_emb.weight.is_cuda:
-            from .training import score_triples
-            return score_triples(self, h_idx, t_idx, r_idx)    # kge_score_triples_fwd / _bwd (train.cu)
+        if self.dissimilarity in (l1_torus_dissimilarity, l2_torus_dissimilarity):
+            from .training import score_triples     # kge_score_triples_fwd / _bwd (train.cu); CPU tensors raise
+            return score_triples(self, h_idx, t_idx, r_idx)
+        # plain 'L1' on fractional parts: not a kernel configuration (the TransE-L1 kernels normalise rows)
         h, t, r = self.ent_emb(h_idx), self.ent_emb(t_idx), self.rel_emb(r_idx)
         h.data.frac_()
         t.data.frac_()
